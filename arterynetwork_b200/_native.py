@@ -1,0 +1,107 @@
+"""ctypes binding of include/vrg_b200.h.  There is no CPU fallback: if the CUDA
+library cannot be loaded, the compute entry points raise."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import _build
+
+i64 = ctypes.c_int64
+vp = ctypes.c_void_p
+
+OK = 0
+ERR_CUDA, ERR_ARG, ERR_LEVELS, ERR_LABEL, ERR_EMPTY_SEED, ERR_NO_BAND, ERR_NOMEM, ERR_NONFINITE = range(-1, -9, -1)
+EXIT_RUNNING, EXIT_CONVERGED, EXIT_MAX_TIME, EXIT_MAX_SEGMENT, EXIT_MAX_ITER = -1, 0, 1, 2, 3
+INTENSITY_F64_DENSE, INTENSITY_F64_BAND, INTENSITY_INDEX = 0, 1, 2
+INTENSITY_MODES = {"f64_dense": 0, "f64_band": 1, "index": 2}
+HALO = 2
+BUF_SEG0, BUF_SEG1, BUF_EXCL, BUF_LOCAL_STATS, BUF_GLOBAL_STATS, BUF_CTRL = range(6)
+ST_N_IN, ST_N_OUT, ST_N_EXCL, ST_N_FLIPS, ST_N_BAND, ST_BAD_LABEL, ST_NONFINITE, ST_EXTRA = 0, 1, 2, 3, 4, 5, 6, 8
+C_STATUS, C_ITER, C_ITER_MAX, C_MAX_SEG, C_APPLY, C_APPLIED, C_TRACE_N, C_SWEEPS = range(8)
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("shape", i64 * 3), ("z_begin", i64), ("z_end", i64), ("device", ctypes.c_int32),
+                ("intensity_mode", ctypes.c_int32), ("H", ctypes.c_double), ("iter_max", i64),
+                ("max_segment_size", i64), ("max_seconds", ctypes.c_double)]
+
+
+class Result(ctypes.Structure):
+    _fields_ = [("iterations", i64), ("exit_reason", i64), ("n_in", i64), ("n_out", i64), ("n_excluded", i64),
+                ("n_levels", i64), ("sweeps", i64), ("kernel_launches", i64)]
+
+
+_SIGS = {
+    "vrg_create": [ctypes.POINTER(Config), ctypes.POINTER(vp)],
+    "vrg_destroy": [vp],
+    "vrg_set_stream": [vp, vp],
+    "vrg_upload": [vp, vp, vp],
+    "vrg_upload_device": [vp, vp, vp],
+    "vrg_upload_value_map": [vp, vp],
+    "vrg_scan_levels": [vp, ctypes.POINTER(i64)],
+    "vrg_get_levels": [vp, vp, i64],
+    "vrg_set_levels": [vp, vp, i64],
+    "vrg_init": [vp],
+    "vrg_run": [vp, ctypes.POINTER(Result)],
+    "vrg_enqueue_decide": [vp],
+    "vrg_enqueue_apply": [vp],
+    "vrg_enqueue_absorb": [vp],
+    "vrg_enqueue_advance": [vp],
+    "vrg_poll": [vp, ctypes.POINTER(Result)],
+    "vrg_buffer_info": [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(i64)],
+    "vrg_plane_geometry": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)],
+    "vrg_use_separate_global_stats": [vp],
+    "vrg_download_labels": [vp, vp],
+    "vrg_download_segmented_map": [vp, vp],
+    "vrg_labels_device": [vp, vp],
+    "vrg_download_segmented": [vp, vp, i64, ctypes.POINTER(i64)],
+    "vrg_get_trace": [vp, vp, i64, ctypes.POINTER(i64)],
+    "vrg_get_table": [vp, vp, vp, i64],
+    "vrg_get_table_levels": [vp, vp, i64],
+    "vrg_phantom_device": [ctypes.c_int, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, ctypes.c_int, vp, vp],
+}
+EXPORTS = sorted(list(_SIGS) + ["vrg_last_error", "vrg_version"])
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Load libvrg_b200.so (building it first when nvcc is around).  Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.find_nvcc() is not None:
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError("vrg_b200: CUDA library %s is missing and cannot be built here (no nvcc); "
+                           "there is no CPU fallback" % _build.LIB)
+    lib = ctypes.CDLL(_build.LIB)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    lib.vrg_last_error.restype = ctypes.c_char_p
+    lib.vrg_version.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+class VRGError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("vrg_b200 error %d: %s" % (code, text))
+        self.code = code
+
+
+def check(rc: int):
+    if rc != OK:
+        text = load().vrg_last_error().decode("utf-8", "replace")
+        if rc in (ERR_ARG, ERR_LEVELS, ERR_LABEL, ERR_EMPTY_SEED, ERR_NO_BAND, ERR_NONFINITE):
+            raise ValueError("vrg_b200: " + text)
+        if rc == ERR_NOMEM:
+            raise MemoryError("vrg_b200: " + text)
+        raise VRGError(rc, text)

@@ -1,0 +1,568 @@
+// Host side of the C-ABI declared in include/vrg_b200.h (no torch types, no CPU fallback:
+// every compute entry point launches the sm_100a kernels in vrg_kernels.cuh or fails).
+#include "../../include/vrg_b200.h"
+#include "vrg_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace vrg;
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                   \
+    } while (0)
+
+struct vrg_handle {
+    vrg_config cfg;
+    Params p;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sms = 148;
+    int64_t nz_own = 0, ext_lo = 0, ext_hi = 0;  // extended slab in global z
+    size_t plane_bytes = 0;                      // one bit-plane buffer (all local planes)
+    double *d_data = nullptr;
+    uint8_t *d_vm = nullptr;
+    uint16_t *d_index = nullptr;
+    uint32_t *d_seg[2] = {nullptr, nullptr}, *d_excl = nullptr, *d_R = nullptr, *d_A0 = nullptr;
+    double *d_levels = nullptr, *d_pin = nullptr, *d_pout = nullptr;
+    uint32_t *d_dbits = nullptr;
+    long long *d_lstats = nullptr, *d_gstats = nullptr, *d_ctrl = nullptr, *d_trace = nullptr;
+    long long *h_ctrl = nullptr;  // pinned
+    unsigned long long *d_hash = nullptr;
+    int *d_hcount = nullptr;
+    std::vector<double> levels;  // table domain (lattice: every slot lev0 + k*step)
+    int64_t n_distinct = 0;
+    bool have_data = false, have_levels = false, inited = false, separate_gstats = false;
+    int64_t launches = 0;
+    int grid = 148 * 8;
+};
+
+static const int HASH_CAP = 1 << 18;
+
+const char *vrg_last_error(void) { return g_err.c_str(); }
+int vrg_version(void) { return 100; }
+
+static void free_levels(vrg_handle *h) {
+    cudaFree(h->d_levels); cudaFree(h->d_pin); cudaFree(h->d_pout); cudaFree(h->d_dbits);
+    cudaFree(h->d_lstats);
+    if (h->separate_gstats) cudaFree(h->d_gstats);
+    h->d_levels = h->d_pin = h->d_pout = nullptr; h->d_dbits = nullptr; h->d_lstats = h->d_gstats = nullptr;
+}
+
+int vrg_create(const vrg_config *cfg, vrg_handle **out) {
+    if (!cfg || !out) return fail(VRG_ERR_ARG, "null argument");
+    const int64_t Z = cfg->shape[0], Y = cfg->shape[1], X = cfg->shape[2];
+    if (Z <= 0 || Y <= 0 || X <= 0 || cfg->z_begin < 0 || cfg->z_end > Z || cfg->z_begin >= cfg->z_end)
+        return fail(VRG_ERR_ARG, "bad shape or slab [%lld,%lld) of Z=%lld", (long long)cfg->z_begin, (long long)cfg->z_end, (long long)Z);
+    if (Y > 0x7FFFFFF0 || X > 0x7FFFFFF0) return fail(VRG_ERR_ARG, "axis too long");
+    if (cfg->intensity_mode < 0 || cfg->intensity_mode > 2) return fail(VRG_ERR_ARG, "bad intensity_mode");
+    if (!(cfg->H > 0) || cfg->iter_max < 1) return fail(VRG_ERR_ARG, "bad H or iter_max");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(VRG_ERR_ARG, "device %d of %d", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+    vrg_handle *h = new vrg_handle();
+    h->cfg = *cfg;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sms = prop.multiProcessorCount;
+    h->grid = h->sms * 8;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    Params &p = h->p;
+    memset(&p, 0, sizeof p);
+    h->nz_own = cfg->z_end - cfg->z_begin;
+    p.Y = (int)Y; p.X = (int)X;
+    p.XW = (int)((X + 31) / 32);
+    p.WP = (p.XW + 3) & ~3;
+    p.nseg = (p.XW + WORDS_PER_WARP - 1) / WORDS_PER_WARP;
+    p.nzl = (int)h->nz_own + 2 * HALO;
+    p.own_lo = HALO; p.own_hi = HALO + (int)h->nz_own;
+    h->ext_lo = std::max<int64_t>(0, cfg->z_begin - HALO);
+    h->ext_hi = std::min<int64_t>(Z, cfg->z_end + HALO);
+    p.valid_lo = (int)(h->ext_lo - (cfg->z_begin - HALO));
+    p.valid_hi = (int)(h->ext_hi - (cfg->z_begin - HALO));
+    p.tail_mask = (X % 32) ? ((1u << (X % 32)) - 1u) : 0xFFFFFFFFu;
+    p.plane_words = (long long)Y * p.WP;
+    p.plane_vox = (long long)Y * X;
+    p.mhH = -0.5 * cfg->H;
+    h->plane_bytes = (size_t)p.nzl * p.plane_words * sizeof(uint32_t);
+    const size_t nvox = (size_t)p.nzl * p.plane_vox;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void **ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
+    alloc((void **)&h->d_data, nvox * sizeof(double));
+    alloc((void **)&h->d_vm, nvox);
+    for (int i = 0; i < 2; ++i) alloc((void **)&h->d_seg[i], h->plane_bytes);
+    alloc((void **)&h->d_excl, h->plane_bytes);
+    alloc((void **)&h->d_R, h->plane_bytes);
+    alloc((void **)&h->d_A0, h->plane_bytes);
+    alloc((void **)&h->d_ctrl, C_WORDS * sizeof(long long));
+    alloc((void **)&h->d_trace, 3 * (cfg->iter_max + 2) * sizeof(long long));
+    alloc((void **)&h->d_hash, (size_t)HASH_CAP * sizeof(unsigned long long));
+    alloc((void **)&h->d_hcount, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_ctrl, C_WORDS * sizeof(long long));
+    if (e != cudaSuccess) {
+        int code = fail(e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA, "allocation: %s", cudaGetErrorString(e));
+        vrg_destroy(h);
+        return code;
+    }
+    // planes outside the volume (and the y/x padding) must read as zero forever
+    CK(cudaMemsetAsync(h->d_data, 0, nvox * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_vm, 3, nvox, h->stream));
+    p.seg[0] = h->d_seg[0]; p.seg[1] = h->d_seg[1];
+    p.R = h->d_R; p.A0 = h->d_A0;
+    p.data = h->d_data;
+    p.ctrl = h->d_ctrl; p.trace = h->d_trace;
+    *out = h;
+    return VRG_OK;
+}
+
+int vrg_destroy(vrg_handle *h) {
+    if (!h) return VRG_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_data); cudaFree(h->d_vm); cudaFree(h->d_index);
+    cudaFree(h->d_seg[0]); cudaFree(h->d_seg[1]); cudaFree(h->d_excl); cudaFree(h->d_R); cudaFree(h->d_A0);
+    cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
+    free_levels(h);
+    if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return VRG_OK;
+}
+
+int vrg_set_stream(vrg_handle *h, void *s) {
+    if (!h) return fail(VRG_ERR_ARG, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    h->stream = (cudaStream_t)s;
+    return VRG_OK;
+}
+
+static int upload_impl(vrg_handle *h, const double *data, const uint8_t *vm, cudaMemcpyKind kind) {
+    if (!h) return fail(VRG_ERR_ARG, "null handle");
+    CK(cudaSetDevice(h->cfg.device));
+    const Params &p = h->p;
+    const size_t off = (size_t)p.valid_lo * p.plane_vox, n = (size_t)(p.valid_hi - p.valid_lo) * p.plane_vox;
+    if (data) {
+        CK(cudaMemcpyAsync(h->d_data + off, data, n * sizeof(double), kind, h->stream));
+        h->have_data = true;
+        h->have_levels = false;
+    }
+    if (vm) CK(cudaMemcpyAsync(h->d_vm + off, vm, n, kind, h->stream));
+    h->inited = false;
+    return VRG_OK;
+}
+int vrg_upload(vrg_handle *h, const double *d, const uint8_t *vm) {
+    if (!d || !vm) return fail(VRG_ERR_ARG, "null buffer");
+    int rc = upload_impl(h, d, vm, cudaMemcpyHostToDevice);
+    if (rc == VRG_OK) CK(cudaStreamSynchronize(h->stream));  // caller may free its pageable buffers
+    return rc;
+}
+int vrg_upload_device(vrg_handle *h, const double *d, const uint8_t *vm) {
+    if (!d && !vm) return fail(VRG_ERR_ARG, "null buffer");
+    return upload_impl(h, d, vm, cudaMemcpyDeviceToDevice);
+}
+int vrg_upload_value_map(vrg_handle *h, const uint8_t *vm) {
+    if (!vm) return fail(VRG_ERR_ARG, "null buffer");
+    int rc = upload_impl(h, nullptr, vm, cudaMemcpyHostToDevice);
+    if (rc == VRG_OK) CK(cudaStreamSynchronize(h->stream));
+    return rc;
+}
+
+// ---- levels -----------------------------------------------------------------------------------
+int vrg_scan_levels(vrg_handle *h, int64_t *n_levels) {
+    if (!h || !h->have_data) return fail(VRG_ERR_ARG, "upload data first");
+    CK(cudaSetDevice(h->cfg.device));
+    const Params &p = h->p;
+    CK(cudaMemsetAsync(h->d_hash, 0xFF, (size_t)HASH_CAP * sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->d_hcount, 0, 4 * sizeof(int), h->stream));
+    const long long n = (long long)(p.valid_hi - p.valid_lo) * p.plane_vox;
+    k_scan_levels<<<h->grid, BLOCK, 0, h->stream>>>(h->d_data + (size_t)p.valid_lo * p.plane_vox, n, h->d_hash, HASH_CAP - 1,
+                                                     h->d_hcount, VRG_MAX_LEVELS, h->d_hcount + 1);
+    h->launches++;
+    CK(cudaGetLastError());
+    int hc[4];
+    CK(cudaMemcpyAsync(hc, h->d_hcount, sizeof hc, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (hc[1]) return fail(VRG_ERR_NONFINITE, "intensity volume holds NaN or Inf");
+    if (hc[2] || hc[0] > VRG_MAX_LEVELS)
+        return fail(VRG_ERR_LEVELS, "more than %d distinct intensity levels: continuous data needs the brute-force Parzen path", VRG_MAX_LEVELS);
+    std::vector<unsigned long long> tab(HASH_CAP);
+    CK(cudaMemcpy(tab.data(), h->d_hash, tab.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    h->levels.clear();
+    for (unsigned long long k : tab)
+        if (k != HEMPTY) { double v; memcpy(&v, &k, 8); h->levels.push_back(v); }
+    std::sort(h->levels.begin(), h->levels.end());
+    h->n_distinct = (int64_t)h->levels.size();
+    if (n_levels) *n_levels = h->n_distinct;
+    return VRG_OK;
+}
+
+int vrg_get_levels(vrg_handle *h, double *out, int64_t cap) {
+    if (!h || !out) return fail(VRG_ERR_ARG, "null argument");
+    if ((int64_t)h->levels.size() > cap) return fail(VRG_ERR_ARG, "levels buffer too small");
+    memcpy(out, h->levels.data(), h->levels.size() * sizeof(double));
+    return VRG_OK;
+}
+
+int vrg_set_levels(vrg_handle *h, const double *lv, int64_t n) {
+    if (!h || !lv || n < 1) return fail(VRG_ERR_ARG, "bad levels");
+    if (n > VRG_MAX_LEVELS) return fail(VRG_ERR_LEVELS, "more than %d distinct intensity levels", VRG_MAX_LEVELS);
+    CK(cudaSetDevice(h->cfg.device));
+    std::vector<double> s(lv, lv + n);
+    std::sort(s.begin(), s.end());
+    s.erase(std::unique(s.begin(), s.end()), s.end());
+    n = (int64_t)s.size();
+    Params &p = h->p;
+    // lattice detection: every level sits on lev0 + k*step with k < 65536 -> O(1) voxel->level mapping
+    p.lattice = 0; p.lev0 = s[0]; p.inv_step = 0.0;
+    std::vector<double> table = s;
+    if (n >= 2) {
+        double step = s[1] - s[0];
+        for (int64_t i = 2; i < n; ++i) step = std::min(step, s[i] - s[i - 1]);
+        const double inv = 1.0 / step;
+        const double span = (s[n - 1] - s[0]) * inv;
+        bool ok = std::isfinite(inv) && span < (double)VRG_MAX_LEVELS - 0.5;
+        std::vector<int64_t> ks(n);
+        for (int64_t i = 0; ok && i < n; ++i) {
+            const double t = (s[i] - s[0]) * inv;
+            ks[i] = (int64_t)std::llrint(t);
+            if (std::fabs(t - (double)ks[i]) > 1e-6 || (i && ks[i] <= ks[i - 1])) ok = false;
+        }
+        if (ok) {
+            const int64_t K = ks[n - 1] + 1;
+            table.assign(K, 0.0);
+            for (int64_t k = 0; k < K; ++k) table[k] = s[0] + (double)k * step;
+            for (int64_t i = 0; i < n; ++i) table[ks[i]] = s[i];
+            p.lattice = 1; p.inv_step = inv;
+        }
+    } else {
+        p.lattice = 1; p.inv_step = 1.0;
+    }
+    h->levels = s;
+    h->n_distinct = n;
+    free_levels(h);
+    h->separate_gstats = false;
+    p.L = (int)table.size();
+    p.LW = (p.L + 31) / 32;
+    const size_t sb = (size_t)(2 * p.L + ST_EXTRA) * sizeof(long long);
+    CK(cudaMalloc((void **)&h->d_levels, p.L * sizeof(double)));
+    CK(cudaMalloc((void **)&h->d_pin, p.L * sizeof(double)));
+    CK(cudaMalloc((void **)&h->d_pout, p.L * sizeof(double)));
+    CK(cudaMalloc((void **)&h->d_dbits, p.LW * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&h->d_lstats, sb));
+    h->d_gstats = h->d_lstats;
+    CK(cudaMemcpyAsync(h->d_levels, table.data(), p.L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_pin, 0, p.L * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_pout, 0, p.L * sizeof(double), h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // `table` is a local
+    p.levels = h->d_levels; p.pin = h->d_pin; p.pout = h->d_pout; p.dbits = h->d_dbits;
+    p.lstats = h->d_lstats; p.gstats = h->d_gstats;
+    h->have_levels = true;
+    h->inited = false;
+    if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) {
+        const size_t nvox = (size_t)p.nzl * p.plane_vox;
+        if (!h->d_index) CK(cudaMalloc((void **)&h->d_index, nvox * sizeof(uint16_t)));
+        k_build_index<<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_data, h->d_index, (long long)nvox);
+        h->launches++;
+        CK(cudaGetLastError());
+        p.index = h->d_index;
+    }
+    return VRG_OK;
+}
+
+int vrg_use_separate_global_stats(vrg_handle *h) {
+    if (!h || !h->have_levels) return fail(VRG_ERR_ARG, "set levels first");
+    if (h->separate_gstats) return VRG_OK;
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t sb = (size_t)(2 * h->p.L + ST_EXTRA) * sizeof(long long);
+    CK(cudaMalloc((void **)&h->d_gstats, sb));
+    CK(cudaMemsetAsync(h->d_gstats, 0, sb, h->stream));
+    h->separate_gstats = true;
+    h->p.gstats = h->d_gstats;
+    return VRG_OK;
+}
+
+// ---- init -------------------------------------------------------------------------------------
+template <int MODE>
+static void launch_init_hist(vrg_handle *h) {
+    const Params &p = h->p;
+    const size_t smem = (size_t)2 * p.L * sizeof(unsigned int);
+    const int use_smem = smem <= 48 * 1024;
+    k_init_hist<MODE><<<h->grid, BLOCK, use_smem ? smem : 0, h->stream>>>(p, use_smem);
+}
+
+int vrg_init(vrg_handle *h) {
+    if (!h || !h->have_data) return fail(VRG_ERR_ARG, "upload first");
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->have_levels) {
+        int64_t n = 0;
+        int rc = vrg_scan_levels(h, &n);
+        if (rc != VRG_OK) return rc;
+        std::vector<double> lv = h->levels;
+        rc = vrg_set_levels(h, lv.data(), (int64_t)lv.size());
+        if (rc != VRG_OK) return rc;
+    }
+    Params &p = h->p;
+    for (int i = 0; i < 2; ++i) CK(cudaMemsetAsync(h->d_seg[i], 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_excl, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_R, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_A0, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_lstats, 0, (size_t)(2 * p.L + ST_EXTRA) * sizeof(long long), h->stream));
+    CK(cudaMemsetAsync(h->d_trace, 0, 3 * (h->cfg.iter_max + 2) * sizeof(long long), h->stream));
+    long long c[C_WORDS];
+    memset(c, 0, sizeof c);
+    c[C_STATUS] = RUNNING; c[C_ITER] = 1; c[C_ITER_MAX] = h->cfg.iter_max; c[C_MAX_SEG] = h->cfg.max_segment_size;
+    c[C_TRACE_N] = 1;
+    memcpy(h->h_ctrl, c, sizeof c);
+    CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    p.excl = h->d_excl;
+    k_init_planes<<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_vm, h->d_excl);
+    k_init_bands<<<h->grid, BLOCK, 0, h->stream>>>(p);
+    switch (h->cfg.intensity_mode) {
+        case VRG_INTENSITY_INDEX: launch_init_hist<MODE_INDEX>(h); break;
+        default: launch_init_hist<MODE_F64_BAND>(h); break;
+    }
+    h->launches += 3;
+    CK(cudaGetLastError());
+    // the init row of the trace and the error checks need the counters on the host
+    std::vector<long long> ex(ST_EXTRA);
+    CK(cudaMemcpyAsync(ex.data(), h->d_lstats + 2 * p.L, ST_EXTRA * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (ex[ST_BAD_LABEL]) return fail(VRG_ERR_LABEL, "initial valueMap may only hold labels 0 (seed), 3 (outside) and 4 (excluded)");
+    if (ex[ST_N_EXCL] == 0 && !h->separate_gstats) p.excl = nullptr;  // no label 4 anywhere: skip the absorb path
+    h->inited = true;
+    if (!h->separate_gstats) {  // single slab: the global view is the local one
+        if (ex[ST_N_IN] == 0) return fail(VRG_ERR_EMPTY_SEED, "no seed voxel (label 0) in valueMap");
+        if (ex[ST_N_BAND] == 0) return fail(VRG_ERR_NO_BAND, "seed has no boundary: every voxel is inside");
+        long long row[3] = {-1, ex[ST_N_IN], ex[ST_N_OUT]};
+        CK(cudaMemcpyAsync(h->d_trace, row, sizeof row, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return VRG_OK;
+}
+
+// ---- iteration ----------------------------------------------------------------------------------
+int vrg_enqueue_decide(vrg_handle *h) {
+    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
+    CK(cudaSetDevice(h->cfg.device));
+    const Params &p = h->p;
+    k_table<<<p.LW, BLOCK, 0, h->stream>>>(p);
+    const size_t smem = (size_t)p.LW * sizeof(uint32_t);
+    switch (h->cfg.intensity_mode) {
+        case VRG_INTENSITY_F64_DENSE: k_decide<MODE_F64_DENSE><<<h->grid, BLOCK, smem, h->stream>>>(p); break;
+        case VRG_INTENSITY_F64_BAND: k_decide<MODE_F64_BAND><<<h->grid, BLOCK, smem, h->stream>>>(p); break;
+        default: k_decide<MODE_INDEX><<<h->grid, BLOCK, smem, h->stream>>>(p); break;
+    }
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
+int vrg_enqueue_apply(vrg_handle *h) {
+    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) k_apply<MODE_INDEX><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    else k_apply<MODE_F64_BAND><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
+int vrg_enqueue_absorb(vrg_handle *h) {
+    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
+    if (!h->p.excl) return VRG_OK;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) k_absorb<MODE_INDEX><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    else k_absorb<MODE_F64_BAND><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
+int vrg_enqueue_advance(vrg_handle *h) {
+    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
+    CK(cudaSetDevice(h->cfg.device));
+    k_advance<<<1, 32, 0, h->stream>>>(h->p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
+
+int vrg_poll(vrg_handle *h, vrg_result *res) {
+    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
+    CK(cudaSetDevice(h->cfg.device));
+    long long ex[ST_EXTRA];
+    CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(ex, h->p.gstats + 2 * h->p.L, sizeof ex, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (res) {
+        res->iterations = h->h_ctrl[C_ITER];
+        res->exit_reason = h->h_ctrl[C_STATUS];
+        res->n_in = ex[ST_N_IN]; res->n_out = ex[ST_N_OUT]; res->n_excluded = ex[ST_N_EXCL];
+        res->n_levels = h->p.L;
+        res->sweeps = h->h_ctrl[C_SWEEPS];
+        res->kernel_launches = h->launches;
+    }
+    return VRG_OK;
+}
+
+int vrg_run(vrg_handle *h, vrg_result *res) {
+    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
+    vrg_result r;
+    const int check_every = 4;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (true) {
+        for (int k = 0; k < check_every; ++k) {
+            int rc;
+            if ((rc = vrg_enqueue_decide(h)) != VRG_OK) return rc;
+            if ((rc = vrg_enqueue_apply(h)) != VRG_OK) return rc;
+            if ((rc = vrg_enqueue_absorb(h)) != VRG_OK) return rc;
+            if ((rc = vrg_enqueue_advance(h)) != VRG_OK) return rc;
+        }
+        int rc = vrg_poll(h, &r);
+        if (rc != VRG_OK) return rc;
+        if (r.exit_reason != VRG_EXIT_RUNNING) break;
+        if (h->cfg.max_seconds > 0 &&
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= h->cfg.max_seconds) {
+            // VRG:97: stop before applying the next flips; the state is that of the last applied update
+            h->h_ctrl[C_STATUS] = VRG_EXIT_MAX_TIME;
+            CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            r.exit_reason = VRG_EXIT_MAX_TIME;
+            break;
+        }
+    }
+    if (res) *res = r;
+    return VRG_OK;
+}
+
+// ---- buffers for a multi-GPU host ------------------------------------------------------------------
+int vrg_buffer_info(vrg_handle *h, int which, void **ptr, int64_t *bytes) {
+    if (!h || !ptr || !bytes) return fail(VRG_ERR_ARG, "null argument");
+    const int64_t sb = (int64_t)(2 * h->p.L + ST_EXTRA) * sizeof(long long);
+    switch (which) {
+        case VRG_BUF_SEG0: *ptr = h->d_seg[0]; *bytes = (int64_t)h->plane_bytes; break;
+        case VRG_BUF_SEG1: *ptr = h->d_seg[1]; *bytes = (int64_t)h->plane_bytes; break;
+        case VRG_BUF_EXCL: *ptr = h->d_excl; *bytes = (int64_t)h->plane_bytes; break;
+        case VRG_BUF_LOCAL_STATS: *ptr = h->d_lstats; *bytes = sb; break;
+        case VRG_BUF_GLOBAL_STATS: *ptr = h->d_gstats; *bytes = sb; break;
+        case VRG_BUF_CTRL: *ptr = h->d_ctrl; *bytes = C_WORDS * sizeof(long long); break;
+        default: return fail(VRG_ERR_ARG, "unknown buffer %d", which);
+    }
+    return VRG_OK;
+}
+int vrg_plane_geometry(vrg_handle *h, int64_t *wpr, int64_t *wpp, int64_t *npl) {
+    if (!h) return fail(VRG_ERR_ARG, "null handle");
+    if (wpr) *wpr = h->p.WP;
+    if (wpp) *wpp = h->p.plane_words;
+    if (npl) *npl = h->p.nzl;
+    return VRG_OK;
+}
+
+// ---- outputs ----------------------------------------------------------------------------------------
+static int labels_impl(vrg_handle *h, uint8_t *dev_out, int seg_only) {
+    k_labels<<<h->grid, BLOCK, 0, h->stream>>>(h->p, dev_out, seg_only);
+    h->launches++;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
+int vrg_labels_device(vrg_handle *h, uint8_t *out) {
+    if (!h || !h->inited || !out) return fail(VRG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->cfg.device));
+    return labels_impl(h, out, 0);
+}
+static int download_impl(vrg_handle *h, uint8_t *out, int seg_only) {
+    if (!h || !h->inited || !out) return fail(VRG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->cfg.device));
+    // d_vm's own planes are free to hold the materialised labels: the seeds were consumed by vrg_init
+    const size_t n = (size_t)h->nz_own * h->p.plane_vox;
+    uint8_t *tmp = nullptr;
+    CK(cudaMalloc((void **)&tmp, n));
+    int rc = labels_impl(h, tmp, seg_only);
+    if (rc == VRG_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, tmp, n, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(VRG_ERR_CUDA, "download: %s", cudaGetErrorString(e));
+    }
+    cudaFree(tmp);
+    return rc;
+}
+int vrg_download_labels(vrg_handle *h, uint8_t *out) { return download_impl(h, out, 0); }
+int vrg_download_segmented_map(vrg_handle *h, uint8_t *out) { return download_impl(h, out, 1); }
+
+int vrg_download_segmented(vrg_handle *h, int64_t *coords, int64_t cap, int64_t *n_out) {
+    if (!h || !h->inited || !n_out) return fail(VRG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->cfg.device));
+    const Params &p = h->p;
+    CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const int par = (int)(h->h_ctrl[C_APPLIED] & 1);
+    const size_t words = (size_t)h->nz_own * p.plane_words;
+    std::vector<uint32_t> plane(words);
+    CK(cudaMemcpy(plane.data(), h->d_seg[par] + (size_t)p.own_lo * p.plane_words, words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    int64_t n = 0;
+    for (int64_t zl = 0; zl < h->nz_own; ++zl)
+        for (int64_t y = 0; y < p.Y; ++y) {
+            const uint32_t *row = plane.data() + (size_t)zl * p.plane_words + (size_t)y * p.WP;
+            for (int c = 0; c < p.XW; ++c) {
+                uint32_t w = row[c];
+                while (w) {
+                    const int b = __builtin_ctz(w); w &= w - 1;
+                    if (coords && n < cap) { coords[3 * n] = h->cfg.z_begin + zl; coords[3 * n + 1] = y; coords[3 * n + 2] = (int64_t)c * 32 + b; }
+                    ++n;
+                }
+            }
+        }
+    *n_out = n;
+    return VRG_OK;
+}
+
+int vrg_get_trace(vrg_handle *h, int64_t *rows, int64_t cap, int64_t *n_rows) {
+    if (!h || !h->inited || !n_rows) return fail(VRG_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const int64_t n = h->h_ctrl[C_TRACE_N];
+    *n_rows = n;
+    if (rows) CK(cudaMemcpy(rows, h->d_trace, (size_t)std::min(n, cap) * 3 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return VRG_OK;
+}
+
+int vrg_get_table(vrg_handle *h, double *pin, double *pout, int64_t cap) {
+    if (!h || !h->have_levels) return fail(VRG_ERR_ARG, "no table yet");
+    if (cap < h->p.L) return fail(VRG_ERR_ARG, "table buffer too small (%d levels)", h->p.L);
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (pin) CK(cudaMemcpy(pin, h->d_pin, h->p.L * sizeof(double), cudaMemcpyDeviceToHost));
+    if (pout) CK(cudaMemcpy(pout, h->d_pout, h->p.L * sizeof(double), cudaMemcpyDeviceToHost));
+    return VRG_OK;
+}
+
+// table-domain levels (lattice: every slot), for hosts that want to index vrg_get_table
+extern "C" int vrg_get_table_levels(vrg_handle *h, double *out, int64_t cap) {
+    if (!h || !h->have_levels || !out) return fail(VRG_ERR_ARG, "no table yet");
+    if (cap < h->p.L) return fail(VRG_ERR_ARG, "buffer too small");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpy(out, h->d_levels, h->p.L * sizeof(double), cudaMemcpyDeviceToHost));
+    return VRG_OK;
+}

@@ -1,0 +1,150 @@
+/* vrg_b200 -- C-ABI of the B200-native variational region growing (VRG) path.
+ *
+ * Drop-in boundary for ONE function of zjx1805/ArteryNetwork:
+ *   Code/variationalRegionGrowing.py:10  variationalRegionGrowing(dataArray, valueMap, H, maxSegmentSize)
+ *   Code/variationalRegionGrowing.py:124 update(...)            (init branch + band state machine)
+ * The reference has no FFI of its own (it is pure Python); these entry points are
+ * what a ctypes binding of that function binds.  Plain C
+ * types only; the caller owns every host buffer, the handle owns device memory.
+ * One handle serves one host thread and one CUDA device.  Every call returns
+ * VRG_OK or a negative vrg_status and never aborts; vrg_last_error() gives text.
+ *
+ * Volume layout: (Z, Y, X) with X fastest -- a C-ordered ndarray of shape
+ * (Z, Y, X).  A handle owns planes [z_begin, z_end) of the global volume (the
+ * whole volume on one GPU; one z-slab per GPU otherwise) plus VRG_HALO halo
+ * planes on each side, which the caller fills from the neighbouring slabs.
+ */
+#ifndef VRG_B200_H
+#define VRG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRG_HALO 2 /* halo planes per side: cancel rule + re-classification need radius 2 */
+
+typedef enum {
+    VRG_OK = 0,
+    VRG_ERR_CUDA = -1,       /* a CUDA call failed (text in vrg_last_error) */
+    VRG_ERR_ARG = -2,        /* bad argument / call order */
+    VRG_ERR_LEVELS = -3,     /* more than VRG_MAX_LEVELS distinct intensities (continuous data) */
+    VRG_ERR_LABEL = -4,      /* initial valueMap holds a label other than 0, 3, 4 */
+    VRG_ERR_EMPTY_SEED = -5, /* no voxel with label 0 (reference: IndexError at VRG:88) */
+    VRG_ERR_NO_BAND = -6,    /* seed has no boundary (reference: IndexError at VRG:88) */
+    VRG_ERR_NOMEM = -7,
+    VRG_ERR_NONFINITE = -8   /* NaN/Inf intensity */
+} vrg_status;
+
+/* why the iteration stopped: the four exits of VRG:91-104,118-121 */
+typedef enum {
+    VRG_EXIT_RUNNING = -1,
+    VRG_EXIT_CONVERGED = 0,   /* no voxel flipped                         VRG:91  */
+    VRG_EXIT_MAX_TIME = 1,    /* wall-clock budget reached (opt-in)       VRG:97  */
+    VRG_EXIT_MAX_SEGMENT = 2, /* len(segmented) >= maxSegmentSize         VRG:101 */
+    VRG_EXIT_MAX_ITER = 3     /* iterMax = 200 updates applied            VRG:56,118 */
+} vrg_exit;
+
+/* how the per-iteration decide kernel reads intensities */
+typedef enum {
+    VRG_INTENSITY_F64_DENSE = 0, /* stream the fp64 volume, every voxel, every iteration (reference dtype) */
+    VRG_INTENSITY_F64_BAND = 1,  /* fp64 volume, but only 32-voxel words that hold a band voxel */
+    VRG_INTENSITY_INDEX = 2      /* uint16 level-index volume built once; band words only */
+} vrg_intensity_mode;
+
+#define VRG_MAX_LEVELS 65536
+
+typedef struct {
+    int64_t shape[3];       /* global volume (Z, Y, X) */
+    int64_t z_begin, z_end; /* planes owned by this handle; 0, Z on a single GPU */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t intensity_mode; /* vrg_intensity_mode */
+    double H;               /* Parzen kernel precision, VRG:10,23 (default 2.25) */
+    int64_t iter_max;       /* VRG:56 (200) */
+    int64_t max_segment_size; /* VRG:10,101 (5000) */
+    double max_seconds;     /* VRG:97 wall-clock exit (reference: 120 s); <= 0 disables it (parity runs) */
+} vrg_config;
+
+typedef struct vrg_handle vrg_handle;
+
+typedef struct {
+    int64_t iterations;  /* the number the reference prints, VRG:94 */
+    int64_t exit_reason; /* vrg_exit */
+    int64_t n_in;        /* #(valueMap in {0,1}) == len(segmented), VRG:49,113 */
+    int64_t n_out;       /* #(valueMap in {2,3}), VRG:50,114 */
+    int64_t n_excluded;  /* #(valueMap == 4) */
+    int64_t n_levels;    /* size of the decision table */
+    int64_t sweeps;      /* decide passes executed == iterations (voxel-updates = N * sweeps) */
+    int64_t kernel_launches;
+} vrg_result;
+
+const char *vrg_last_error(void);
+int vrg_version(void);
+
+/* lifetime ---------------------------------------------------------------- */
+int vrg_create(const vrg_config *cfg, vrg_handle **out);
+int vrg_destroy(vrg_handle *h);
+/* run every kernel on this CUDA stream (a cudaStream_t passed as void*); default: a stream the handle owns */
+int vrg_set_stream(vrg_handle *h, void *cuda_stream);
+
+/* inputs: replaces reading dataArray / valueMap, VRG:40-46 ------------------ */
+/* Extended slab = planes [max(0, z_begin-VRG_HALO), min(Z, z_end+VRG_HALO)); the pointers address its first plane.
+ * data: float64 intensities; value_map: uint8 labels (0 seed, 3 outside, 4 excluded). */
+int vrg_upload(vrg_handle *h, const double *data_host, const uint8_t *value_map_host);
+int vrg_upload_device(vrg_handle *h, const double *data_dev, const uint8_t *value_map_dev);
+int vrg_upload_value_map(vrg_handle *h, const uint8_t *value_map_host); /* new seeds, same data */
+
+/* distinct intensity levels (the decision table's domain) ------------------- */
+int vrg_scan_levels(vrg_handle *h, int64_t *n_levels);             /* local slab */
+int vrg_get_levels(vrg_handle *h, double *levels_out, int64_t cap); /* sorted */
+int vrg_set_levels(vrg_handle *h, const double *levels, int64_t n); /* union over all slabs (multi-GPU) */
+
+/* init branch of update(), VRG:129-155: seeds, 4->3 around seeds, bands, region histograms */
+int vrg_init(vrg_handle *h);
+
+/* iteration loop, VRG:58-117.  vrg_run drives one GPU to an exit; the three
+ * enqueue calls are the same kernels for a host that interleaves the slab halo
+ * exchange and the statistics all-reduce between them (multi-GPU). */
+int vrg_run(vrg_handle *h, vrg_result *res);
+int vrg_enqueue_decide(vrg_handle *h);  /* decision table + flip flags (VRG:79-88) */
+int vrg_enqueue_apply(vrg_handle *h);   /* flips, cancel rule, region statistics (VRG:165-233) */
+int vrg_enqueue_absorb(vrg_handle *h);  /* 4->3 absorption (VRG:167-168,177-179); no-op without label 4 */
+int vrg_enqueue_advance(vrg_handle *h); /* exit tests + trace row (VRG:91-117) */
+int vrg_poll(vrg_handle *h, vrg_result *res); /* synchronises the stream */
+
+/* device buffers a multi-GPU host exchanges between the enqueue calls ------- */
+typedef enum {
+    VRG_BUF_SEG0 = 0,     /* segmented bit-plane, ping */
+    VRG_BUF_SEG1 = 1,     /* segmented bit-plane, pong */
+    VRG_BUF_EXCL = 2,     /* excluded (label 4) bit-plane */
+    VRG_BUF_LOCAL_STATS = 3,  /* int64[2*n_levels + 8]: this slab's histograms and counters */
+    VRG_BUF_GLOBAL_STATS = 4, /* same layout, summed over slabs (aliases LOCAL on one GPU) */
+    VRG_BUF_CTRL = 5
+} vrg_buffer;
+int vrg_buffer_info(vrg_handle *h, int which, void **dev_ptr, int64_t *bytes);
+/* bit-plane geometry: words (uint32, 32 voxels along x) per row and rows*words per plane */
+int vrg_plane_geometry(vrg_handle *h, int64_t *words_per_row, int64_t *words_per_plane, int64_t *n_planes_local);
+int vrg_use_separate_global_stats(vrg_handle *h); /* multi-GPU: un-alias GLOBAL from LOCAL */
+
+/* outputs: the return values of VRG:96 -------------------------------------- */
+int vrg_download_labels(vrg_handle *h, uint8_t *value_map_out);   /* own planes, canonical labels 0..4 */
+int vrg_download_segmented_map(vrg_handle *h, uint8_t *seg_out);  /* own planes, 0/1 */
+int vrg_labels_device(vrg_handle *h, uint8_t *value_map_dev_out); /* same, into a device buffer */
+/* segmented voxel coordinates (z,y,x) of own planes in C order; returns count via n (cap in rows) */
+int vrg_download_segmented(vrg_handle *h, int64_t *coords_out, int64_t cap, int64_t *n);
+int vrg_get_trace(vrg_handle *h, int64_t *rows_out, int64_t cap_rows, int64_t *n_rows); /* (n_flips,n_in,n_out) */
+/* last decision table: in/out normalised Parzen sums per level (VRG:79-82), for parity checks */
+int vrg_get_table(vrg_handle *h, double *pin_out, double *pout_out, int64_t cap);
+int vrg_get_table_levels(vrg_handle *h, double *levels_out, int64_t cap); /* the table's level of each slot */
+
+/* synthetic phantom generated on the device (bench configs that exceed host RAM) */
+int vrg_phantom_device(int device, const int64_t *shape, int64_t z0, int64_t nz, const int64_t *segments,
+                       int64_t n_segments, const int64_t *roots, int64_t n_roots, int64_t seed, int64_t quantum,
+                       int64_t sigma_k, int64_t exclude_below_k, int use_exclude, double *data_dev,
+                       uint8_t *value_map_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
