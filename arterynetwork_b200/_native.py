@@ -49,6 +49,8 @@ _SIGS = {
     "vrg_enqueue_absorb": [vp],
     "vrg_enqueue_advance": [vp],
     "vrg_poll": [vp, ctypes.POINTER(Result)],
+    "vrg_profile": [vp, ctypes.c_int],
+    "vrg_get_profile": [vp, vp, vp],
     "vrg_buffer_info": [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(i64)],
     "vrg_plane_geometry": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)],
     "vrg_use_separate_global_stats": [vp],

@@ -55,7 +55,36 @@ struct vrg_handle {
     bool have_data = false, have_levels = false, inited = false, separate_gstats = false;
     int64_t launches = 0;
     int grid = 148 * 8;
+    // optional per-kernel timing (CUDA events on the launch stream), see vrg_profile
+    bool prof = false;
+    std::vector<cudaEvent_t> ev;   // 4 events per enqueued iteration: decide begin/end, apply begin/end
+    size_t ev_used = 0;
+    int64_t prof_sweeps0 = 0;      // C_SWEEPS when the pending events started
+    double prof_ms[2] = {0, 0};
+    int64_t prof_n[2] = {0, 0};
 };
+
+static cudaEvent_t prof_event(vrg_handle *h) {
+    if (h->ev_used == h->ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev.push_back(e);
+    }
+    return h->ev[h->ev_used++];
+}
+// fold finished event pairs into the totals; only launches that did real work count (no-op launches
+// after the exit would drag the average down).  Call after a stream synchronise.
+static void prof_collect(vrg_handle *h, int64_t sweeps_now) {
+    const int64_t real = sweeps_now - h->prof_sweeps0;
+    for (size_t i = 0; i + 3 < h->ev_used; i += 4) {
+        if ((int64_t)(i / 4) >= real) break;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) { h->prof_ms[0] += ms; h->prof_n[0]++; }
+        if (cudaEventElapsedTime(&ms, h->ev[i + 2], h->ev[i + 3]) == cudaSuccess) { h->prof_ms[1] += ms; h->prof_n[1]++; }
+    }
+    h->ev_used = 0;
+    h->prof_sweeps0 = sweeps_now;
+}
 
 static const int HASH_CAP = 1 << 18;
 
@@ -146,6 +175,7 @@ int vrg_destroy(vrg_handle *h) {
     cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
     free_levels(h);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return VRG_OK;
@@ -354,6 +384,8 @@ int vrg_init(vrg_handle *h) {
     if (ex[ST_BAD_LABEL]) return fail(VRG_ERR_LABEL, "initial valueMap may only hold labels 0 (seed), 3 (outside) and 4 (excluded)");
     if (ex[ST_N_EXCL] == 0 && !h->separate_gstats) p.excl = nullptr;  // no label 4 anywhere: skip the absorb path
     h->inited = true;
+    h->ev_used = 0;
+    h->prof_sweeps0 = 0;
     if (!h->separate_gstats) {  // single slab: the global view is the local one
         if (ex[ST_N_IN] == 0) return fail(VRG_ERR_EMPTY_SEED, "no seed voxel (label 0) in valueMap");
         if (ex[ST_N_BAND] == 0) return fail(VRG_ERR_NO_BAND, "seed has no boundary: every voxel is inside");
@@ -371,11 +403,13 @@ int vrg_enqueue_decide(vrg_handle *h) {
     const Params &p = h->p;
     k_table<<<p.LW, BLOCK, 0, h->stream>>>(p);
     const size_t smem = (size_t)p.LW * sizeof(uint32_t);
+    if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     switch (h->cfg.intensity_mode) {
         case VRG_INTENSITY_F64_DENSE: k_decide<MODE_F64_DENSE><<<h->grid, BLOCK, smem, h->stream>>>(p); break;
         case VRG_INTENSITY_F64_BAND: k_decide<MODE_F64_BAND><<<h->grid, BLOCK, smem, h->stream>>>(p); break;
         default: k_decide<MODE_INDEX><<<h->grid, BLOCK, smem, h->stream>>>(p); break;
     }
+    if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     h->launches += 2;
     CK(cudaGetLastError());
     return VRG_OK;
@@ -383,8 +417,10 @@ int vrg_enqueue_decide(vrg_handle *h) {
 int vrg_enqueue_apply(vrg_handle *h) {
     if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
     CK(cudaSetDevice(h->cfg.device));
+    if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) k_apply<MODE_INDEX><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
     else k_apply<MODE_F64_BAND><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     h->launches++;
     CK(cudaGetLastError());
     return VRG_OK;
@@ -415,6 +451,7 @@ int vrg_poll(vrg_handle *h, vrg_result *res) {
     CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(ex, h->p.gstats + 2 * h->p.L, sizeof ex, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->prof) prof_collect(h, h->h_ctrl[C_SWEEPS]);
     if (res) {
         res->iterations = h->h_ctrl[C_ITER];
         res->exit_reason = h->h_ctrl[C_STATUS];
@@ -453,6 +490,20 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
         }
     }
     if (res) *res = r;
+    return VRG_OK;
+}
+
+int vrg_profile(vrg_handle *h, int enable) {
+    if (!h) return fail(VRG_ERR_ARG, "null handle");
+    h->prof = enable != 0;
+    h->ev_used = 0;
+    h->prof_ms[0] = h->prof_ms[1] = 0;
+    h->prof_n[0] = h->prof_n[1] = 0;
+    return VRG_OK;
+}
+int vrg_get_profile(vrg_handle *h, double *ms_total, int64_t *launches) {
+    if (!h || !ms_total || !launches) return fail(VRG_ERR_ARG, "null argument");
+    for (int i = 0; i < 2; ++i) { ms_total[i] = h->prof_ms[i]; launches[i] = h->prof_n[i]; }
     return VRG_OK;
 }
 

@@ -130,6 +130,15 @@ class VRGEngine:
     def enqueue_advance(self):
         nat.check(self.lib.vrg_enqueue_advance(self._h))
 
+    def profile(self, enable=True):
+        nat.check(self.lib.vrg_profile(self._h, int(bool(enable))))
+
+    def get_profile(self) -> dict:
+        ms = (ctypes.c_double * 2)()
+        n = (nat.i64 * 2)()
+        nat.check(self.lib.vrg_get_profile(self._h, ctypes.addressof(ms), ctypes.addressof(n)))
+        return {"decide_ms": ms[0], "decide_launches": int(n[0]), "apply_ms": ms[1], "apply_launches": int(n[1])}
+
     def use_separate_global_stats(self):
         nat.check(self.lib.vrg_use_separate_global_stats(self._h))
 

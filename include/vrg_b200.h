@@ -113,6 +113,11 @@ int vrg_enqueue_absorb(vrg_handle *h);  /* 4->3 absorption (VRG:167-168,177-179)
 int vrg_enqueue_advance(vrg_handle *h); /* exit tests + trace row (VRG:91-117) */
 int vrg_poll(vrg_handle *h, vrg_result *res); /* synchronises the stream */
 
+/* per-kernel device time (CUDA events on the launch stream) accumulated over launches that did real work:
+ * index 0 = decide (the stencil sweep), 1 = apply.  For roofline reporting. */
+int vrg_profile(vrg_handle *h, int enable);
+int vrg_get_profile(vrg_handle *h, double *ms_total /*[2]*/, int64_t *launches /*[2]*/);
+
 /* device buffers a multi-GPU host exchanges between the enqueue calls ------- */
 typedef enum {
     VRG_BUF_SEG0 = 0,     /* segmented bit-plane, ping */
