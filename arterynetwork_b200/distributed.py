@@ -1,0 +1,279 @@
+"""z-slab multi-GPU driver: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The volume is cut into contiguous slabs along z, the slowest axis (SURVEY.md
+section 8(e)).  Each rank owns one slab plus ``HALO`` = 2 halo planes per side
+and runs the same kernels as the single-GPU path; between them the host
+interleaves the only two exchanges the algorithm has:
+
+* after ``apply``  -- the two boundary planes of the NEW segmented bit-plane go
+  to each neighbour (the next decide needs the 26-neighbourhood of its own
+  planes +-1, i.e. segmented state at distance 2);
+* after ``absorb`` -- one SUM all-reduce of the int64 statistics vector
+  ``[hist_in[L], hist_out[L], n_in, n_out, n_excluded, n_flips, ...]``; every
+  rank then derives the same decision table.  When the input holds label 4 the
+  excluded plane's boundary planes are exchanged as well.
+
+Intensities never move after upload (each rank uploads its extended slab).
+Integer statistics make the result independent of the number of ranks: labels,
+iteration count and trace are bit-identical to the single-GPU run.
+
+The driver is engine-agnostic: ``tests/`` drive it on CPU with ``gloo`` and a
+NumPy slab engine (world_size 2); on GPUs it drives ``VRGEngine`` over NCCL.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from . import _native as nat
+
+HALO = nat.HALO
+
+
+def slab_bounds(Z: int, world: int):
+    """Balanced contiguous z-slabs: rank r owns [b[r], b[r+1])."""
+    base, rem = divmod(Z, world)
+    b = [0]
+    for r in range(world):
+        b.append(b[-1] + base + (1 if r < rem else 0))
+    if min(b[i + 1] - b[i] for i in range(world)) < HALO:
+        raise ValueError("each slab needs at least %d planes (Z=%d over %d ranks)" % (HALO, Z, world))
+    return b
+
+
+class _CudaBlob:
+    """Minimal ``__cuda_array_interface__`` carrier so torch can view library-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class GpuSlabEngine:
+    """Adapter: VRGEngine + torch views of the buffers the driver exchanges."""
+
+    def __init__(self, eng, device):
+        import torch
+        self.eng = eng
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.own_planes = eng.own_planes
+
+    def bind_buffers(self):
+        torch, eng = self.torch, self.eng
+        _, wpp, nzl = eng.plane_geometry()
+
+        def view(which, shape, typestr):
+            ptr, _ = eng.buffer(which)
+            return torch.as_tensor(_CudaBlob(ptr, shape, typestr), device=self.device)
+        self.seg = [view(nat.BUF_SEG0, (nzl, wpp), "<i4"), view(nat.BUF_SEG1, (nzl, wpp), "<i4")]
+        self.excl = view(nat.BUF_EXCL, (nzl, wpp), "<i4")
+        n = eng.buffer(nat.BUF_LOCAL_STATS)[1] // 8
+        self.local_stats = view(nat.BUF_LOCAL_STATS, (n,), "<i8")
+        self.global_stats = view(nat.BUF_GLOBAL_STATS, (n,), "<i8")
+
+    # the protocol the driver uses ------------------------------------------------------------
+    def local_levels(self):
+        return self.eng.scan_levels()
+
+    def set_levels(self, levels):
+        self.eng.set_levels(levels)
+        self.eng.use_separate_global_stats()
+
+    def init(self):
+        self.eng.init()
+        self.bind_buffers()
+
+    def decide(self):
+        self.eng.enqueue_decide()
+
+    def apply(self):
+        self.eng.enqueue_apply()
+
+    def absorb(self):
+        self.eng.enqueue_absorb()
+
+    def advance(self):
+        self.eng.enqueue_advance()
+
+    def poll(self):
+        return self.eng.poll()
+
+    def trace(self):
+        return self.eng.trace()
+
+    def labels(self):
+        return self.eng.labels()
+
+
+class DistributedVRG:
+    """Runs the slab protocol over an initialised ``torch.distributed`` process group."""
+
+    def __init__(self, engine, rank, world, check_every=4):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.e, self.rank, self.world = engine, rank, world
+        self.check_every = check_every
+        self.iters_enqueued = 0
+        self.has_excl = True
+
+    # -- collectives ----------------------------------------------------------------------------
+    def _exchange(self, t):
+        """Send my boundary planes to the neighbours' halo planes of tensor ``t`` (planes x words)."""
+        dist, n = self.dist, self.e.own_planes
+        ops = []
+        if self.rank > 0:  # lower neighbour: my first own planes -> its upper halo; its last planes -> my lower halo
+            ops.append(dist.P2POp(dist.isend, t[HALO:2 * HALO], self.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, t[0:HALO], self.rank - 1))
+        if self.rank < self.world - 1:
+            ops.append(dist.P2POp(dist.isend, t[n:n + HALO], self.rank + 1))
+            ops.append(dist.P2POp(dist.irecv, t[HALO + n:2 * HALO + n], self.rank + 1))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def _allreduce_stats(self):
+        self.e.global_stats.copy_(self.e.local_stats)
+        self.dist.all_reduce(self.e.global_stats, op=self.dist.ReduceOp.SUM)
+
+    # -- phases ---------------------------------------------------------------------------------
+    def prepare_levels(self):
+        """Union of the slabs' intensity levels: every rank builds the same table domain."""
+        mine = np.asarray(self.e.local_levels(), dtype=np.float64)
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, mine)
+        levels = np.unique(np.concatenate(gathered))
+        self.e.set_levels(levels)
+        return levels
+
+    def init(self):
+        self.e.init()
+        self._exchange(self.e.seg[0])  # seeds next to a slab boundary were uploaded with the halo; keep planes coherent
+        self._exchange(self.e.excl)
+        self._allreduce_stats()
+        g = self.e.global_stats.cpu().numpy()
+        base = len(g) - nat.ST_EXTRA
+        if g[base + nat.ST_BAD_LABEL]:
+            raise ValueError("vrg_b200: initial valueMap may only hold labels 0 (seed), 3 (outside) and 4 (excluded)")
+        if g[base + nat.ST_N_IN] == 0:
+            raise ValueError("vrg_b200: no seed voxel (label 0) in valueMap")
+        if g[base + nat.ST_N_BAND] == 0:
+            raise ValueError("vrg_b200: seed has no boundary: every voxel is inside")
+        self.has_excl = bool(g[base + nat.ST_N_EXCL] > 0)
+        self.init_row = (-1, int(g[base + nat.ST_N_IN]), int(g[base + nat.ST_N_OUT]))
+        self.iters_enqueued = 0
+
+    def iterate_once(self):
+        e = self.e
+        nxt = (self.iters_enqueued + 1) & 1  # apply writes the other segmented plane
+        e.decide()
+        e.apply()
+        self._exchange(e.seg[nxt])
+        if self.has_excl:
+            e.absorb()
+            self._exchange(e.excl)
+        self._allreduce_stats()
+        e.advance()
+        self.iters_enqueued += 1
+
+    def run(self):
+        while True:
+            for _ in range(self.check_every):
+                self.iterate_once()
+            res = self.e.poll()
+            if res["exit_reason"] != nat.EXIT_RUNNING:
+                return res
+
+    def trace(self):
+        t = np.array(self.e.trace(), copy=True)
+        t[0] = self.init_row
+        return t
+
+
+# ------------------------------------------------------------------------------------------------
+def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
+    """bench.py --gpus N under torchrun: strong scaling of the named volume over z-slabs."""
+    import torch
+    import torch.distributed as dist
+    from .engine import VRGEngine
+    import bench
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    shape = workloads[args.workload]
+    nvox = shape[0] * shape[1] * shape[2]
+    b = slab_bounds(shape[0], world)
+    z0, z1 = b[rank], b[rank + 1]
+    e0, e1 = max(0, z0 - HALO), min(shape[0], z1 + HALO)
+    d_data, d_vm = bench.device_phantom(shape, args.seed, e0, e1 - e0, local)
+    eng = VRGEngine(shape, max_segment_size=10 ** 15, intensity=args.intensity, device=local, z_begin=z0, z_end=z1)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    drv = DistributedVRG(GpuSlabEngine(eng, local), rank, world)
+
+    def step():
+        eng.upload_device(d_data.data_ptr(), d_vm.data_ptr())
+        drv.prepare_levels()
+        drv.init()
+        return drv.run()
+
+    for _ in range(args.warmup):
+        res = step()
+    sampler = bench.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile(True)
+    l0 = eng.poll()["kernel_launches"]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    start.record()
+    sweeps = 0
+    for _ in range(args.steps):
+        res = step()
+        sweeps += res["sweeps"]
+    end.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([start.elapsed_time(end)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
+    ms = float(ms.item())
+    prof = eng.get_profile()
+    launches = eng.poll()["kernel_launches"] - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # checksum of the result labels so runs at different N can be compared
+    lab = torch.empty((z1 - z0,) + tuple(shape[1:]), dtype=torch.uint8, device="cuda")
+    eng.labels_device(lab.data_ptr())
+    cs = torch.stack([(lab == k).sum() for k in range(5)]).to(torch.int64)
+    dist.all_reduce(cs)
+    value = nvox * sweeps / (ms * 1e-3) / 1e9
+    if rank == 0:
+        per_launch_ms = prof["decide_ms"] / max(1, prof["decide_launches"])
+        local_vox = (min(shape[0], z1 + 1) - max(0, z0 - 1)) * shape[1] * shape[2]
+        achieved = algo_bytes * local_vox / (per_launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": metric, "value": value, "unit": "Gvoxel-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s %dx%dx%d vessel-forest phantom, seed %d" % (args.workload, shape[2], shape[1], shape[0], args.seed),
+                       "intensity_mode": args.intensity, "partition": "z-slabs, %d planes per rank, halo %d" % (z1 - z0, HALO),
+                       "sweeps_per_step": sweeps // args.steps, "segmented_voxels": res["n_in"],
+                       "label_histogram": [int(x) for x in cs.tolist()],
+                       "l2": "inputs larger than L2; no flush",
+                       "step": "upload_device (D2D) + level scan/all-gather + init + all iterations"},
+            "clocks": clocks,
+            "e2e": None,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_decide", "achieved": achieved, "peak": peak[0], "peak_kind": peak[1],
+                         "unit": "GB/s", "frac": achieved / peak[0], "traffic": None, "ms_per_launch": per_launch_ms,
+                         "note": "rank 0's slab (own planes +-1)"},
+        }
+        print(json.dumps(line))
+    eng.close()
+    dist.destroy_process_group()

@@ -1,0 +1,168 @@
+"""TEST-ONLY NumPy slab engine: the same per-slab protocol as the CUDA kernels (halo planes,
+local/global statistics vectors, decide / apply / absorb / advance), built on the oracle's rules,
+so the multi-rank driver (arterynetwork_b200/distributed.py) can be exercised on CPU with gloo."""
+import numpy as np
+import torch
+
+from arterynetwork_b200 import _native as nat
+from oracle.vrg_oracle import A, dil3
+
+HALO = nat.HALO
+
+
+class NumpySlabEngine:
+    def __init__(self, shape, z_begin, z_end, data, value_map, H=2.25, max_segment_size=10 ** 15, iter_max=200):
+        self.shape = shape
+        Z, Y, X = shape
+        self.z_begin, self.z_end = z_begin, z_end
+        self.own_planes = z_end - z_begin
+        self.nzl = self.own_planes + 2 * HALO
+        e0, e1 = max(0, z_begin - HALO), min(Z, z_end + HALO)
+        self.vlo, self.vhi = e0 - (z_begin - HALO), e1 - (z_begin - HALO)
+        self.data = np.zeros((self.nzl, Y, X))
+        self.vm = np.full((self.nzl, Y, X), 3, dtype=np.uint8)
+        self.data[self.vlo:self.vhi] = data[e0:e1]
+        self.vm[self.vlo:self.vhi] = value_map[e0:e1]
+        self.inb = np.zeros((self.nzl, Y, X), dtype=bool)
+        self.inb[self.vlo:self.vhi] = True
+        self.H, self.max_seg, self.iter_max = H, max_segment_size, iter_max
+        self.own = slice(HALO, HALO + self.own_planes)
+        self.own1 = slice(max(self.vlo, HALO - 1), min(self.vhi, HALO + self.own_planes + 1))
+
+    # planes x voxels byte tensors stand in for the bit-planes
+    def _planes(self):
+        n = self.shape[1] * self.shape[2]
+        self.seg = [torch.zeros((self.nzl, n), dtype=torch.uint8), torch.zeros((self.nzl, n), dtype=torch.uint8)]
+        self.excl = torch.zeros((self.nzl, n), dtype=torch.uint8)
+
+    def _np(self, t):
+        return t.numpy().reshape((self.nzl,) + tuple(self.shape[1:])).view(np.bool_)
+
+    def local_levels(self):
+        return np.unique(self.data[self.vlo:self.vhi])
+
+    def set_levels(self, levels):
+        self.levels = np.asarray(levels, dtype=np.float64)
+        self.L = len(self.levels)
+        self.idx = np.searchsorted(self.levels, self.data)
+        self.idx[~self.inb] = 0
+        diff = self.levels[:, None] - self.levels[None, :]
+        self.kmat = A * np.exp(-0.5 * self.H * diff ** 2)
+        self.local_stats = torch.zeros(2 * self.L + nat.ST_EXTRA, dtype=torch.int64)
+        self.global_stats = torch.zeros_like(self.local_stats)
+
+    def init(self):
+        self._planes()
+        S, E = self._np(self.seg[0]), self._np(self.excl)
+        S[:] = (self.vm == 0) & self.inb
+        E[:] = (self.vm == 4) & self.inb & ~dil3(S)
+        st = self.local_stats.numpy()
+        st[:] = 0
+        so, eo, io = S[self.own], E[self.own], self.idx[self.own]
+        st[: self.L] = np.bincount(io[so], minlength=self.L)
+        st[self.L: 2 * self.L] = np.bincount(io[~so & ~eo], minlength=self.L)
+        b = 2 * self.L
+        st[b + nat.ST_N_IN] = so.sum()
+        st[b + nat.ST_N_OUT] = (~so & ~eo).sum()
+        st[b + nat.ST_N_EXCL] = eo.sum()
+        st[b + nat.ST_BAD_LABEL] = int((~np.isin(self.vm[self.vlo:self.vhi], (0, 3, 4))).any())
+        nonseg = ~S & self.inb
+        band = (S & dil3(nonseg)) | (nonseg & ~E & dil3(S))
+        st[b + nat.ST_N_BAND] = band[self.own].sum()
+        self.ctrl = {"status": nat.EXIT_RUNNING, "iter": 1, "applied": 0, "sweeps": 0, "apply": 1}
+        self.trace_rows = [(-1, 0, 0)]
+
+    def decide(self):
+        if self.ctrl["status"] != nat.EXIT_RUNNING:
+            return
+        g = self.global_stats.numpy()
+        b = 2 * self.L
+        self.ctrl["apply"] = int(g[b + nat.ST_N_IN] < self.max_seg)
+        self.local_stats[b + nat.ST_N_FLIPS] = 0
+        with np.errstate(all="ignore"):
+            pin = (g[: self.L].astype(np.float64) @ self.kmat) / g[b + nat.ST_N_IN]
+            pout = (g[self.L: b].astype(np.float64) @ self.kmat) / g[b + nat.ST_N_OUT]
+        d = pin >= pout
+        S, E = self._np(self.seg[self.ctrl["applied"] & 1]), self._np(self.excl)
+        nonseg = ~S & self.inb
+        inner, outer = S & dil3(nonseg), nonseg & ~E & dil3(S)
+        dv = d[self.idx]
+        self.R = np.zeros_like(S)
+        self.A0 = np.zeros_like(S)
+        self.R[self.own1] = (inner & ~dv)[self.own1]
+        self.A0[self.own1] = (outer & dv)[self.own1]
+        self.local_stats[b + nat.ST_N_FLIPS] = int(self.R[self.own].sum() + self.A0[self.own].sum())
+
+    def apply(self):
+        if self.ctrl["status"] != nat.EXIT_RUNNING or not self.ctrl["apply"]:
+            return
+        par = self.ctrl["applied"] & 1
+        S, S2 = self._np(self.seg[par]), self._np(self.seg[par ^ 1])
+        keep = S & ~self.R
+        a = self.A0 & dil3(keep)
+        S2[self.own] = (keep | a)[self.own]
+        st = self.local_stats.numpy()
+        io = self.idx[self.own]
+        ra, aa = self.R[self.own], a[self.own]
+        dr, da = np.bincount(io[ra], minlength=self.L), np.bincount(io[aa], minlength=self.L)
+        st[: self.L] += da - dr
+        st[self.L: 2 * self.L] += dr - da
+        b = 2 * self.L
+        st[b + nat.ST_N_IN] += int(aa.sum()) - int(ra.sum())
+        st[b + nat.ST_N_OUT] -= int(aa.sum()) - int(ra.sum())
+
+    def absorb(self):
+        if self.ctrl["status"] != nat.EXIT_RUNNING or not self.ctrl["apply"]:
+            return
+        par = self.ctrl["applied"] & 1
+        S, S2, E = self._np(self.seg[par]), self._np(self.seg[par ^ 1]), self._np(self.excl)
+        hit = dil3(dil3(S ^ S2)) | dil3(self.R | self.A0)
+        ab = np.zeros_like(E)
+        ab[self.own] = (E & hit)[self.own]
+        E[self.own] &= ~ab[self.own]
+        st = self.local_stats.numpy()
+        st[self.L: 2 * self.L] += np.bincount(self.idx[ab], minlength=self.L)
+        b = 2 * self.L
+        st[b + nat.ST_N_OUT] += int(ab.sum())
+        st[b + nat.ST_N_EXCL] -= int(ab.sum())
+
+    def advance(self):
+        c = self.ctrl
+        if c["status"] != nat.EXIT_RUNNING:
+            return
+        g = self.global_stats.numpy()
+        b = 2 * self.L
+        c["sweeps"] += 1
+        if g[b + nat.ST_N_FLIPS] == 0:
+            c["status"] = nat.EXIT_CONVERGED
+            return
+        if not c["apply"]:
+            c["status"] = nat.EXIT_MAX_SEGMENT
+            return
+        self.trace_rows.append((int(g[b + nat.ST_N_FLIPS]), int(g[b + nat.ST_N_IN]), int(g[b + nat.ST_N_OUT])))
+        c["applied"] += 1
+        c["iter"] += 1
+        if c["iter"] > self.iter_max:
+            c["status"] = nat.EXIT_MAX_ITER
+
+    def poll(self):
+        g = self.global_stats.numpy()
+        b = 2 * self.L
+        return {"iterations": self.ctrl["iter"], "exit_reason": self.ctrl["status"], "n_in": int(g[b + nat.ST_N_IN]),
+                "n_out": int(g[b + nat.ST_N_OUT]), "n_excluded": int(g[b + nat.ST_N_EXCL]), "n_levels": self.L,
+                "sweeps": self.ctrl["sweeps"], "kernel_launches": 0}
+
+    def trace(self):
+        return np.asarray(self.trace_rows, dtype=np.int64)
+
+    def labels(self):
+        from oracle.vrg_oracle import canonical_labels
+        S, E = self._np(self.seg[self.ctrl["applied"] & 1]), self._np(self.excl)
+        nonseg = ~S & self.inb
+        lab = np.full(S.shape, 3, dtype=np.uint8)
+        lab[S] = 0
+        lab[S & dil3(nonseg)] = 1
+        lab[nonseg & dil3(S)] = 2
+        lab[E] = 4
+        assert canonical_labels is not None
+        return lab[self.own]
