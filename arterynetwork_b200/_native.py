@@ -16,7 +16,7 @@ EXIT_RUNNING, EXIT_CONVERGED, EXIT_MAX_TIME, EXIT_MAX_SEGMENT, EXIT_MAX_ITER = -
 INTENSITY_F64_DENSE, INTENSITY_F64_BAND, INTENSITY_INDEX = 0, 1, 2
 INTENSITY_MODES = {"f64_dense": 0, "f64_band": 1, "index": 2}
 HALO = 2
-BUF_SEG0, BUF_SEG1, BUF_EXCL, BUF_LOCAL_STATS, BUF_GLOBAL_STATS, BUF_CTRL = range(6)
+BUF_SEG, BUF_EXCL, BUF_FLIPS, BUF_CANCELLED, BUF_LOCAL_STATS, BUF_GLOBAL_STATS, BUF_CTRL = range(7)
 ST_N_IN, ST_N_OUT, ST_N_EXCL, ST_N_FLIPS, ST_N_BAND, ST_BAD_LABEL, ST_NONFINITE, ST_EXTRA = 0, 1, 2, 3, 4, 5, 6, 8
 C_STATUS, C_ITER, C_ITER_MAX, C_MAX_SEG, C_APPLY, C_APPLIED, C_TRACE_N, C_SWEEPS = range(8)
 
@@ -45,7 +45,8 @@ _SIGS = {
     "vrg_init": [vp],
     "vrg_run": [vp, ctypes.POINTER(Result)],
     "vrg_enqueue_decide": [vp],
-    "vrg_enqueue_apply": [vp],
+    "vrg_enqueue_cancel": [vp],
+    "vrg_enqueue_flip": [vp],
     "vrg_enqueue_absorb": [vp],
     "vrg_enqueue_advance": [vp],
     "vrg_poll": [vp, ctypes.POINTER(Result)],

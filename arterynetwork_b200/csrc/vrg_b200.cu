@@ -40,29 +40,32 @@ struct vrg_handle {
     int sms = 148;
     int64_t nz_own = 0, ext_lo = 0, ext_hi = 0;  // extended slab in global z
     size_t plane_bytes = 0;                      // one bit-plane buffer (all local planes)
+    size_t rowflag_bytes = 0;
     double *d_data = nullptr;
-    uint8_t *d_vm = nullptr;
+    uint8_t *d_vm = nullptr, *d_rowflag = nullptr, *d_labels = nullptr;
     uint16_t *d_index = nullptr;
-    uint32_t *d_seg[2] = {nullptr, nullptr}, *d_excl = nullptr, *d_R = nullptr, *d_A0 = nullptr;
+    uint32_t *d_S = nullptr, *d_E = nullptr, *d_F = nullptr, *d_C = nullptr;
     double *d_levels = nullptr, *d_pin = nullptr, *d_pout = nullptr;
     uint32_t *d_dbits = nullptr;
     long long *d_lstats = nullptr, *d_gstats = nullptr, *d_ctrl = nullptr, *d_trace = nullptr;
     long long *h_ctrl = nullptr;  // pinned
     unsigned long long *d_hash = nullptr;
     int *d_hcount = nullptr;
-    std::vector<double> levels;  // table domain (lattice: every slot lev0 + k*step)
+    std::vector<double> levels;  // distinct levels seen (sorted)
     int64_t n_distinct = 0;
     bool have_data = false, have_levels = false, inited = false, separate_gstats = false;
     int64_t launches = 0;
     int grid = 148 * 8;
     // optional per-kernel timing (CUDA events on the launch stream), see vrg_profile
     bool prof = false;
-    std::vector<cudaEvent_t> ev;   // 4 events per enqueued iteration: decide begin/end, apply begin/end
+    std::vector<cudaEvent_t> ev;   // 4 events per enqueued iteration: decide begin/end, cancel begin/end
     size_t ev_used = 0;
     int64_t prof_sweeps0 = 0;      // C_SWEEPS when the pending events started
     double prof_ms[2] = {0, 0};
     int64_t prof_n[2] = {0, 0};
 };
+
+static const int HASH_CAP = 1 << 18;
 
 static cudaEvent_t prof_event(vrg_handle *h) {
     if (h->ev_used == h->ev.size()) {
@@ -86,10 +89,8 @@ static void prof_collect(vrg_handle *h, int64_t sweeps_now) {
     h->prof_sweeps0 = sweeps_now;
 }
 
-static const int HASH_CAP = 1 << 18;
-
 const char *vrg_last_error(void) { return g_err.c_str(); }
-int vrg_version(void) { return 100; }
+int vrg_version(void) { return 101; }
 
 static void free_levels(vrg_handle *h) {
     cudaFree(h->d_levels); cudaFree(h->d_pin); cudaFree(h->d_pout); cudaFree(h->d_dbits);
@@ -136,15 +137,17 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     p.plane_vox = (long long)Y * X;
     p.mhH = -0.5 * cfg->H;
     h->plane_bytes = (size_t)p.nzl * p.plane_words * sizeof(uint32_t);
+    h->rowflag_bytes = (size_t)p.nzl * Y * p.nseg;
     const size_t nvox = (size_t)p.nzl * p.plane_vox;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void **ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
     alloc((void **)&h->d_data, nvox * sizeof(double));
     alloc((void **)&h->d_vm, nvox);
-    for (int i = 0; i < 2; ++i) alloc((void **)&h->d_seg[i], h->plane_bytes);
-    alloc((void **)&h->d_excl, h->plane_bytes);
-    alloc((void **)&h->d_R, h->plane_bytes);
-    alloc((void **)&h->d_A0, h->plane_bytes);
+    alloc((void **)&h->d_S, h->plane_bytes);
+    alloc((void **)&h->d_E, h->plane_bytes);
+    alloc((void **)&h->d_F, h->plane_bytes);
+    alloc((void **)&h->d_C, h->plane_bytes);
+    alloc((void **)&h->d_rowflag, h->rowflag_bytes);
     alloc((void **)&h->d_ctrl, C_WORDS * sizeof(long long));
     alloc((void **)&h->d_trace, 3 * (cfg->iter_max + 2) * sizeof(long long));
     alloc((void **)&h->d_hash, (size_t)HASH_CAP * sizeof(unsigned long long));
@@ -155,11 +158,10 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
         vrg_destroy(h);
         return code;
     }
-    // planes outside the volume (and the y/x padding) must read as zero forever
+    // planes outside the volume must read as neutral forever
     CK(cudaMemsetAsync(h->d_data, 0, nvox * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_vm, 3, nvox, h->stream));
-    p.seg[0] = h->d_seg[0]; p.seg[1] = h->d_seg[1];
-    p.R = h->d_R; p.A0 = h->d_A0;
+    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag;
     p.data = h->d_data;
     p.ctrl = h->d_ctrl; p.trace = h->d_trace;
     *out = h;
@@ -170,8 +172,8 @@ int vrg_destroy(vrg_handle *h) {
     if (!h) return VRG_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_data); cudaFree(h->d_vm); cudaFree(h->d_index);
-    cudaFree(h->d_seg[0]); cudaFree(h->d_seg[1]); cudaFree(h->d_excl); cudaFree(h->d_R); cudaFree(h->d_A0);
+    cudaFree(h->d_data); cudaFree(h->d_vm); cudaFree(h->d_index); cudaFree(h->d_labels);
+    cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag);
     cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
     free_levels(h);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -339,9 +341,9 @@ int vrg_use_separate_global_stats(vrg_handle *h) {
 template <int MODE>
 static void launch_init_hist(vrg_handle *h) {
     const Params &p = h->p;
-    const size_t smem = (size_t)2 * p.L * sizeof(unsigned int);
-    const int use_smem = smem <= 48 * 1024;
-    k_init_hist<MODE><<<h->grid, BLOCK, use_smem ? smem : 0, h->stream>>>(p, use_smem);
+    const size_t one = (size_t)2 * p.L * sizeof(unsigned int);
+    const int copies = (int)std::min<size_t>(WARPS, (48 * 1024) / one);
+    k_init_hist<MODE><<<h->grid, BLOCK, copies * one, h->stream>>>(p, copies);
 }
 
 int vrg_init(vrg_handle *h) {
@@ -356,10 +358,11 @@ int vrg_init(vrg_handle *h) {
         if (rc != VRG_OK) return rc;
     }
     Params &p = h->p;
-    for (int i = 0; i < 2; ++i) CK(cudaMemsetAsync(h->d_seg[i], 0, h->plane_bytes, h->stream));
-    CK(cudaMemsetAsync(h->d_excl, 0, h->plane_bytes, h->stream));
-    CK(cudaMemsetAsync(h->d_R, 0, h->plane_bytes, h->stream));
-    CK(cudaMemsetAsync(h->d_A0, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_S, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_E, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_F, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_C, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_rowflag, 0, h->rowflag_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_lstats, 0, (size_t)(2 * p.L + ST_EXTRA) * sizeof(long long), h->stream));
     CK(cudaMemsetAsync(h->d_trace, 0, 3 * (h->cfg.iter_max + 2) * sizeof(long long), h->stream));
     long long c[C_WORDS];
@@ -368,8 +371,8 @@ int vrg_init(vrg_handle *h) {
     c[C_TRACE_N] = 1;
     memcpy(h->h_ctrl, c, sizeof c);
     CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof c, cudaMemcpyHostToDevice, h->stream));
-    p.excl = h->d_excl;
-    k_init_planes<<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_vm, h->d_excl);
+    p.E = h->d_E; p.C = h->d_C;
+    k_init_planes<<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_vm, h->d_E);
     k_init_bands<<<h->grid, BLOCK, 0, h->stream>>>(p);
     switch (h->cfg.intensity_mode) {
         case VRG_INTENSITY_INDEX: launch_init_hist<MODE_INDEX>(h); break;
@@ -382,7 +385,7 @@ int vrg_init(vrg_handle *h) {
     CK(cudaMemcpyAsync(ex.data(), h->d_lstats + 2 * p.L, ST_EXTRA * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (ex[ST_BAD_LABEL]) return fail(VRG_ERR_LABEL, "initial valueMap may only hold labels 0 (seed), 3 (outside) and 4 (excluded)");
-    if (ex[ST_N_EXCL] == 0 && !h->separate_gstats) p.excl = nullptr;  // no label 4 anywhere: skip the absorb path
+    if (ex[ST_N_EXCL] == 0 && !h->separate_gstats) { p.E = nullptr; p.C = nullptr; }  // no label 4: skip the absorb path
     h->inited = true;
     h->ev_used = 0;
     h->prof_sweeps0 = 0;
@@ -397,9 +400,12 @@ int vrg_init(vrg_handle *h) {
 }
 
 // ---- iteration ----------------------------------------------------------------------------------
+#define NEED_INIT() \
+    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first"); \
+    CK(cudaSetDevice(h->cfg.device))
+
 int vrg_enqueue_decide(vrg_handle *h) {
-    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
-    CK(cudaSetDevice(h->cfg.device));
+    NEED_INIT();
     const Params &p = h->p;
     k_table<<<p.LW, BLOCK, 0, h->stream>>>(p);
     const size_t smem = (size_t)p.LW * sizeof(uint32_t);
@@ -414,30 +420,34 @@ int vrg_enqueue_decide(vrg_handle *h) {
     CK(cudaGetLastError());
     return VRG_OK;
 }
-int vrg_enqueue_apply(vrg_handle *h) {
-    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
-    CK(cudaSetDevice(h->cfg.device));
+int vrg_enqueue_cancel(vrg_handle *h) {
+    NEED_INIT();
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
-    if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) k_apply<MODE_INDEX><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
-    else k_apply<MODE_F64_BAND><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) k_cancel<MODE_INDEX><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    else k_cancel<MODE_F64_BAND><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     h->launches++;
     CK(cudaGetLastError());
     return VRG_OK;
 }
 int vrg_enqueue_absorb(vrg_handle *h) {
-    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
-    if (!h->p.excl) return VRG_OK;
-    CK(cudaSetDevice(h->cfg.device));
+    NEED_INIT();
+    if (!h->p.E) return VRG_OK;
     if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) k_absorb<MODE_INDEX><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
     else k_absorb<MODE_F64_BAND><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
     h->launches++;
     CK(cudaGetLastError());
     return VRG_OK;
 }
+int vrg_enqueue_flip(vrg_handle *h) {
+    NEED_INIT();
+    k_flip<<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
 int vrg_enqueue_advance(vrg_handle *h) {
-    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
-    CK(cudaSetDevice(h->cfg.device));
+    NEED_INIT();
     k_advance<<<1, 32, 0, h->stream>>>(h->p);
     h->launches++;
     CK(cudaGetLastError());
@@ -445,8 +455,7 @@ int vrg_enqueue_advance(vrg_handle *h) {
 }
 
 int vrg_poll(vrg_handle *h, vrg_result *res) {
-    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
-    CK(cudaSetDevice(h->cfg.device));
+    NEED_INIT();
     long long ex[ST_EXTRA];
     CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(ex, h->p.gstats + 2 * h->p.L, sizeof ex, cudaMemcpyDeviceToHost, h->stream));
@@ -464,16 +473,17 @@ int vrg_poll(vrg_handle *h, vrg_result *res) {
 }
 
 int vrg_run(vrg_handle *h, vrg_result *res) {
-    if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first");
+    NEED_INIT();
     vrg_result r;
-    const int check_every = 4;
+    const int check_every = 8;
     const auto t0 = std::chrono::steady_clock::now();
     while (true) {
         for (int k = 0; k < check_every; ++k) {
             int rc;
             if ((rc = vrg_enqueue_decide(h)) != VRG_OK) return rc;
-            if ((rc = vrg_enqueue_apply(h)) != VRG_OK) return rc;
+            if ((rc = vrg_enqueue_cancel(h)) != VRG_OK) return rc;
             if ((rc = vrg_enqueue_absorb(h)) != VRG_OK) return rc;
+            if ((rc = vrg_enqueue_flip(h)) != VRG_OK) return rc;
             if ((rc = vrg_enqueue_advance(h)) != VRG_OK) return rc;
         }
         int rc = vrg_poll(h, &r);
@@ -512,9 +522,10 @@ int vrg_buffer_info(vrg_handle *h, int which, void **ptr, int64_t *bytes) {
     if (!h || !ptr || !bytes) return fail(VRG_ERR_ARG, "null argument");
     const int64_t sb = (int64_t)(2 * h->p.L + ST_EXTRA) * sizeof(long long);
     switch (which) {
-        case VRG_BUF_SEG0: *ptr = h->d_seg[0]; *bytes = (int64_t)h->plane_bytes; break;
-        case VRG_BUF_SEG1: *ptr = h->d_seg[1]; *bytes = (int64_t)h->plane_bytes; break;
-        case VRG_BUF_EXCL: *ptr = h->d_excl; *bytes = (int64_t)h->plane_bytes; break;
+        case VRG_BUF_SEG: *ptr = h->d_S; *bytes = (int64_t)h->plane_bytes; break;
+        case VRG_BUF_EXCL: *ptr = h->d_E; *bytes = (int64_t)h->plane_bytes; break;
+        case VRG_BUF_FLIPS: *ptr = h->d_F; *bytes = (int64_t)h->plane_bytes; break;
+        case VRG_BUF_CANCELLED: *ptr = h->d_C; *bytes = (int64_t)h->plane_bytes; break;
         case VRG_BUF_LOCAL_STATS: *ptr = h->d_lstats; *bytes = sb; break;
         case VRG_BUF_GLOBAL_STATS: *ptr = h->d_gstats; *bytes = sb; break;
         case VRG_BUF_CTRL: *ptr = h->d_ctrl; *bytes = C_WORDS * sizeof(long long); break;
@@ -538,39 +549,32 @@ static int labels_impl(vrg_handle *h, uint8_t *dev_out, int seg_only) {
     return VRG_OK;
 }
 int vrg_labels_device(vrg_handle *h, uint8_t *out) {
-    if (!h || !h->inited || !out) return fail(VRG_ERR_ARG, "bad argument");
-    CK(cudaSetDevice(h->cfg.device));
+    NEED_INIT();
+    if (!out) return fail(VRG_ERR_ARG, "null buffer");
     return labels_impl(h, out, 0);
 }
 static int download_impl(vrg_handle *h, uint8_t *out, int seg_only) {
-    if (!h || !h->inited || !out) return fail(VRG_ERR_ARG, "bad argument");
-    CK(cudaSetDevice(h->cfg.device));
-    // d_vm's own planes are free to hold the materialised labels: the seeds were consumed by vrg_init
+    NEED_INIT();
+    if (!out) return fail(VRG_ERR_ARG, "null buffer");
     const size_t n = (size_t)h->nz_own * h->p.plane_vox;
-    uint8_t *tmp = nullptr;
-    CK(cudaMalloc((void **)&tmp, n));
-    int rc = labels_impl(h, tmp, seg_only);
-    if (rc == VRG_OK) {
-        cudaError_t e = cudaMemcpyAsync(out, tmp, n, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail(VRG_ERR_CUDA, "download: %s", cudaGetErrorString(e));
-    }
-    cudaFree(tmp);
-    return rc;
+    if (!h->d_labels) CK(cudaMalloc((void **)&h->d_labels, n));
+    int rc = labels_impl(h, h->d_labels, seg_only);
+    if (rc != VRG_OK) return rc;
+    CK(cudaMemcpyAsync(out, h->d_labels, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return VRG_OK;
 }
 int vrg_download_labels(vrg_handle *h, uint8_t *out) { return download_impl(h, out, 0); }
 int vrg_download_segmented_map(vrg_handle *h, uint8_t *out) { return download_impl(h, out, 1); }
 
 int vrg_download_segmented(vrg_handle *h, int64_t *coords, int64_t cap, int64_t *n_out) {
-    if (!h || !h->inited || !n_out) return fail(VRG_ERR_ARG, "bad argument");
-    CK(cudaSetDevice(h->cfg.device));
+    NEED_INIT();
+    if (!n_out) return fail(VRG_ERR_ARG, "null argument");
     const Params &p = h->p;
-    CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    const int par = (int)(h->h_ctrl[C_APPLIED] & 1);
     const size_t words = (size_t)h->nz_own * p.plane_words;
     std::vector<uint32_t> plane(words);
-    CK(cudaMemcpy(plane.data(), h->d_seg[par] + (size_t)p.own_lo * p.plane_words, words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(plane.data(), h->d_S + (size_t)p.own_lo * p.plane_words, words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     int64_t n = 0;
     for (int64_t zl = 0; zl < h->nz_own; ++zl)
         for (int64_t y = 0; y < p.Y; ++y) {
@@ -589,8 +593,8 @@ int vrg_download_segmented(vrg_handle *h, int64_t *coords, int64_t cap, int64_t 
 }
 
 int vrg_get_trace(vrg_handle *h, int64_t *rows, int64_t cap, int64_t *n_rows) {
-    if (!h || !h->inited || !n_rows) return fail(VRG_ERR_ARG, "bad argument");
-    CK(cudaSetDevice(h->cfg.device));
+    NEED_INIT();
+    if (!n_rows) return fail(VRG_ERR_ARG, "null argument");
     CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     const int64_t n = h->h_ctrl[C_TRACE_N];
@@ -609,8 +613,7 @@ int vrg_get_table(vrg_handle *h, double *pin, double *pout, int64_t cap) {
     return VRG_OK;
 }
 
-// table-domain levels (lattice: every slot), for hosts that want to index vrg_get_table
-extern "C" int vrg_get_table_levels(vrg_handle *h, double *out, int64_t cap) {
+int vrg_get_table_levels(vrg_handle *h, double *out, int64_t cap) {
     if (!h || !h->have_levels || !out) return fail(VRG_ERR_ARG, "no table yet");
     if (cap < h->p.L) return fail(VRG_ERR_ARG, "buffer too small");
     CK(cudaSetDevice(h->cfg.device));

@@ -1,17 +1,19 @@
 // Device code of the B200-native variational region growing path (sm_100a).
 //
-// State is bit-packed along x: one uint32 word = 32 voxels of one row.  Three
-// persistent bit-planes (segmented S ping/pong, excluded E) plus two per-iteration
-// flag planes (R = inner-band voxels that leave, A0 = outer-band voxels that want
-// to enter).  The reference's label alphabet (VRG:21) is a function of (S, E) and
-// the 26-neighbourhood, so it is never stored; it is materialised on download.
+// State is bit-packed along x: one uint32 word = 32 voxels of one row.  Planes:
+//   S  segmented (updated in place)          E  excluded, label 4 (only if the input has any)
+//   F  flip flags of the current iteration   C  cancelled additions (only with E)
+// plus one byte per (row, 30-word segment) saying whether its F words are non-zero, so that the
+// kernels after the sweep touch only rows at the moving front.  The reference's label alphabet
+// (VRG:21) is a function of (S, E) and the 26-neighbourhood; it is materialised on download.
 //
 // Per iteration (reference: Code/variationalRegionGrowing.py, VRG:line):
-//   k_table   region histograms -> normalised Parzen sums per level -> decision bit   VRG:79-87,151-155
-//   k_decide  bands from S (26-neighbourhood), decision per voxel, R / A0 planes       VRG:87-88,139-145
-//   k_apply   cancel rule, S' = (S & ~R) | A, integer histogram deltas                 VRG:165-233
-//   k_absorb  label 4 -> 3 around flips (only when the input holds label 4)            VRG:167-168,177-179
-//   k_advance exit tests and trace row                                                 VRG:91-117
+//   k_table   region histograms -> normalised Parzen sums per level -> decision bit      VRG:79-87,151-155
+//   k_decide  the stencil sweep: bands from S (26-neighbourhood), decision per voxel, F   VRG:87-88,139-145
+//   k_cancel  cancel rule on flagged rows, executed flips, integer histogram deltas       VRG:183-190,198,232-247
+//   k_absorb  label 4 -> 3 around flips (only when the input holds label 4)               VRG:167-168,177-179
+//   k_flip    S ^= F on flagged rows                                                      VRG:173,201
+//   k_advance exit tests and trace row                                                    VRG:91-117
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,8 +22,10 @@ namespace vrg {
 
 constexpr int HALO = 2;
 constexpr int WORDS_PER_WARP = 30;  // a warp covers 30 output words + 1 halo word on each side
+constexpr int ROWS_PER_UNIT = 16;   // rows a warp slides over per work unit of the sweep
 constexpr int BLOCK = 256;
 constexpr int WARPS = BLOCK / 32;
+constexpr unsigned FULL = 0xFFFFFFFFu;
 
 enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, ST_BAD_LABEL = 5, ST_NONFINITE = 6, ST_EXTRA = 8 };
 enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_WORDS = 16 };
@@ -39,9 +43,8 @@ struct Params {
     long long plane_words;            // Y * WP
     long long plane_vox;              // Y * X
     // state
-    uint32_t *seg[2];
-    uint32_t *excl;                   // nullptr when the run never had label 4
-    uint32_t *R, *A0;
+    uint32_t *S, *E, *F, *C;          // E, C: nullptr when the run never had label 4
+    uint8_t *rowflag;                 // [nzl * Y * nseg]
     const double *data;               // fp64 intensities, local planes
     const uint16_t *index;            // level index volume (MODE_INDEX)
     // levels / table
@@ -63,26 +66,25 @@ __device__ __forceinline__ uint32_t valid_mask(const Params &p, int c) {
     return c < p.XW - 1 ? 0xFFFFFFFFu : (c == p.XW - 1 ? p.tail_mask : 0u);
 }
 
-// x-dilation by one voxel of a row of words held one-per-lane
+// x-dilation of a row of words held one-per-lane (lane l = column c0 + l)
 __device__ __forceinline__ uint32_t dilate_x1(uint32_t v) {
-    uint32_t l = __shfl_up_sync(0xFFFFFFFFu, v, 1), r = __shfl_down_sync(0xFFFFFFFFu, v, 1);
-    return v | (v << 1) | (v >> 1) | (l >> 31) | (r << 31);
+    const uint32_t l = __shfl_up_sync(FULL, v, 1), r = __shfl_down_sync(FULL, v, 1);
+    return v | __funnelshift_l(l, v, 1) | __funnelshift_r(v, r, 1);
 }
 __device__ __forceinline__ uint32_t dilate_x2(uint32_t v) {
-    uint32_t l = __shfl_up_sync(0xFFFFFFFFu, v, 1), r = __shfl_down_sync(0xFFFFFFFFu, v, 1);
-    return v | (v << 1) | (v >> 1) | (v << 2) | (v >> 2) | (l >> 31) | (l >> 30) | (r << 31) | (r << 30);
+    const uint32_t l = __shfl_up_sync(FULL, v, 1), r = __shfl_down_sync(FULL, v, 1);
+    return v | __funnelshift_l(l, v, 1) | __funnelshift_r(v, r, 1) | __funnelshift_l(l, v, 2) | __funnelshift_r(v, r, 2);
 }
 
 __device__ __forceinline__ int level_of(const Params &p, double v) {
     if (p.lattice) {
         // round-to-nearest via the 2^52+2^51 trick: the integer lands in the low word
-        double t = __fma_rn(v - p.lev0, p.inv_step, 6755399441055744.0);
-        return __double2loint(t);
+        return __double2loint(__fma_rn(v - p.lev0, p.inv_step, 6755399441055744.0));
     }
     int lo = 0, hi = p.L - 1;
     v += 0.0;
     while (lo < hi) {
-        int m = (lo + hi) >> 1;
+        const int m = (lo + hi) >> 1;
         if (p.levels[m] < v) lo = m + 1; else hi = m;
     }
     return lo;
@@ -94,21 +96,9 @@ __device__ __forceinline__ int level_at(const Params &p, long long vox) {
     return level_of(p, p.data[vox]);
 }
 
-struct RowSeg { int zl, y, c; bool inrange; };
-__device__ __forceinline__ RowSeg decode_row(const Params &p, long long r, int zbase, int lane) {
-    RowSeg s;
-    int sg = (int)(r % p.nseg);
-    long long t = r / p.nseg;
-    s.y = (int)(t % p.Y);
-    s.zl = zbase + (int)(t / p.Y);
-    s.c = sg * WORDS_PER_WARP - 1 + lane;
-    s.inrange = s.c >= 0 && s.c < p.XW;
-    return s;
-}
-
 __device__ __forceinline__ long long warp_sum(long long v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
 
@@ -127,25 +117,25 @@ __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t mybits = 0;
     for (int k = 0; k < 32 / WARPS; ++k) {
-        int b = blockIdx.x * 32 + warp * (32 / WARPS) + k;
+        const int b = blockIdx.x * 32 + warp * (32 / WARPS) + k;
         if (b >= p.L) break;
         if (g[b] + g[p.L + b] == 0) continue;  // level absent from both regions: never looked up
         const double lb = p.levels[b];
         double si = 0.0, so = 0.0;
         for (int c = lane; c < p.L; c += 32) {
-            long long hi = g[c], ho = g[p.L + c];
+            const long long hi = g[c], ho = g[p.L + c];
             if ((hi | ho) == 0) continue;
-            double diff = p.levels[c] - lb;
-            double kv = 0.3989422804014327 * exp(p.mhH * (diff * diff));  // A * exp(-0.5*H*d^2), VRG:7,154
+            const double diff = p.levels[c] - lb;
+            const double kv = 0.3989422804014327 * exp(p.mhH * (diff * diff));  // A * exp(-0.5*H*d^2), VRG:7,154
             si += (double)hi * kv;
             so += (double)ho * kv;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            si += __shfl_xor_sync(0xFFFFFFFFu, si, o);
-            so += __shfl_xor_sync(0xFFFFFFFFu, so, o);
+            si += __shfl_xor_sync(FULL, si, o);
+            so += __shfl_xor_sync(FULL, so, o);
         }
-        double pi = si / (double)n_in, po = so / (double)n_out;  // VRG:81-82
+        const double pi = si / (double)n_in, po = so / (double)n_out;  // VRG:81-82
         if (lane == 0) { p.pin[b] = pi; p.pout[b] = po; }
         if (pi >= po) mybits |= 1u << (warp * (32 / WARPS) + k);  // ties go inside, VRG:87
     }
@@ -159,141 +149,207 @@ __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_decide: bands from the segmented plane, decision bit per voxel, flip flag planes.
+// Sliding 3x3 (z,y) window over the segmented plane for one lane's word column.
+// o = OR of the three planes' words of a row, a = AND (out-of-volume rows/planes: o = 0, a = ~0).
+struct Window {
+    const uint32_t *z0, *z1, *z2;  // column pointers of planes zl-1, zl, zl+1 (nullptr = outside the volume)
+    int Y, WP;
+    __device__ __forceinline__ void row(int yy, uint32_t &o, uint32_t &a, uint32_t &s) const {
+        o = 0u; a = 0xFFFFFFFFu; s = 0u;
+        if (z1 != nullptr && yy >= 0 && yy < Y) {
+            const long long off = (long long)yy * WP;
+            s = z1[off];
+            const uint32_t w0 = z0 ? z0[off] : 0u, w2 = z2 ? z2[off] : 0u;
+            const uint32_t a0 = z0 ? w0 : 0xFFFFFFFFu, a2 = z2 ? w2 : 0xFFFFFFFFu;
+            o = w0 | s | w2;
+            a = a0 & s & a2;
+        }
+    }
+};
+
+// k_decide: the stencil sweep.  A warp owns a strip of ROWS_PER_UNIT rows x 30 words of one plane and slides
+// down it, so every new row costs three 128-byte loads of S.  Bands:
+//   inner = S & dil26(~S in volume)      (segmented with an unsegmented in-bounds neighbour, VRG:139-142)
+//   outer = ~S & ~E & dil26(S)           (unsegmented, not excluded, with a segmented neighbour, VRG:143-145)
+// Decision D = table bit of the voxel's intensity level; a band voxel flips iff D != S (VRG:87).
+// MODE_F64_DENSE evaluates D for every voxel of the volume (streams the fp64 volume, 8 B/voxel);
+// the BAND/INDEX modes only for the 32-voxel words that hold a band voxel.
 template <int MODE>
 __global__ void __launch_bounds__(BLOCK) k_decide(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
     extern __shared__ uint32_t s_dbits[];
     for (int i = threadIdx.x; i < p.LW; i += BLOCK) s_dbits[i] = p.dbits[i];
     __syncthreads();
-    const int par = (int)(p.ctrl[C_APPLIED] & 1);
-    const uint32_t *__restrict__ S = p.seg[par];
-    const uint32_t *__restrict__ E = p.excl;
     const int lane = threadIdx.x & 31;
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
-    const long long nrows = (long long)(zhi - zlo) * p.Y * p.nseg;
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
     const long long nwarps = (long long)gridDim.x * WARPS;
     long long flips = 0;
-    for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
-        const RowSeg rs = decode_row(p, r, zlo, lane);
-        const uint32_t vm = rs.inrange ? valid_mask(p, rs.c) : 0u;
-        uint32_t vs = 0, vn = 0, s = 0;
-        if (rs.inrange) {
+    for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+        const int sg = (int)(u % p.nseg);
+        const long long t = u / p.nseg;
+        const int y0 = (int)(t % nyb) * ROWS_PER_UNIT, zl = zlo + (int)(t / nyb);
+        const int y1 = min(p.Y, y0 + ROWS_PER_UNIT);
+        const int c0 = sg * WORDS_PER_WARP - 1, c = c0 + lane;
+        const bool inr = c >= 0 && c < p.XW;
+        const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
+        const uint32_t vm = inr ? valid_mask(p, c) : 0u;
+        const bool own = zl >= p.own_lo && zl < p.own_hi;
+        Window w;
+        w.Y = p.Y; w.WP = p.WP;
+        const uint32_t *col = p.S + (long long)zl * p.plane_words + c;
+        w.z1 = inr ? col : nullptr;
+        w.z0 = (inr && zl - 1 >= p.valid_lo) ? col - p.plane_words : nullptr;
+        w.z2 = (inr && zl + 1 < p.valid_hi) ? col + p.plane_words : nullptr;
+        uint32_t o_prev, a_prev, s_prev, o_cur, a_cur, s_cur, o_next, a_next, s_next;
+        w.row(y0 - 1, o_prev, a_prev, s_prev);
+        w.row(y0, o_cur, a_cur, s_cur);
+        for (int y = y0; y < y1; ++y) {
+            w.row(y + 1, o_next, a_next, s_next);
+            const uint32_t vs = o_prev | o_cur | o_next;
+            const uint32_t vn = ~(a_prev & a_cur & a_next) & vm;
+            const uint32_t dil_s = dilate_x1(vs), dil_n = dilate_x1(vn);
+            const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+            const uint32_t s = s_cur;
+            uint32_t outer = ~s & vm & dil_s;
+            if (p.E != nullptr && active && outer) outer &= ~p.E[widx];
+            const uint32_t band = active ? ((s & dil_n) | outer) : 0u;
+            const unsigned act = __ballot_sync(FULL, band != 0u);
+            const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X;
+            uint32_t D = 0;
+            if (MODE == MODE_F64_DENSE) {
+                // every voxel of the row segment: word j of the segment lives in lane j
+                const double *drow = p.data + rowvox + (long long)(c0 + 1) * 32 + lane;
+                const int xlane = (c0 + 1) * 32 + lane;
+                constexpr int U = 10;
 #pragma unroll
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int zz = rs.zl + dz;
-                if (zz < p.valid_lo || zz >= p.valid_hi) continue;
+                for (int jb = 0; jb < WORDS_PER_WARP; jb += U) {
+                    if (c0 + 1 + jb >= p.XW) break;  // warp-uniform
+                    double v[U];
 #pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int yy = rs.y + dy;
-                    if (yy < 0 || yy >= p.Y) continue;
-                    const uint32_t w = S[(long long)zz * p.plane_words + (long long)yy * p.WP + rs.c];
-                    vs |= w;
-                    vn |= ~w & vm;
-                    if (dz == 0 && dy == 0) s = w;
+                    for (int k = 0; k < U; ++k)
+                        v[k] = (xlane + (jb + k) * 32 < p.X) ? drow[(jb + k) * 32] : p.lev0;
+#pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        const int l = level_of(p, v[k]);
+                        const unsigned word = __ballot_sync(FULL, (s_dbits[l >> 5] >> (l & 31)) & 1u);
+                        if (lane == jb + k + 1) D = word;
+                    }
+                }
+            } else {
+                unsigned m = act;
+                while (m) {  // warp-uniform: only words that hold a band voxel
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int x = (c0 + j) * 32 + lane;
+                    uint32_t bit = 0;
+                    if (x < p.X) {
+                        const int l = level_at<MODE>(p, rowvox + x);
+                        bit = (s_dbits[l >> 5] >> (l & 31)) & 1u;
+                    }
+                    const unsigned word = __ballot_sync(FULL, bit);
+                    if (lane == j) D = word;
                 }
             }
-        }
-        const long long widx = (long long)rs.zl * p.plane_words + (long long)rs.y * p.WP + rs.c;
-        const uint32_t e = (E != nullptr && rs.inrange) ? E[widx] : 0u;
-        const uint32_t dil_s = dilate_x1(vs), dil_n = dilate_x1(vn);
-        const bool active = rs.inrange && lane >= 1 && lane <= WORDS_PER_WARP;
-        const uint32_t innerB = active ? (s & dil_n) : 0u;             // segmented with an unsegmented in-bounds neighbour
-        const uint32_t outerB = active ? (~s & vm & ~e & dil_s) : 0u;  // unsegmented, not excluded, segmented neighbour
-        const uint32_t band = innerB | outerB;
-        uint32_t D = 0;
-        const long long rowvox = (long long)rs.zl * p.plane_vox + (long long)rs.y * p.X;
-        const int c0 = rs.c - lane;  // column of lane 0
-        constexpr int U = 6;
-#pragma unroll 1
-        for (int j0 = 1; j0 <= WORDS_PER_WARP; j0 += U) {
-            if (c0 + j0 >= p.XW) break;
-            int lev[U];
-            bool on[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int j = j0 + u, cj = c0 + j;
-                const uint32_t bw = __shfl_sync(0xFFFFFFFFu, band, j);
-                const int x = cj * 32 + lane;
-                const bool wordon = cj < p.XW && (MODE == MODE_F64_DENSE || bw != 0u);
-                on[u] = wordon;
-                lev[u] = -1;
-                if (wordon && x < p.X) lev[u] = level_at<MODE>(p, rowvox + x);
+            const uint32_t f = band & (D ^ s);  // inner band leaves iff in < out, outer band enters iff in >= out
+            const long long ridx = ((long long)zl * p.Y + y) * p.nseg + sg;
+            const bool any = __ballot_sync(FULL, f != 0u) != 0u;
+            const uint8_t was = p.rowflag[ridx];
+            if (any || was) {  // warp-uniform: rows away from the front cost no store
+                if (active) {
+                    p.F[widx] = f;
+                    if (p.C != nullptr) p.C[widx] = 0u;  // k_cancel refills it for rows that still flip
+                }
+                if (lane == 0 && (any != (was != 0))) p.rowflag[ridx] = any ? 1 : 0;
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!on[u]) continue;  // warp-uniform
-                const int l = lev[u];
-                const uint32_t bit = l >= 0 ? (s_dbits[l >> 5] >> (l & 31)) & 1u : 0u;
-                const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
-                if (lane == j0 + u) D = word;
-            }
+            if (own) flips += __popc(f);
+            o_prev = o_cur; a_prev = a_cur; s_prev = s_cur;
+            o_cur = o_next; a_cur = a_next; s_cur = s_next;
         }
-        const uint32_t Rw = innerB & ~D;  // inner band leaves iff in < out
-        const uint32_t Aw = outerB & D;   // outer band enters iff in >= out
-        if (active) { p.R[widx] = Rw; p.A0[widx] = Aw; }
-        if (rs.zl >= p.own_lo && rs.zl < p.own_hi) flips += __popc(Rw) + __popc(Aw);
     }
     flips = warp_sum(flips);
     if (lane == 0 && flips) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_FLIPS], (unsigned long long)flips);
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_apply: cancel rule + new segmented plane + integer statistics.
-template <int MODE>
-__global__ void __launch_bounds__(BLOCK) k_apply(Params p) {
-    if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
-    const int par = (int)(p.ctrl[C_APPLIED] & 1);
-    const uint32_t *__restrict__ S = p.seg[par];
-    uint32_t *__restrict__ S2 = p.seg[par ^ 1];
+// Rows whose flag is set, enumerated 32 at a time per warp: calls fn(zl, y, sg) warp-uniformly.
+template <typename Fn>
+__device__ __forceinline__ void for_flagged_rows(const Params &p, int zlo, int zhi, Fn fn) {
     const int lane = threadIdx.x & 31;
-    const long long nrows = (long long)(p.own_hi - p.own_lo) * p.Y * p.nseg;
-    const long long nwarps = (long long)gridDim.x * WARPS;
-    long long d_in = 0;
-    unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
-    for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
-        const RowSeg rs = decode_row(p, r, p.own_lo, lane);
-        uint32_t keepv = 0, s = 0, rw = 0;
-        if (rs.inrange) {
-#pragma unroll
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int zz = rs.zl + dz;
-                if (zz < p.valid_lo || zz >= p.valid_hi) continue;
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int yy = rs.y + dy;
-                    if (yy < 0 || yy >= p.Y) continue;
-                    const long long i = (long long)zz * p.plane_words + (long long)yy * p.WP + rs.c;
-                    const uint32_t w = S[i], rr = p.R[i];
-                    keepv |= w & ~rr;
-                    if (dz == 0 && dy == 0) { s = w; rw = rr; }
-                }
-            }
-        }
-        const long long widx = (long long)rs.zl * p.plane_words + (long long)rs.y * p.WP + rs.c;
-        const bool active = rs.inrange && lane >= 1 && lane <= WORDS_PER_WARP;
-        const uint32_t a0 = active ? p.A0[widx] : 0u;
-        const uint32_t dilk = dilate_x1(keepv);
-        const uint32_t a = a0 & dilk;  // an addition needs a segmented neighbour that stays (VRG:183-190 then 198)
-        if (!active) continue;
-        S2[widx] = (s & ~rw) | a;
-        d_in += __popc(a) - __popc(rw);
-        const long long rowvox = (long long)rs.zl * p.plane_vox + (long long)rs.y * p.X + (long long)rs.c * 32;
-        uint32_t m = rw;
-        while (m) {  // leaves the inside region: histogram deltas replace VRG:232-247
-            const int b = __ffs(m) - 1; m &= m - 1;
-            const int l = level_at<MODE>(p, rowvox + b);
-            atomicAdd(&hin[l], ~0ull);
-            atomicAdd(&hout[l], 1ull);
-        }
-        m = a;
+    const long long base = (long long)zlo * p.Y * p.nseg, nrows = (long long)(zhi - zlo) * p.Y * p.nseg;
+    const long long nchunks = (nrows + 31) / 32, nwarps = (long long)gridDim.x * WARPS;
+    for (long long k = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); k < nchunks; k += nwarps) {
+        const long long r = k * 32 + lane;
+        unsigned m = __ballot_sync(FULL, r < nrows && p.rowflag[base + r] != 0);
         while (m) {
-            const int b = __ffs(m) - 1; m &= m - 1;
-            const int l = level_at<MODE>(p, rowvox + b);
-            atomicAdd(&hin[l], 1ull);
-            atomicAdd(&hout[l], ~0ull);
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const long long rr = base + k * 32 + j;
+            const int sg = (int)(rr % p.nseg);
+            const long long t = rr / p.nseg;
+            fn((int)(t / p.Y), (int)(t % p.Y), sg);
         }
     }
+}
+
+// k_cancel: an outer-band voxel marked to enter is dropped when every segmented neighbour leaves in the same
+// iteration (VRG:183-190 then VRG:198).  Rewrites F to the executed flips (race-free: only non-segmented bits are
+// cleared, neighbours read F & S), keeps the cancelled ones in C for the absorb rule, and applies the integer
+// histogram deltas that replace the reference's incremental float sums (VRG:232-247).
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
+    if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
+    const int lane = threadIdx.x & 31;
+    long long d_in = 0;
+    unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
+    for_flagged_rows(p, p.own_lo, p.own_hi, [&](int zl, int y, int sg) {
+        const int c = sg * WORDS_PER_WARP - 1 + lane;
+        const bool inr = c >= 0 && c < p.XW;
+        const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
+        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+        const uint32_t s = inr ? p.S[widx] : 0u, f = inr ? p.F[widx] : 0u;
+        const uint32_t a0 = active ? (f & ~s) : 0u, r = active ? (f & s) : 0u;
+        uint32_t a = 0;
+        if (__ballot_sync(FULL, a0 != 0u)) {
+            uint32_t keepv = s & ~f;
+            if (inr) {
+#pragma unroll
+                for (int dz = -1; dz <= 1; ++dz) {
+                    const int zz = zl + dz;
+                    if (zz < p.valid_lo || zz >= p.valid_hi) continue;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int yy = y + dy;
+                        if ((dz == 0 && dy == 0) || yy < 0 || yy >= p.Y) continue;
+                        const long long i = (long long)zz * p.plane_words + (long long)yy * p.WP + c;
+                        keepv |= p.S[i] & ~p.F[i];
+                    }
+                }
+            }
+            a = a0 & dilate_x1(keepv);
+            if (active && a != a0) p.F[widx] = r | a;
+        }
+        if (p.C != nullptr && active) p.C[widx] = a0 & ~a;
+        if (active) {
+            d_in += __popc(a) - __popc(r);
+            const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
+            uint32_t m = r;
+            while (m) {
+                const int b = __ffs(m) - 1; m &= m - 1;
+                const int l = level_at<MODE>(p, rowvox + b);
+                atomicAdd(&hin[l], ~0ull);
+                atomicAdd(&hout[l], 1ull);
+            }
+            m = a;
+            while (m) {
+                const int b = __ffs(m) - 1; m &= m - 1;
+                const int l = level_at<MODE>(p, rowvox + b);
+                atomicAdd(&hin[l], 1ull);
+                atomicAdd(&hout[l], ~0ull);
+            }
+        }
+    });
     d_in = warp_sum(d_in);
     if (lane == 0 && d_in) {
         atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_IN], (unsigned long long)d_in);
@@ -301,45 +357,80 @@ __global__ void __launch_bounds__(BLOCK) k_apply(Params p) {
     }
 }
 
+// k_flip: S ^= F.  Own planes: flagged rows only.  Halo planes (multi-GPU, after the F exchange): every row.
+__global__ void __launch_bounds__(BLOCK) k_flip(Params p) {
+    if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
+    const int lane = threadIdx.x & 31;
+    for_flagged_rows(p, p.own_lo, p.own_hi, [&](int zl, int y, int sg) {
+        const int c = sg * WORDS_PER_WARP + lane;
+        if (lane < WORDS_PER_WARP && c < p.XW) {
+            const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+            p.S[widx] ^= p.F[widx];
+        }
+    });
+    const long long tid = (long long)blockIdx.x * BLOCK + threadIdx.x, nth = (long long)gridDim.x * BLOCK;
+    for (int side = 0; side < 2; ++side) {
+        const int zlo = side ? p.own_hi : max(p.valid_lo, p.own_lo - HALO);
+        const int zhi = side ? min(p.valid_hi, p.own_hi + HALO) : p.own_lo;
+        if (zhi <= zlo) continue;
+        const long long b = (long long)zlo * p.plane_words, n = (long long)(zhi - zlo) * p.plane_words;
+        for (long long i = tid; i < n; i += nth) {
+            const uint32_t f = p.F[b + i];
+            if (f) p.S[b + i] ^= f;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
-// k_absorb: excluded voxels within 1 of any listed flip, or within 2 of an executed flip, become outside.
-// Runs after k_apply (and after the S' halo exchange on multi-GPU); `applied` parity still names the old plane.
+// k_absorb: excluded voxels within 1 of any listed flip (executed or cancelled), or within 2 of an executed flip,
+// become outside (VRG:167-168, 177-179, 207-208).  Runs after k_cancel (and the F/C halo exchange).
 template <int MODE>
 __global__ void __launch_bounds__(BLOCK) k_absorb(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
-    const int par = (int)(p.ctrl[C_APPLIED] & 1);
-    const uint32_t *__restrict__ S = p.seg[par], *__restrict__ S2 = p.seg[par ^ 1];
     const int lane = threadIdx.x & 31;
     const long long nrows = (long long)(p.own_hi - p.own_lo) * p.Y * p.nseg;
     const long long nwarps = (long long)gridDim.x * WARPS;
     long long n_abs = 0;
     unsigned long long *hout = (unsigned long long *)p.lstats + p.L;
-    for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
-        const RowSeg rs = decode_row(p, r, p.own_lo, lane);
-        const long long widx = (long long)rs.zl * p.plane_words + (long long)rs.y * p.WP + rs.c;
-        const bool active = rs.inrange && lane >= 1 && lane <= WORDS_PER_WARP;
-        const uint32_t e = active ? p.excl[widx] : 0u;
-        if (__ballot_sync(0xFFFFFFFFu, e != 0u) == 0u) continue;
-        uint32_t ve = 0, vf = 0;
-        if (rs.inrange) {
+    for (long long rr = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); rr < nrows; rr += nwarps) {
+        const int sg = (int)(rr % p.nseg);
+        const long long t = rr / p.nseg;
+        const int y = (int)(t % p.Y), zl = p.own_lo + (int)(t / p.Y);
+        // any flagged row within +-2 rows/planes (and the neighbouring segments)?  75 candidates, 3 per lane
+        bool near = false;
+        for (int q = lane; q < 75; q += 32) {
+            const int dz = q / 15 - 2, dy = (q / 3) % 5 - 2, ds = q % 3 - 1;
+            const int zz = zl + dz, yy = y + dy, ss = sg + ds;
+            if (zz >= p.valid_lo && zz < p.valid_hi && yy >= 0 && yy < p.Y && ss >= 0 && ss < p.nseg)
+                near |= p.rowflag[((long long)zz * p.Y + yy) * p.nseg + ss] != 0;
+        }
+        if (!__ballot_sync(FULL, near)) continue;
+        const int c = sg * WORDS_PER_WARP - 1 + lane;
+        const bool inr = c >= 0 && c < p.XW;
+        const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
+        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+        const uint32_t e = active ? p.E[widx] : 0u;
+        if (!__ballot_sync(FULL, e != 0u)) continue;
+        uint32_t ve = 0, vc = 0;
+        if (inr) {
             for (int dz = -2; dz <= 2; ++dz) {
-                const int zz = rs.zl + dz;
+                const int zz = zl + dz;
                 if (zz < p.valid_lo || zz >= p.valid_hi) continue;
                 for (int dy = -2; dy <= 2; ++dy) {
-                    const int yy = rs.y + dy;
+                    const int yy = y + dy;
                     if (yy < 0 || yy >= p.Y) continue;
-                    const long long i = (long long)zz * p.plane_words + (long long)yy * p.WP + rs.c;
-                    ve |= S[i] ^ S2[i];  // executed flips
-                    if (dz >= -1 && dz <= 1 && dy >= -1 && dy <= 1) vf |= p.R[i] | p.A0[i];  // every listed flip
+                    const long long i = (long long)zz * p.plane_words + (long long)yy * p.WP + c;
+                    ve |= p.F[i];
+                    if (dz >= -1 && dz <= 1 && dy >= -1 && dy <= 1) vc |= p.C[i];
                 }
             }
         }
-        const uint32_t hit = dilate_x2(ve) | dilate_x1(vf);
+        const uint32_t hit = dilate_x2(ve) | dilate_x1(vc);
         uint32_t ab = e & hit;
         if (!active || ab == 0u) continue;
-        p.excl[widx] = e & ~ab;
+        p.E[widx] = e & ~ab;
         n_abs += __popc(ab);
-        const long long rowvox = (long long)rs.zl * p.plane_vox + (long long)rs.y * p.X + (long long)rs.c * 32;
+        const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
         while (ab) {
             const int b = __ffs(ab) - 1; ab &= ab - 1;
             atomicAdd(&hout[level_at<MODE>(p, rowvox + b)], 1ull);  // addedPoints, VRG:235,247
@@ -373,93 +464,114 @@ __global__ void k_advance(Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// init branch of update(), VRG:129-145
+// init branch of update(), VRG:129-145: bit-planes from the uint8 valueMap, 16 voxels per lane-load
 __global__ void __launch_bounds__(BLOCK) k_init_planes(Params p, const uint8_t *__restrict__ vm, uint32_t *eraw) {
-    const int lane = threadIdx.x & 31;
-    const long long nrows = (long long)(p.valid_hi - p.valid_lo) * p.Y * p.XW;
-    const long long nwarps = (long long)gridDim.x * WARPS;
+    const long long nw = (long long)(p.valid_hi - p.valid_lo) * p.Y * p.XW;
     bool bad = false;
-    for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
-        const int c = (int)(r % p.XW);
-        const long long t = r / p.XW;
+    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < nw; i += (long long)gridDim.x * BLOCK) {
+        const int c = (int)(i % p.XW);
+        const long long t = i / p.XW;
         const int y = (int)(t % p.Y), zl = p.valid_lo + (int)(t / p.Y);
-        const int x = c * 32 + lane;
-        uint8_t v = 3;
-        if (x < p.X) v = vm[(long long)zl * p.plane_vox + (long long)y * p.X + x];
-        bad |= !(v == 0 || v == 3 || v == 4);
-        const uint32_t s = __ballot_sync(0xFFFFFFFFu, v == 0), e = __ballot_sync(0xFFFFFFFFu, v == 4);
-        if (lane == 0) {
-            const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
-            p.seg[0][widx] = s;
-            if (eraw) eraw[widx] = e;
+        const uint8_t *src = vm + (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
+        const int n = min(32, p.X - c * 32);
+        uint32_t s = 0, e = 0;
+        if (n == 32 && (((uintptr_t)src) & 15) == 0) {
+            const uint4 *q = (const uint4 *)src;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint4 v = q[h];
+                const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t byte = (ws[k] >> (8 * b)) & 0xFFu;
+                        const int bit = h * 16 + k * 4 + b;
+                        s |= (uint32_t)(byte == 0u) << bit;
+                        e |= (uint32_t)(byte == 4u) << bit;
+                        bad |= !(byte == 0u || byte == 3u || byte == 4u);
+                    }
+            }
+        } else {
+            for (int b = 0; b < n; ++b) {
+                const uint32_t byte = src[b];
+                s |= (uint32_t)(byte == 0u) << b;
+                e |= (uint32_t)(byte == 4u) << b;
+                bad |= !(byte == 0u || byte == 3u || byte == 4u);
+            }
         }
+        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+        p.S[widx] = s;
+        if (eraw) eraw[widx] = e;
     }
     if (bad) p.lstats[2 * p.L + ST_BAD_LABEL] = 1;
 }
 
-// E = Eraw & ~dil3(S) (VRG:137), and the initial band count.  In place on p.excl (only the centre word is read).
+// E = Eraw & ~dil26(S) (VRG:137), and the initial band count.  In place on p.E (only the centre word is read).
 __global__ void __launch_bounds__(BLOCK) k_init_bands(Params p) {
-    const uint32_t *__restrict__ S = p.seg[0];
     const int lane = threadIdx.x & 31;
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
     const long long nrows = (long long)(zhi - zlo) * p.Y * p.nseg;
     const long long nwarps = (long long)gridDim.x * WARPS;
     long long nband = 0;
     for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
-        const RowSeg rs = decode_row(p, r, zlo, lane);
-        const uint32_t vm = rs.inrange ? valid_mask(p, rs.c) : 0u;
+        const int sg = (int)(r % p.nseg);
+        const long long t = r / p.nseg;
+        const int y = (int)(t % p.Y), zl = zlo + (int)(t / p.Y);
+        const int c = sg * WORDS_PER_WARP - 1 + lane;
+        const bool inr = c >= 0 && c < p.XW;
+        const uint32_t vm = inr ? valid_mask(p, c) : 0u;
         uint32_t vs = 0, vn = 0, s = 0;
-        if (rs.inrange) {
+        if (inr) {
             for (int dz = -1; dz <= 1; ++dz) {
-                const int zz = rs.zl + dz;
+                const int zz = zl + dz;
                 if (zz < p.valid_lo || zz >= p.valid_hi) continue;
                 for (int dy = -1; dy <= 1; ++dy) {
-                    const int yy = rs.y + dy;
+                    const int yy = y + dy;
                     if (yy < 0 || yy >= p.Y) continue;
-                    const uint32_t w = S[(long long)zz * p.plane_words + (long long)yy * p.WP + rs.c];
+                    const uint32_t w = p.S[(long long)zz * p.plane_words + (long long)yy * p.WP + c];
                     vs |= w; vn |= ~w & vm;
                     if (dz == 0 && dy == 0) s = w;
                 }
             }
         }
         const uint32_t dil_s = dilate_x1(vs), dil_n = dilate_x1(vn);
-        const bool active = rs.inrange && lane >= 1 && lane <= WORDS_PER_WARP;
+        const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
         if (!active) continue;
-        const long long widx = (long long)rs.zl * p.plane_words + (long long)rs.y * p.WP + rs.c;
+        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
         uint32_t e = 0;
-        if (p.excl) { e = p.excl[widx] & ~dil_s; p.excl[widx] = e; }
-        if (rs.zl >= p.own_lo && rs.zl < p.own_hi) nband += __popc(s & dil_n) + __popc(~s & vm & ~e & dil_s);
+        if (p.E) { e = p.E[widx] & ~dil_s; p.E[widx] = e; }
+        if (zl >= p.own_lo && zl < p.own_hi) nband += __popc(s & dil_n) + __popc(~s & vm & ~e & dil_s);
     }
     nband = warp_sum(nband);
     if (lane == 0 && nband) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_BAND], (unsigned long long)nband);
 }
 
-// region histograms and sizes over own planes (VRG:49-52, 149-150 as integer counts)
+// region histograms and sizes over own planes (VRG:49-52, 149-150 as integer counts).
+// Per-warp private shared histograms keep the shared-memory atomics off the few hot background levels.
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK) k_init_hist(Params p, int use_smem) {
-    extern __shared__ unsigned int s_h[];  // [2L] when use_smem
-    if (use_smem) {
-        for (int i = threadIdx.x; i < 2 * p.L; i += BLOCK) s_h[i] = 0;
-        __syncthreads();
-    }
-    const uint32_t *__restrict__ S = p.seg[0];
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(BLOCK) k_init_hist(Params p, int copies) {
+    extern __shared__ unsigned int s_h[];  // [copies][2L] when copies > 0
+    for (int i = threadIdx.x; i < copies * 2 * p.L; i += BLOCK) s_h[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int *mine = copies ? s_h + (size_t)(warp % max(copies, 1)) * 2 * p.L : nullptr;
     const long long nrows = (long long)(p.own_hi - p.own_lo) * p.Y * p.XW;
     const long long nwarps = (long long)gridDim.x * WARPS;
     unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
     long long n_in = 0, n_out = 0, n_ex = 0;
-    for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+    for (long long r = (long long)blockIdx.x * WARPS + warp; r < nrows; r += nwarps) {
         const int c = (int)(r % p.XW);
         const long long t = r / p.XW;
         const int y = (int)(t % p.Y), zl = p.own_lo + (int)(t / p.Y);
         const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
-        const uint32_t s = S[widx], e = p.excl ? p.excl[widx] : 0u;
+        const uint32_t s = p.S[widx], e = p.E ? p.E[widx] : 0u;
         const int x = c * 32 + lane;
         if (x >= p.X) continue;
         const int l = level_at<MODE>(p, (long long)zl * p.plane_vox + (long long)y * p.X + x);
         const uint32_t bit = 1u << lane;
-        if (s & bit) { n_in++; if (use_smem) atomicAdd(&s_h[l], 1u); else atomicAdd(&hin[l], 1ull); }
-        else if (!(e & bit)) { n_out++; if (use_smem) atomicAdd(&s_h[p.L + l], 1u); else atomicAdd(&hout[l], 1ull); }
+        if (s & bit) { n_in++; if (mine) atomicAdd(&mine[l], 1u); else atomicAdd(&hin[l], 1ull); }
+        else if (!(e & bit)) { n_out++; if (mine) atomicAdd(&mine[p.L + l], 1u); else atomicAdd(&hout[l], 1ull); }
         else n_ex++;
     }
     n_in = warp_sum(n_in); n_out = warp_sum(n_out); n_ex = warp_sum(n_ex);
@@ -468,10 +580,13 @@ __global__ void __launch_bounds__(BLOCK) k_init_hist(Params p, int use_smem) {
         if (n_out) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_OUT], (unsigned long long)n_out);
         if (n_ex) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_EXCL], (unsigned long long)n_ex);
     }
-    if (use_smem) {
+    if (copies) {
         __syncthreads();
-        for (int i = threadIdx.x; i < 2 * p.L; i += BLOCK)
-            if (s_h[i]) atomicAdd(&hin[i], (unsigned long long)s_h[i]);
+        for (int i = threadIdx.x; i < 2 * p.L; i += BLOCK) {
+            unsigned long long tot = 0;
+            for (int k = 0; k < copies; ++k) tot += s_h[(size_t)k * 2 * p.L + i];
+            if (tot) atomicAdd(&hin[i], tot);
+        }
     }
 }
 
@@ -487,18 +602,18 @@ __global__ void __launch_bounds__(BLOCK) k_scan_levels(const double *__restrict_
                                                        int cap_mask, int *count, int max_count, int *flags) {
     unsigned long long last = HEMPTY;
     for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) {
-        double v = data[i] + 0.0;
+        const double v = data[i] + 0.0;
         if (!isfinite(v)) { flags[0] = 1; continue; }
-        unsigned long long key = (unsigned long long)__double_as_longlong(v);
+        const unsigned long long key = (unsigned long long)__double_as_longlong(v);
         if (key == last) continue;
         last = key;
         unsigned int h = (unsigned int)mix64(key) & cap_mask;
         while (true) {
-            unsigned long long cur = table[h];
+            const unsigned long long cur = table[h];
             if (cur == key) break;
             if (cur == HEMPTY) {
                 if (*(volatile int *)count >= max_count) { flags[1] = 1; break; }
-                unsigned long long old = atomicCAS(&table[h], HEMPTY, key);
+                const unsigned long long old = atomicCAS(&table[h], HEMPTY, key);
                 if (old == HEMPTY) { atomicAdd(count, 1); break; }
                 if (old == key) break;
             }
@@ -515,46 +630,56 @@ __global__ void __launch_bounds__(BLOCK) k_build_index(Params p, const double *_
 // ---------------------------------------------------------------------------------------------
 // outputs: canonical labels (VRG:21) or the 0/1 segmented map, one byte per voxel, own planes only
 __global__ void __launch_bounds__(BLOCK) k_labels(Params p, uint8_t *__restrict__ out, int seg_only) {
-    const int par = (int)(p.ctrl[C_APPLIED] & 1);
-    const uint32_t *__restrict__ S = p.seg[par];
     const int lane = threadIdx.x & 31;
     const long long nrows = (long long)(p.own_hi - p.own_lo) * p.Y * p.nseg;
     const long long nwarps = (long long)gridDim.x * WARPS;
     for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
-        const RowSeg rs = decode_row(p, r, p.own_lo, lane);
-        const uint32_t vm = rs.inrange ? valid_mask(p, rs.c) : 0u;
+        const int sg = (int)(r % p.nseg);
+        const long long t = r / p.nseg;
+        const int y = (int)(t % p.Y), zl = p.own_lo + (int)(t / p.Y);
+        const int c0 = sg * WORDS_PER_WARP - 1, c = c0 + lane;
+        const bool inr = c >= 0 && c < p.XW;
+        const uint32_t vm = inr ? valid_mask(p, c) : 0u;
         uint32_t vs = 0, vn = 0, s = 0;
-        if (rs.inrange) {
+        if (inr) {
             for (int dz = -1; dz <= 1; ++dz) {
-                const int zz = rs.zl + dz;
+                const int zz = zl + dz;
                 if (zz < p.valid_lo || zz >= p.valid_hi) continue;
                 for (int dy = -1; dy <= 1; ++dy) {
-                    const int yy = rs.y + dy;
+                    const int yy = y + dy;
                     if (yy < 0 || yy >= p.Y) continue;
-                    const uint32_t w = S[(long long)zz * p.plane_words + (long long)yy * p.WP + rs.c];
+                    const uint32_t w = p.S[(long long)zz * p.plane_words + (long long)yy * p.WP + c];
                     vs |= w; vn |= ~w & vm;
                     if (dz == 0 && dy == 0) s = w;
                 }
             }
         }
-        const long long widx = (long long)rs.zl * p.plane_words + (long long)rs.y * p.WP + rs.c;
-        const uint32_t e = (p.excl && rs.inrange) ? p.excl[widx] : 0u;
+        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+        const uint32_t e = (p.E && inr) ? p.E[widx] : 0u;
         const uint32_t dil_s = dilate_x1(vs), dil_n = dilate_x1(vn);
         const uint32_t inner = s & dil_n, outer = ~s & ~e & dil_s;
-        const long long rowout = ((long long)(rs.zl - p.own_lo) * p.Y + rs.y) * p.X;
-        const int c0 = rs.c - lane;
-        for (int j = 1; j <= WORDS_PER_WARP; ++j) {
-            const int cj = c0 + j;
-            if (cj >= p.XW) break;
-            const uint32_t sj = __shfl_sync(0xFFFFFFFFu, s, j), ij = __shfl_sync(0xFFFFFFFFu, inner, j);
-            const uint32_t oj = __shfl_sync(0xFFFFFFFFu, outer, j), ej = __shfl_sync(0xFFFFFFFFu, e, j);
-            const int x = cj * 32 + lane;
-            if (x >= p.X) continue;
-            const uint32_t bit = 1u << lane;
-            uint8_t lab;
-            if (seg_only) lab = (sj & bit) ? 1 : 0;
-            else lab = (sj & bit) ? ((ij & bit) ? 1 : 0) : ((ej & bit) ? 4 : ((oj & bit) ? 2 : 3));
-            out[rowout + x] = lab;
+        // 4 voxels (bytes) per lane and store: a warp writes 128 consecutive voxels = 4 words per step
+        uint8_t *rowout = out + ((long long)(zl - p.own_lo) * p.Y + y) * p.X;
+        for (int j0 = 1; j0 <= WORDS_PER_WARP; j0 += 4) {
+            if (c0 + j0 >= p.XW) break;
+            const int src = j0 + (lane >> 3);  // lane that holds this lane's word
+            const uint32_t sj = __shfl_sync(FULL, s, src), ij = __shfl_sync(FULL, inner, src);
+            const uint32_t oj = __shfl_sync(FULL, outer, src), ej = __shfl_sync(FULL, e, src);
+            if (src > WORDS_PER_WARP) continue;
+            const int x = (c0 + src) * 32 + (lane & 7) * 4;
+            uint32_t pack = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t bit = 1u << ((lane & 7) * 4 + b);
+                uint32_t lab;
+                if (seg_only) lab = (sj & bit) ? 1u : 0u;
+                else lab = (sj & bit) ? ((ij & bit) ? 1u : 0u) : ((ej & bit) ? 4u : ((oj & bit) ? 2u : 3u));
+                pack |= lab << (8 * b);
+            }
+            if (x + 3 < p.X && ((((uintptr_t)(rowout + x)) & 3) == 0)) *(uint32_t *)(rowout + x) = pack;
+            else
+                for (int b = 0; b < 4; ++b)
+                    if (x + b < p.X) rowout[x + b] = (uint8_t)(pack >> (8 * b));
         }
     }
 }

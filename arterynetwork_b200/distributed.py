@@ -5,13 +5,13 @@ section 8(e)).  Each rank owns one slab plus ``HALO`` = 2 halo planes per side
 and runs the same kernels as the single-GPU path; between them the host
 interleaves the only two exchanges the algorithm has:
 
-* after ``apply``  -- the two boundary planes of the NEW segmented bit-plane go
-  to each neighbour (the next decide needs the 26-neighbourhood of its own
-  planes +-1, i.e. segmented state at distance 2);
-* after ``absorb`` -- one SUM all-reduce of the int64 statistics vector
+* after ``cancel`` -- the two boundary planes of the executed-flip bit-plane go
+  to each neighbour, which applies them to its halo copy of the segmented plane
+  (the next sweep classifies own planes +-1, i.e. needs state at distance 2);
+* after ``flip``   -- one SUM all-reduce of the int64 statistics vector
   ``[hist_in[L], hist_out[L], n_in, n_out, n_excluded, n_flips, ...]``; every
   rank then derives the same decision table.  When the input holds label 4 the
-  excluded plane's boundary planes are exchanged as well.
+  cancelled-flip and excluded planes' boundary planes are exchanged as well.
 
 Intensities never move after upload (each rank uploads its extended slab).
 Integer statistics make the result independent of the number of ranks: labels,
@@ -68,8 +68,10 @@ class GpuSlabEngine:
         def view(which, shape, typestr):
             ptr, _ = eng.buffer(which)
             return torch.as_tensor(_CudaBlob(ptr, shape, typestr), device=self.device)
-        self.seg = [view(nat.BUF_SEG0, (nzl, wpp), "<i4"), view(nat.BUF_SEG1, (nzl, wpp), "<i4")]
+        self.seg = view(nat.BUF_SEG, (nzl, wpp), "<i4")
         self.excl = view(nat.BUF_EXCL, (nzl, wpp), "<i4")
+        self.flips = view(nat.BUF_FLIPS, (nzl, wpp), "<i4")
+        self.cancelled = view(nat.BUF_CANCELLED, (nzl, wpp), "<i4")
         n = eng.buffer(nat.BUF_LOCAL_STATS)[1] // 8
         self.local_stats = view(nat.BUF_LOCAL_STATS, (n,), "<i8")
         self.global_stats = view(nat.BUF_GLOBAL_STATS, (n,), "<i8")
@@ -89,8 +91,11 @@ class GpuSlabEngine:
     def decide(self):
         self.eng.enqueue_decide()
 
-    def apply(self):
-        self.eng.enqueue_apply()
+    def cancel(self):
+        self.eng.enqueue_cancel()
+
+    def flip(self):
+        self.eng.enqueue_flip()
 
     def absorb(self):
         self.eng.enqueue_absorb()
@@ -151,8 +156,7 @@ class DistributedVRG:
 
     def init(self):
         self.e.init()
-        self._exchange(self.e.seg[0])  # seeds next to a slab boundary were uploaded with the halo; keep planes coherent
-        self._exchange(self.e.excl)
+        self._exchange(self.e.excl)  # the 4->3 absorption around seeds (VRG:137) is computed for own planes +-1 only
         self._allreduce_stats()
         g = self.e.global_stats.cpu().numpy()
         base = len(g) - nat.ST_EXTRA
@@ -168,12 +172,14 @@ class DistributedVRG:
 
     def iterate_once(self):
         e = self.e
-        nxt = (self.iters_enqueued + 1) & 1  # apply writes the other segmented plane
         e.decide()
-        e.apply()
-        self._exchange(e.seg[nxt])
+        e.cancel()
+        self._exchange(e.flips)
         if self.has_excl:
+            self._exchange(e.cancelled)
             e.absorb()
+        e.flip()
+        if self.has_excl:
             self._exchange(e.excl)
         self._allreduce_stats()
         e.advance()

@@ -121,11 +121,14 @@ class VRGEngine:
     def enqueue_decide(self):
         nat.check(self.lib.vrg_enqueue_decide(self._h))
 
-    def enqueue_apply(self):
-        nat.check(self.lib.vrg_enqueue_apply(self._h))
+    def enqueue_cancel(self):
+        nat.check(self.lib.vrg_enqueue_cancel(self._h))
 
     def enqueue_absorb(self):
         nat.check(self.lib.vrg_enqueue_absorb(self._h))
+
+    def enqueue_flip(self):
+        nat.check(self.lib.vrg_enqueue_flip(self._h))
 
     def enqueue_advance(self):
         nat.check(self.lib.vrg_enqueue_advance(self._h))
@@ -137,7 +140,7 @@ class VRGEngine:
         ms = (ctypes.c_double * 2)()
         n = (nat.i64 * 2)()
         nat.check(self.lib.vrg_get_profile(self._h, ctypes.addressof(ms), ctypes.addressof(n)))
-        return {"decide_ms": ms[0], "decide_launches": int(n[0]), "apply_ms": ms[1], "apply_launches": int(n[1])}
+        return {"decide_ms": ms[0], "decide_launches": int(n[0]), "cancel_ms": ms[1], "cancel_launches": int(n[1])}
 
     def use_separate_global_stats(self):
         nat.check(self.lib.vrg_use_separate_global_stats(self._h))

@@ -197,7 +197,7 @@ def roofline_of(r, nvox, peak, peak_kind, traffic=None):
             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * nvox, "ms_per_launch": per_launch_ms,
             "launches_timed": prof["decide_launches"],
             "share_of_step": prof["decide_ms"] / r["ms"],
-            "apply_ms_per_launch": prof["apply_ms"] / max(1, prof["apply_launches"])}
+            "cancel_ms_per_launch": prof["cancel_ms"] / max(1, prof["cancel_launches"])}
 
 
 def run_single(args):

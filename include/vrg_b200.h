@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VRG_HALO 2 /* halo planes per side: cancel rule + re-classification need radius 2 */
+#define VRG_HALO 2 /* halo planes per side: band classification of own planes +-1 needs state at distance 2 */
 
 typedef enum {
     VRG_OK = 0,
@@ -41,14 +41,14 @@ typedef enum {
 typedef enum {
     VRG_EXIT_RUNNING = -1,
     VRG_EXIT_CONVERGED = 0,   /* no voxel flipped                         VRG:91  */
-    VRG_EXIT_MAX_TIME = 1,    /* wall-clock budget reached (opt-in)       VRG:97  */
+    VRG_EXIT_MAX_TIME = 1,    /* wall-clock budget reached                VRG:97  */
     VRG_EXIT_MAX_SEGMENT = 2, /* len(segmented) >= maxSegmentSize         VRG:101 */
     VRG_EXIT_MAX_ITER = 3     /* iterMax = 200 updates applied            VRG:56,118 */
 } vrg_exit;
 
-/* how the per-iteration decide kernel reads intensities */
+/* how the per-iteration sweep reads intensities */
 typedef enum {
-    VRG_INTENSITY_F64_DENSE = 0, /* stream the fp64 volume, every voxel, every iteration (reference dtype) */
+    VRG_INTENSITY_F64_DENSE = 0, /* stream the fp64 volume: every voxel's decision, every iteration (reference dtype) */
     VRG_INTENSITY_F64_BAND = 1,  /* fp64 volume, but only 32-voxel words that hold a band voxel */
     VRG_INTENSITY_INDEX = 2      /* uint16 level-index volume built once; band words only */
 } vrg_intensity_mode;
@@ -103,29 +103,32 @@ int vrg_set_levels(vrg_handle *h, const double *levels, int64_t n); /* union ove
 /* init branch of update(), VRG:129-155: seeds, 4->3 around seeds, bands, region histograms */
 int vrg_init(vrg_handle *h);
 
-/* iteration loop, VRG:58-117.  vrg_run drives one GPU to an exit; the three
- * enqueue calls are the same kernels for a host that interleaves the slab halo
- * exchange and the statistics all-reduce between them (multi-GPU). */
+/* iteration loop, VRG:58-117.  vrg_run drives one GPU to an exit; the enqueue
+ * calls are the same kernels for a host that interleaves the slab halo exchange
+ * and the statistics all-reduce between them (multi-GPU), in this order:
+ *   decide, cancel, [exchange FLIPS (+CANCELLED)], absorb, flip, [exchange EXCL], [all-reduce stats], advance */
 int vrg_run(vrg_handle *h, vrg_result *res);
-int vrg_enqueue_decide(vrg_handle *h);  /* decision table + flip flags (VRG:79-88) */
-int vrg_enqueue_apply(vrg_handle *h);   /* flips, cancel rule, region statistics (VRG:165-233) */
+int vrg_enqueue_decide(vrg_handle *h);  /* decision table + the stencil sweep: flip flags (VRG:79-88) */
+int vrg_enqueue_cancel(vrg_handle *h);  /* cancel rule, executed flips, region statistics (VRG:183-190,198,232-247) */
 int vrg_enqueue_absorb(vrg_handle *h);  /* 4->3 absorption (VRG:167-168,177-179); no-op without label 4 */
+int vrg_enqueue_flip(vrg_handle *h);    /* segmented ^= executed flips (VRG:173,201) */
 int vrg_enqueue_advance(vrg_handle *h); /* exit tests + trace row (VRG:91-117) */
 int vrg_poll(vrg_handle *h, vrg_result *res); /* synchronises the stream */
 
 /* per-kernel device time (CUDA events on the launch stream) accumulated over launches that did real work:
- * index 0 = decide (the stencil sweep), 1 = apply.  For roofline reporting. */
+ * index 0 = decide (the stencil sweep), 1 = cancel.  For roofline reporting. */
 int vrg_profile(vrg_handle *h, int enable);
 int vrg_get_profile(vrg_handle *h, double *ms_total /*[2]*/, int64_t *launches /*[2]*/);
 
 /* device buffers a multi-GPU host exchanges between the enqueue calls ------- */
 typedef enum {
-    VRG_BUF_SEG0 = 0,     /* segmented bit-plane, ping */
-    VRG_BUF_SEG1 = 1,     /* segmented bit-plane, pong */
-    VRG_BUF_EXCL = 2,     /* excluded (label 4) bit-plane */
-    VRG_BUF_LOCAL_STATS = 3,  /* int64[2*n_levels + 8]: this slab's histograms and counters */
-    VRG_BUF_GLOBAL_STATS = 4, /* same layout, summed over slabs (aliases LOCAL on one GPU) */
-    VRG_BUF_CTRL = 5
+    VRG_BUF_SEG = 0,          /* segmented bit-plane */
+    VRG_BUF_EXCL = 1,         /* excluded (label 4) bit-plane */
+    VRG_BUF_FLIPS = 2,        /* flip flags of the current iteration */
+    VRG_BUF_CANCELLED = 3,    /* cancelled additions of the current iteration */
+    VRG_BUF_LOCAL_STATS = 4,  /* int64[2*n_levels + 8]: this slab's histograms and counters */
+    VRG_BUF_GLOBAL_STATS = 5, /* same layout, summed over slabs (aliases LOCAL on one GPU) */
+    VRG_BUF_CTRL = 6
 } vrg_buffer;
 int vrg_buffer_info(vrg_handle *h, int which, void **dev_ptr, int64_t *bytes);
 /* bit-plane geometry: words (uint32, 32 voxels along x) per row and rows*words per plane */

@@ -14,7 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_decide -s 4 -c
     python scripts/profile_step.py --workload c3 --intensity f64_dense --iters 8 > gpurun_out/ncu_dense.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_decide -s 4 -c 2 -f -o gpurun_out/decide_band \
     python scripts/profile_step.py --workload c3 --intensity f64_band --iters 8 > gpurun_out/ncu_band.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_apply -s 4 -c 1 -f -o gpurun_out/apply \
-    python scripts/profile_step.py --workload c3 --intensity f64_band --iters 8 > gpurun_out/ncu_apply.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_cancel -s 4 -c 1 -f -o gpurun_out/cancel \
+    python scripts/profile_step.py --workload c3 --intensity f64_band --iters 8 > gpurun_out/ncu_cancel.log 2>&1
 ls -la gpurun_out
 tail -3 gpurun_out/pytest_gpu.txt; cat gpurun_out/bench_c3.json; tail -5 gpurun_out/bench_c3.err

@@ -32,8 +32,7 @@ class NumpySlabEngine:
     # planes x voxels byte tensors stand in for the bit-planes
     def _planes(self):
         n = self.shape[1] * self.shape[2]
-        self.seg = [torch.zeros((self.nzl, n), dtype=torch.uint8), torch.zeros((self.nzl, n), dtype=torch.uint8)]
-        self.excl = torch.zeros((self.nzl, n), dtype=torch.uint8)
+        self.seg, self.excl, self.flips, self.cancelled = (torch.zeros((self.nzl, n), dtype=torch.uint8) for _ in range(4))
 
     def _np(self, t):
         return t.numpy().reshape((self.nzl,) + tuple(self.shape[1:])).view(np.bool_)
@@ -53,9 +52,10 @@ class NumpySlabEngine:
 
     def init(self):
         self._planes()
-        S, E = self._np(self.seg[0]), self._np(self.excl)
+        S, E = self._np(self.seg), self._np(self.excl)
         S[:] = (self.vm == 0) & self.inb
-        E[:] = (self.vm == 4) & self.inb & ~dil3(S)
+        E[:] = (self.vm == 4) & self.inb
+        E[self.own1] &= ~dil3(S)[self.own1]  # like the kernel: absorbed around seeds on own planes +-1 only
         st = self.local_stats.numpy()
         st[:] = 0
         so, eo, io = S[self.own], E[self.own], self.idx[self.own]
@@ -83,27 +83,26 @@ class NumpySlabEngine:
             pin = (g[: self.L].astype(np.float64) @ self.kmat) / g[b + nat.ST_N_IN]
             pout = (g[self.L: b].astype(np.float64) @ self.kmat) / g[b + nat.ST_N_OUT]
         d = pin >= pout
-        S, E = self._np(self.seg[self.ctrl["applied"] & 1]), self._np(self.excl)
+        S, E, F = self._np(self.seg), self._np(self.excl), self._np(self.flips)
         nonseg = ~S & self.inb
-        inner, outer = S & dil3(nonseg), nonseg & ~E & dil3(S)
-        dv = d[self.idx]
-        self.R = np.zeros_like(S)
-        self.A0 = np.zeros_like(S)
-        self.R[self.own1] = (inner & ~dv)[self.own1]
-        self.A0[self.own1] = (outer & dv)[self.own1]
-        self.local_stats[b + nat.ST_N_FLIPS] = int(self.R[self.own].sum() + self.A0[self.own].sum())
+        band = (S & dil3(nonseg)) | (nonseg & ~E & dil3(S))
+        F[self.own1] = (band & (d[self.idx] ^ S))[self.own1]  # flips on own planes +-1; outer halo planes keep stale data
+        self.local_stats[b + nat.ST_N_FLIPS] = int(F[self.own].sum())
 
-    def apply(self):
+    def cancel(self):
         if self.ctrl["status"] != nat.EXIT_RUNNING or not self.ctrl["apply"]:
             return
-        par = self.ctrl["applied"] & 1
-        S, S2 = self._np(self.seg[par]), self._np(self.seg[par ^ 1])
-        keep = S & ~self.R
-        a = self.A0 & dil3(keep)
-        S2[self.own] = (keep | a)[self.own]
+        S, F, C = self._np(self.seg), self._np(self.flips), self._np(self.cancelled)
+        Fv = np.zeros_like(F)
+        Fv[self.own1] = F[self.own1]  # the cancel rule looks one plane out, never at the stale outer halo
+        keep = S & ~Fv
+        a0, r = Fv & ~S, Fv & S
+        a = a0 & dil3(keep)
+        F[self.own] = (r | a)[self.own]
+        C[self.own] = (a0 & ~a)[self.own]
         st = self.local_stats.numpy()
         io = self.idx[self.own]
-        ra, aa = self.R[self.own], a[self.own]
+        ra, aa = r[self.own], a[self.own]
         dr, da = np.bincount(io[ra], minlength=self.L), np.bincount(io[aa], minlength=self.L)
         st[: self.L] += da - dr
         st[self.L: 2 * self.L] += dr - da
@@ -114,9 +113,10 @@ class NumpySlabEngine:
     def absorb(self):
         if self.ctrl["status"] != nat.EXIT_RUNNING or not self.ctrl["apply"]:
             return
-        par = self.ctrl["applied"] & 1
-        S, S2, E = self._np(self.seg[par]), self._np(self.seg[par ^ 1]), self._np(self.excl)
-        hit = dil3(dil3(S ^ S2)) | dil3(self.R | self.A0)
+        F, C, E = self._np(self.flips), self._np(self.cancelled), self._np(self.excl)
+        Cv = np.zeros_like(C)
+        Cv[self.own1] = C[self.own1]
+        hit = dil3(dil3(F & self.inb)) | dil3(Cv & self.inb)
         ab = np.zeros_like(E)
         ab[self.own] = (E & hit)[self.own]
         E[self.own] &= ~ab[self.own]
@@ -125,6 +125,12 @@ class NumpySlabEngine:
         b = 2 * self.L
         st[b + nat.ST_N_OUT] += int(ab.sum())
         st[b + nat.ST_N_EXCL] -= int(ab.sum())
+
+    def flip(self):
+        if self.ctrl["status"] != nat.EXIT_RUNNING or not self.ctrl["apply"]:
+            return
+        S, F = self._np(self.seg), self._np(self.flips)
+        S ^= F & self.inb  # own planes and the (exchanged) halo planes
 
     def advance(self):
         c = self.ctrl
@@ -157,7 +163,7 @@ class NumpySlabEngine:
 
     def labels(self):
         from oracle.vrg_oracle import canonical_labels
-        S, E = self._np(self.seg[self.ctrl["applied"] & 1]), self._np(self.excl)
+        S, E = self._np(self.seg), self._np(self.excl)
         nonseg = ~S & self.inb
         lab = np.full(S.shape, 3, dtype=np.uint8)
         lab[S] = 0
