@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -56,6 +57,7 @@ struct vrg_handle {
     bool have_data = false, have_levels = false, inited = false, separate_gstats = false;
     int64_t launches = 0;
     int grid = 148 * 8;
+    bool dense_attr_set = false, force_ldg = false;
     // optional per-kernel timing (CUDA events on the launch stream), see vrg_profile
     bool prof = false;
     std::vector<cudaEvent_t> ev;   // 4 events per enqueued iteration: decide begin/end, cancel begin/end
@@ -66,6 +68,21 @@ struct vrg_handle {
 };
 
 static const int HASH_CAP = 1 << 18;
+
+// kernel<MODE, LATTICE> dispatch on the two run-time switches
+#define LAUNCH_ML(KERNEL, GRID, BLK, SMEM, ...)                                                           \
+    do {                                                                                                  \
+        const bool idx_ = h->cfg.intensity_mode == VRG_INTENSITY_INDEX, lat_ = h->p.lattice != 0;         \
+        if (idx_ && lat_) KERNEL<MODE_INDEX, true><<<GRID, BLK, SMEM, h->stream>>>(__VA_ARGS__);          \
+        else if (idx_) KERNEL<MODE_INDEX, false><<<GRID, BLK, SMEM, h->stream>>>(__VA_ARGS__);            \
+        else if (lat_) KERNEL<MODE_F64_BAND, true><<<GRID, BLK, SMEM, h->stream>>>(__VA_ARGS__);          \
+        else KERNEL<MODE_F64_BAND, false><<<GRID, BLK, SMEM, h->stream>>>(__VA_ARGS__);                   \
+    } while (0)
+
+static size_t dense_smem_bytes(const Params &p) {
+    return (size_t)((p.LW * 4 + 127) & ~127) + ((DENSE_WARPS * DENSE_STAGES * 8 + 127) & ~127) +
+           (size_t)DENSE_WARPS * DENSE_STAGES * STAGE_BYTES;
+}
 
 static cudaEvent_t prof_event(vrg_handle *h) {
     if (h->ev_used == h->ev.size()) {
@@ -117,6 +134,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     h->sms = prop.multiProcessorCount;
     h->grid = h->sms * 8;
+    h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;  // A/B switch: dense sweep with plain loads instead of the TMA ring
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     Params &p = h->p;
@@ -317,7 +335,8 @@ int vrg_set_levels(vrg_handle *h, const double *lv, int64_t n) {
     if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) {
         const size_t nvox = (size_t)p.nzl * p.plane_vox;
         if (!h->d_index) CK(cudaMalloc((void **)&h->d_index, nvox * sizeof(uint16_t)));
-        k_build_index<<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_data, h->d_index, (long long)nvox);
+        if (p.lattice) k_build_index<true><<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_data, h->d_index, (long long)nvox);
+        else k_build_index<false><<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_data, h->d_index, (long long)nvox);
         h->launches++;
         CK(cudaGetLastError());
         p.index = h->d_index;
@@ -338,12 +357,11 @@ int vrg_use_separate_global_stats(vrg_handle *h) {
 }
 
 // ---- init -------------------------------------------------------------------------------------
-template <int MODE>
 static void launch_init_hist(vrg_handle *h) {
     const Params &p = h->p;
     const size_t one = (size_t)2 * p.L * sizeof(unsigned int);
     const int copies = (int)std::min<size_t>(WARPS, (48 * 1024) / one);
-    k_init_hist<MODE><<<h->grid, BLOCK, copies * one, h->stream>>>(p, copies);
+    LAUNCH_ML(k_init_hist, h->grid, BLOCK, copies * one, p, copies);
 }
 
 int vrg_init(vrg_handle *h) {
@@ -374,10 +392,7 @@ int vrg_init(vrg_handle *h) {
     p.E = h->d_E; p.C = h->d_C;
     k_init_planes<<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_vm, h->d_E);
     k_init_bands<<<h->grid, BLOCK, 0, h->stream>>>(p);
-    switch (h->cfg.intensity_mode) {
-        case VRG_INTENSITY_INDEX: launch_init_hist<MODE_INDEX>(h); break;
-        default: launch_init_hist<MODE_F64_BAND>(h); break;
-    }
+    launch_init_hist(h);
     h->launches += 3;
     CK(cudaGetLastError());
     // the init row of the trace and the error checks need the counters on the host
@@ -410,10 +425,20 @@ int vrg_enqueue_decide(vrg_handle *h) {
     k_table<<<p.LW, BLOCK, 0, h->stream>>>(p);
     const size_t smem = (size_t)p.LW * sizeof(uint32_t);
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
-    switch (h->cfg.intensity_mode) {
-        case VRG_INTENSITY_F64_DENSE: k_decide<MODE_F64_DENSE><<<h->grid, BLOCK, smem, h->stream>>>(p); break;
-        case VRG_INTENSITY_F64_BAND: k_decide<MODE_F64_BAND><<<h->grid, BLOCK, smem, h->stream>>>(p); break;
-        default: k_decide<MODE_INDEX><<<h->grid, BLOCK, smem, h->stream>>>(p); break;
+    if (h->cfg.intensity_mode == VRG_INTENSITY_F64_DENSE) {
+        const size_t dsm = dense_smem_bytes(p);
+        if ((p.X & 1) == 0 && dsm <= 227 * 1024 && !h->force_ldg) {  // TMA ring: 16-byte aligned row segments
+            if (!h->dense_attr_set) {
+                CK(cudaFuncSetAttribute(k_sweep_dense<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                CK(cudaFuncSetAttribute(k_sweep_dense<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                h->dense_attr_set = true;
+            }
+            if (p.lattice) k_sweep_dense<true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+            else k_sweep_dense<false><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+        } else if (p.lattice) k_sweep_dense_ldg<true><<<h->grid, BLOCK, smem, h->stream>>>(p);
+        else k_sweep_dense_ldg<false><<<h->grid, BLOCK, smem, h->stream>>>(p);
+    } else {
+        LAUNCH_ML(k_sweep_band, h->grid, BLOCK, smem, p);
     }
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     h->launches += 2;
@@ -423,8 +448,7 @@ int vrg_enqueue_decide(vrg_handle *h) {
 int vrg_enqueue_cancel(vrg_handle *h) {
     NEED_INIT();
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
-    if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) k_cancel<MODE_INDEX><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
-    else k_cancel<MODE_F64_BAND><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    LAUNCH_ML(k_cancel, h->grid, BLOCK, 0, h->p);
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     h->launches++;
     CK(cudaGetLastError());
@@ -433,8 +457,7 @@ int vrg_enqueue_cancel(vrg_handle *h) {
 int vrg_enqueue_absorb(vrg_handle *h) {
     NEED_INIT();
     if (!h->p.E) return VRG_OK;
-    if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) k_absorb<MODE_INDEX><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
-    else k_absorb<MODE_F64_BAND><<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    LAUNCH_ML(k_absorb, h->grid, BLOCK, 0, h->p);
     h->launches++;
     CK(cudaGetLastError());
     return VRG_OK;

@@ -9,7 +9,7 @@
 //
 // Per iteration (reference: Code/variationalRegionGrowing.py, VRG:line):
 //   k_table   region histograms -> normalised Parzen sums per level -> decision bit      VRG:79-87,151-155
-//   k_decide  the stencil sweep: bands from S (26-neighbourhood), decision per voxel, F   VRG:87-88,139-145
+//   k_sweep*  the stencil sweep: bands from S (26-neighbourhood), decision per voxel, F   VRG:87-88,139-145
 //   k_cancel  cancel rule on flagged rows, executed flips, integer histogram deltas       VRG:183-190,198,232-247
 //   k_absorb  label 4 -> 3 around flips (only when the input holds label 4)               VRG:167-168,177-179
 //   k_flip    S ^= F on flagged rows                                                      VRG:173,201
@@ -26,6 +26,10 @@ constexpr int ROWS_PER_UNIT = 16;   // rows a warp slides over per work unit of 
 constexpr int BLOCK = 256;
 constexpr int WARPS = BLOCK / 32;
 constexpr unsigned FULL = 0xFFFFFFFFu;
+// dense sweep: per-warp ring of TMA bulk-copy stages, one stage = the fp64 intensities of one row segment
+constexpr int DENSE_WARPS = 14;
+constexpr int DENSE_STAGES = 2;
+constexpr int STAGE_BYTES = WORDS_PER_WARP * 32 * 8;
 
 enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, ST_BAD_LABEL = 5, ST_NONFINITE = 6, ST_EXTRA = 8 };
 enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_WORDS = 16 };
@@ -76,11 +80,11 @@ __device__ __forceinline__ uint32_t dilate_x2(uint32_t v) {
     return v | __funnelshift_l(l, v, 1) | __funnelshift_r(v, r, 1) | __funnelshift_l(l, v, 2) | __funnelshift_r(v, r, 2);
 }
 
+// intensity -> table slot.  LATTICE: levels sit on lev0 + k*step, one DADD + one DFMA (round-to-nearest via the
+// 2^52+2^51 trick: the integer lands in the low word).  Otherwise a binary search over the sorted levels.
+template <bool LATTICE>
 __device__ __forceinline__ int level_of(const Params &p, double v) {
-    if (p.lattice) {
-        // round-to-nearest via the 2^52+2^51 trick: the integer lands in the low word
-        return __double2loint(__fma_rn(v - p.lev0, p.inv_step, 6755399441055744.0));
-    }
+    if (LATTICE) return __double2loint(__fma_rn(v - p.lev0, p.inv_step, 6755399441055744.0));
     int lo = 0, hi = p.L - 1;
     v += 0.0;
     while (lo < hi) {
@@ -90,10 +94,10 @@ __device__ __forceinline__ int level_of(const Params &p, double v) {
     return lo;
 }
 
-template <int MODE>
+template <int MODE, bool LATTICE>
 __device__ __forceinline__ int level_at(const Params &p, long long vox) {
     if (MODE == MODE_INDEX) return p.index[vox];
-    return level_of(p, p.data[vox]);
+    return level_of<LATTICE>(p, p.data[vox]);
 }
 
 __device__ __forceinline__ long long warp_sum(long long v) {
@@ -149,33 +153,88 @@ __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sliding 3x3 (z,y) window over the segmented plane for one lane's word column.
-// o = OR of the three planes' words of a row, a = AND (out-of-volume rows/planes: o = 0, a = ~0).
-struct Window {
+// The sweep's per-lane state: a sliding 3x3 (z,y) window over the segmented plane for one word column.
+// For a row, o = OR of the three planes' words and a = AND (outside the volume: o = 0, a = ~0), so
+//   dil26(S)            = x-dilate(o[y-1] | o[y] | o[y+1])
+//   dil26(~S in volume) = x-dilate(~(a[y-1] & a[y] & a[y+1]) & valid)
+// Rows are loaded two ahead of their use, so the L2 latency of the three 128-byte loads per row is hidden.
+struct Strip {
     const uint32_t *z0, *z1, *z2;  // column pointers of planes zl-1, zl, zl+1 (nullptr = outside the volume)
     int Y, WP;
+    uint32_t vm;
+    bool active;
+    uint32_t op, ap, oc, ac, sc, on, an, sn, o2, a2, s2;  // rows y-1, y, y+1, y+2
+
     __device__ __forceinline__ void row(int yy, uint32_t &o, uint32_t &a, uint32_t &s) const {
         o = 0u; a = 0xFFFFFFFFu; s = 0u;
         if (z1 != nullptr && yy >= 0 && yy < Y) {
             const long long off = (long long)yy * WP;
             s = z1[off];
             const uint32_t w0 = z0 ? z0[off] : 0u, w2 = z2 ? z2[off] : 0u;
-            const uint32_t a0 = z0 ? w0 : 0xFFFFFFFFu, a2 = z2 ? w2 : 0xFFFFFFFFu;
             o = w0 | s | w2;
-            a = a0 & s & a2;
+            a = (z0 ? w0 : 0xFFFFFFFFu) & s & (z2 ? w2 : 0xFFFFFFFFu);
         }
+    }
+    __device__ __forceinline__ void begin(const Params &p, int zl, int y0, int c, int lane) {
+        const bool inr = c >= 0 && c < p.XW;
+        active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
+        vm = inr ? valid_mask(p, c) : 0u;
+        Y = p.Y; WP = p.WP;
+        const uint32_t *col = p.S + (long long)zl * p.plane_words + c;
+        z1 = inr ? col : nullptr;
+        z0 = (inr && zl - 1 >= p.valid_lo) ? col - p.plane_words : nullptr;
+        z2 = (inr && zl + 1 < p.valid_hi) ? col + p.plane_words : nullptr;
+        uint32_t sp;
+        row(y0 - 1, op, ap, sp);
+        row(y0, oc, ac, sc);
+        row(y0 + 1, on, an, sn);
+    }
+    // bands of row y (s = segmented word, returns inner | outer-without-E); then slides one row down
+    __device__ __forceinline__ void step(int y, uint32_t &s, uint32_t &inner, uint32_t &outer) {
+        row(y + 2, o2, a2, s2);
+        const uint32_t dil_s = dilate_x1(op | oc | on);
+        const uint32_t dil_n = dilate_x1(~(ap & ac & an) & vm);
+        s = sc;
+        inner = active ? (s & dil_n) : 0u;
+        outer = active ? (~s & vm & dil_s) : 0u;
+        op = oc; ap = ac;
+        oc = on; ac = an; sc = sn;
+        on = o2; an = a2; sn = s2;
     }
 };
 
-// k_decide: the stencil sweep.  A warp owns a strip of ROWS_PER_UNIT rows x 30 words of one plane and slides
-// down it, so every new row costs three 128-byte loads of S.  Bands:
+struct Unit { int zl, y0, y1, sg; };
+__device__ __forceinline__ Unit decode_unit(const Params &p, long long u, int zlo, int nyb) {
+    Unit r;
+    r.sg = (int)(u % p.nseg);
+    const long long t = u / p.nseg;
+    r.y0 = (int)(t % nyb) * ROWS_PER_UNIT;
+    r.zl = zlo + (int)(t / nyb);
+    r.y1 = min(p.Y, r.y0 + ROWS_PER_UNIT);
+    return r;
+}
+
+// writes the flip word of a row segment; rows away from the front cost no store (warp-uniform branch)
+__device__ __forceinline__ void store_flips(const Params &p, long long widx, long long ridx, uint32_t f, bool active, int lane) {
+    const bool any = __ballot_sync(FULL, f != 0u) != 0u;
+    const uint8_t was = p.rowflag[ridx];
+    if (any || was) {
+        if (active) {
+            p.F[widx] = f;
+            if (p.C != nullptr) p.C[widx] = 0u;  // k_cancel refills it for rows that still flip
+        }
+        if (lane == 0 && (any != (was != 0))) p.rowflag[ridx] = any ? 1 : 0;
+    }
+}
+
+// k_sweep_band: the stencil sweep of the BAND / INDEX modes.  A warp owns a strip of ROWS_PER_UNIT rows x 30 words
+// of one plane and slides down it.  Bands:
 //   inner = S & dil26(~S in volume)      (segmented with an unsegmented in-bounds neighbour, VRG:139-142)
 //   outer = ~S & ~E & dil26(S)           (unsegmented, not excluded, with a segmented neighbour, VRG:143-145)
-// Decision D = table bit of the voxel's intensity level; a band voxel flips iff D != S (VRG:87).
-// MODE_F64_DENSE evaluates D for every voxel of the volume (streams the fp64 volume, 8 B/voxel);
-// the BAND/INDEX modes only for the 32-voxel words that hold a band voxel.
-template <int MODE>
-__global__ void __launch_bounds__(BLOCK) k_decide(Params p) {
+// The decision bit D is looked up only for the 32-voxel words that hold a band voxel (four gathers in flight);
+// a band voxel flips iff D != S (VRG:87).
+template <int MODE, bool LATTICE>
+__global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
     extern __shared__ uint32_t s_dbits[];
     for (int i = threadIdx.x; i < p.LW; i += BLOCK) s_dbits[i] = p.dbits[i];
@@ -186,86 +245,234 @@ __global__ void __launch_bounds__(BLOCK) k_decide(Params p) {
     const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
     const long long nwarps = (long long)gridDim.x * WARPS;
     long long flips = 0;
+    Strip st;
     for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
-        const int sg = (int)(u % p.nseg);
-        const long long t = u / p.nseg;
-        const int y0 = (int)(t % nyb) * ROWS_PER_UNIT, zl = zlo + (int)(t / nyb);
-        const int y1 = min(p.Y, y0 + ROWS_PER_UNIT);
-        const int c0 = sg * WORDS_PER_WARP - 1, c = c0 + lane;
-        const bool inr = c >= 0 && c < p.XW;
-        const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
-        const uint32_t vm = inr ? valid_mask(p, c) : 0u;
-        const bool own = zl >= p.own_lo && zl < p.own_hi;
-        Window w;
-        w.Y = p.Y; w.WP = p.WP;
-        const uint32_t *col = p.S + (long long)zl * p.plane_words + c;
-        w.z1 = inr ? col : nullptr;
-        w.z0 = (inr && zl - 1 >= p.valid_lo) ? col - p.plane_words : nullptr;
-        w.z2 = (inr && zl + 1 < p.valid_hi) ? col + p.plane_words : nullptr;
-        uint32_t o_prev, a_prev, s_prev, o_cur, a_cur, s_cur, o_next, a_next, s_next;
-        w.row(y0 - 1, o_prev, a_prev, s_prev);
-        w.row(y0, o_cur, a_cur, s_cur);
-        for (int y = y0; y < y1; ++y) {
-            w.row(y + 1, o_next, a_next, s_next);
-            const uint32_t vs = o_prev | o_cur | o_next;
-            const uint32_t vn = ~(a_prev & a_cur & a_next) & vm;
-            const uint32_t dil_s = dilate_x1(vs), dil_n = dilate_x1(vn);
-            const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
-            const uint32_t s = s_cur;
-            uint32_t outer = ~s & vm & dil_s;
-            if (p.E != nullptr && active && outer) outer &= ~p.E[widx];
-            const uint32_t band = active ? ((s & dil_n) | outer) : 0u;
-            const unsigned act = __ballot_sync(FULL, band != 0u);
-            const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X;
+        const Unit un = decode_unit(p, u, zlo, nyb);
+        const int c0 = un.sg * WORDS_PER_WARP - 1, c = c0 + lane;
+        const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
+        st.begin(p, un.zl, un.y0, c, lane);
+        for (int y = un.y0; y < un.y1; ++y) {
+            uint32_t s, inner, outer;
+            st.step(y, s, inner, outer);
+            const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
+            if (p.E != nullptr && outer) outer &= ~p.E[widx];
+            const uint32_t band = inner | outer;
+            unsigned m = __ballot_sync(FULL, band != 0u);
             uint32_t D = 0;
-            if (MODE == MODE_F64_DENSE) {
-                // every voxel of the row segment: word j of the segment lives in lane j
-                const double *drow = p.data + rowvox + (long long)(c0 + 1) * 32 + lane;
-                const int xlane = (c0 + 1) * 32 + lane;
-                constexpr int U = 10;
+            const long long rowvox = (long long)un.zl * p.plane_vox + (long long)y * p.X + lane;
+            while (m) {  // warp-uniform: only words that hold a band voxel, four at a time
+                int js[4], lv[4];
 #pragma unroll
-                for (int jb = 0; jb < WORDS_PER_WARP; jb += U) {
-                    if (c0 + 1 + jb >= p.XW) break;  // warp-uniform
-                    double v[U];
-#pragma unroll
-                    for (int k = 0; k < U; ++k)
-                        v[k] = (xlane + (jb + k) * 32 < p.X) ? drow[(jb + k) * 32] : p.lev0;
-#pragma unroll
-                    for (int k = 0; k < U; ++k) {
-                        const int l = level_of(p, v[k]);
-                        const unsigned word = __ballot_sync(FULL, (s_dbits[l >> 5] >> (l & 31)) & 1u);
-                        if (lane == jb + k + 1) D = word;
+                for (int k = 0; k < 4; ++k) {
+                    js[k] = -1; lv[k] = -1;
+                    if (m) {
+                        js[k] = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int x = (c0 + js[k]) * 32 + lane;
+                        if (x < p.X) lv[k] = level_at<MODE, LATTICE>(p, rowvox + (long long)(c0 + js[k]) * 32);
                     }
                 }
-            } else {
-                unsigned m = act;
-                while (m) {  // warp-uniform: only words that hold a band voxel
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int x = (c0 + j) * 32 + lane;
-                    uint32_t bit = 0;
-                    if (x < p.X) {
-                        const int l = level_at<MODE>(p, rowvox + x);
-                        bit = (s_dbits[l >> 5] >> (l & 31)) & 1u;
-                    }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (js[k] < 0) break;
+                    const int l = lv[k];
+                    const uint32_t bit = l >= 0 ? (s_dbits[l >> 5] >> (l & 31)) & 1u : 0u;
                     const unsigned word = __ballot_sync(FULL, bit);
-                    if (lane == j) D = word;
+                    if (lane == js[k]) D = word;
                 }
             }
             const uint32_t f = band & (D ^ s);  // inner band leaves iff in < out, outer band enters iff in >= out
-            const long long ridx = ((long long)zl * p.Y + y) * p.nseg + sg;
-            const bool any = __ballot_sync(FULL, f != 0u) != 0u;
-            const uint8_t was = p.rowflag[ridx];
-            if (any || was) {  // warp-uniform: rows away from the front cost no store
-                if (active) {
-                    p.F[widx] = f;
-                    if (p.C != nullptr) p.C[widx] = 0u;  // k_cancel refills it for rows that still flip
-                }
-                if (lane == 0 && (any != (was != 0))) p.rowflag[ridx] = any ? 1 : 0;
-            }
+            store_flips(p, widx, ((long long)un.zl * p.Y + y) * p.nseg + un.sg, f, st.active, lane);
             if (own) flips += __popc(f);
-            o_prev = o_cur; a_prev = a_cur; s_prev = s_cur;
-            o_cur = o_next; a_cur = a_next; s_cur = s_next;
+        }
+    }
+    flips = warp_sum(flips);
+    if (lane == 0 && flips) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_FLIPS], (unsigned long long)flips);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA helpers (1-D bulk copies, cp.async.bulk -> SASS UBLKCP) and mbarriers
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// the (unit, row) sequence of one warp, walked twice: once by the TMA prefetcher, once by the consumer
+struct RowCursor {
+    long long u, nunits, stride;
+    int zlo, nyb, y;
+    Unit un;
+    __device__ __forceinline__ void start(const Params &p, long long u0, long long n, long long s, int zlo_, int nyb_) {
+        u = u0; nunits = n; stride = s; zlo = zlo_; nyb = nyb_;
+        if (u < nunits) { un = decode_unit(p, u, zlo, nyb); y = un.y0; }
+    }
+    __device__ __forceinline__ bool valid() const { return u < nunits; }
+    __device__ __forceinline__ void next(const Params &p) {
+        if (++y >= un.y1) {
+            u += stride;
+            if (u < nunits) { un = decode_unit(p, u, zlo, nyb); y = un.y0; }
+        }
+    }
+};
+
+// k_sweep_dense: the stencil sweep of the F64_DENSE mode.  Every voxel's decision is evaluated from its fp64 intensity
+// every iteration: the volume is streamed at 8 B/voxel by 1-D TMA bulk copies, one row segment (<= 7680 B) per stage,
+// into a per-warp ring in shared memory; the warp that consumed a stage re-arms it, so no cross-warp sync exists.
+// Needs X even (16-byte alignment of every row segment); otherwise the host launches k_sweep_dense_ldg.
+template <bool LATTICE>
+__global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
+    if (p.ctrl[C_STATUS] != RUNNING) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *s_dbits = (uint32_t *)smem_raw;
+    const int dbits_bytes = (p.LW * 4 + 127) & ~127;
+    uint64_t *bars = (uint64_t *)(smem_raw + dbits_bytes);                                     // [DENSE_WARPS][DENSE_STAGES]
+    double *stages = (double *)(smem_raw + dbits_bytes + ((DENSE_WARPS * DENSE_STAGES * 8 + 127) & ~127));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < p.LW; i += DENSE_WARPS * 32) s_dbits[i] = p.dbits[i];
+    uint64_t *mybar = bars + warp * DENSE_STAGES;
+    double *mystage = stages + (size_t)warp * DENSE_STAGES * (STAGE_BYTES / 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < DENSE_STAGES; ++s) mbar_init(mybar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
+    const long long nwarps = (long long)gridDim.x * DENSE_WARPS;
+    const long long u0 = (long long)blockIdx.x * DENSE_WARPS + warp;
+    RowCursor pre, cur;
+    pre.start(p, u0, nunits, nwarps, zlo, nyb);
+    cur.start(p, u0, nunits, nwarps, zlo, nyb);
+    auto issue = [&](const RowCursor &rc, int s) {  // lane 0 only
+        const int x0 = rc.un.sg * WORDS_PER_WARP * 32;
+        const uint32_t bytes = (uint32_t)min(WORDS_PER_WARP * 32, p.X - x0) * 8u;
+        const double *src = p.data + (long long)rc.un.zl * p.plane_vox + (long long)rc.y * p.X + x0;
+        mbar_expect_tx(mybar + s, bytes);
+        tma_bulk_load(mystage + (size_t)s * (STAGE_BYTES / 8), src, bytes, mybar + s);
+    };
+#pragma unroll
+    for (int s = 0; s < DENSE_STAGES; ++s) {
+        if (pre.valid()) {
+            if (lane == 0) issue(pre, s);
+            pre.next(p);
+        }
+    }
+    int stage = 0;
+    uint32_t parity = 0;
+    long long flips = 0;
+    Strip st;
+    int c0 = 0;
+    bool own = false;
+    while (cur.valid()) {
+        const int y = cur.y;
+        if (y == cur.un.y0) {  // new unit: (re)start the window
+            c0 = cur.un.sg * WORDS_PER_WARP - 1;
+            own = cur.un.zl >= p.own_lo && cur.un.zl < p.own_hi;
+            st.begin(p, cur.un.zl, cur.un.y0, c0 + lane, lane);
+        }
+        uint32_t s, inner, outer;
+        st.step(y, s, inner, outer);
+        const long long widx = (long long)cur.un.zl * p.plane_words + (long long)y * p.WP + c0 + lane;
+        if (p.E != nullptr && outer) outer &= ~p.E[widx];
+        const uint32_t band = inner | outer;
+        // decision bit of every voxel of the row segment: word j of the segment ends up in lane j + 1
+        const int nvox = min(WORDS_PER_WARP * 32, p.X - (c0 + 1) * 32);
+        const int nfull = nvox >> 5;
+        const double *sv = mystage + (size_t)stage * (STAGE_BYTES / 8) + lane;
+        mbar_wait(mybar + stage, parity);
+        uint32_t D = 0;
+#pragma unroll
+        for (int j = 0; j < WORDS_PER_WARP; ++j) {
+            if (j >= nfull) break;  // warp-uniform
+            const int l = level_of<LATTICE>(p, sv[j * 32]);
+            const unsigned word = __ballot_sync(FULL, (s_dbits[l >> 5] >> (l & 31)) & 1u);
+            if (lane == j + 1) D = word;
+        }
+        if (nvox & 31) {  // ragged last word: lanes past the row end read nothing
+            const double v = lane < (nvox & 31) ? sv[nfull * 32] : p.lev0;
+            const int l = level_of<LATTICE>(p, v);
+            const unsigned word = __ballot_sync(FULL, (s_dbits[l >> 5] >> (l & 31)) & 1u);
+            if (lane == nfull + 1) D = word;
+        }
+        __syncwarp();
+        if (pre.valid()) {  // the stage is drained (values are in registers): re-arm it for a later row
+            if (lane == 0) issue(pre, stage);
+            pre.next(p);
+        }
+        if (++stage == DENSE_STAGES) { stage = 0; parity ^= 1u; }
+        const uint32_t f = band & (D ^ s);
+        store_flips(p, widx, ((long long)cur.un.zl * p.Y + y) * p.nseg + cur.un.sg, f, st.active, lane);
+        if (own) flips += __popc(f);
+        cur.next(p);
+    }
+    flips = warp_sum(flips);
+    if (lane == 0 && flips) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_FLIPS], (unsigned long long)flips);
+}
+
+// Fallback of the dense sweep for odd X (row segments not 16-byte aligned): plain coalesced 8-byte loads.
+template <bool LATTICE>
+__global__ void __launch_bounds__(BLOCK) k_sweep_dense_ldg(Params p) {
+    if (p.ctrl[C_STATUS] != RUNNING) return;
+    extern __shared__ uint32_t s_dbits[];
+    for (int i = threadIdx.x; i < p.LW; i += BLOCK) s_dbits[i] = p.dbits[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
+    const long long nwarps = (long long)gridDim.x * WARPS;
+    long long flips = 0;
+    Strip st;
+    for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+        const Unit un = decode_unit(p, u, zlo, nyb);
+        const int c0 = un.sg * WORDS_PER_WARP - 1, c = c0 + lane;
+        const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
+        st.begin(p, un.zl, un.y0, c, lane);
+        for (int y = un.y0; y < un.y1; ++y) {
+            uint32_t s, inner, outer;
+            st.step(y, s, inner, outer);
+            const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
+            if (p.E != nullptr && outer) outer &= ~p.E[widx];
+            const uint32_t band = inner | outer;
+            const int xlane = (c0 + 1) * 32 + lane;
+            const double *drow = p.data + (long long)un.zl * p.plane_vox + (long long)y * p.X + xlane;
+            uint32_t D = 0;
+            constexpr int U = 10;
+#pragma unroll
+            for (int jb = 0; jb < WORDS_PER_WARP; jb += U) {
+                if (c0 + 1 + jb >= p.XW) break;  // warp-uniform
+                double v[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) v[k] = (xlane + (jb + k) * 32 < p.X) ? drow[(jb + k) * 32] : p.lev0;
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const int l = level_of<LATTICE>(p, v[k]);
+                    const unsigned word = __ballot_sync(FULL, (s_dbits[l >> 5] >> (l & 31)) & 1u);
+                    if (lane == jb + k + 1) D = word;
+                }
+            }
+            const uint32_t f = band & (D ^ s);
+            store_flips(p, widx, ((long long)un.zl * p.Y + y) * p.nseg + un.sg, f, st.active, lane);
+            if (own) flips += __popc(f);
         }
     }
     flips = warp_sum(flips);
@@ -297,7 +504,7 @@ __device__ __forceinline__ void for_flagged_rows(const Params &p, int zlo, int z
 // iteration (VRG:183-190 then VRG:198).  Rewrites F to the executed flips (race-free: only non-segmented bits are
 // cleared, neighbours read F & S), keeps the cancelled ones in C for the absorb rule, and applies the integer
 // histogram deltas that replace the reference's incremental float sums (VRG:232-247).
-template <int MODE>
+template <int MODE, bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
     const int lane = threadIdx.x & 31;
@@ -337,14 +544,14 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
             uint32_t m = r;
             while (m) {
                 const int b = __ffs(m) - 1; m &= m - 1;
-                const int l = level_at<MODE>(p, rowvox + b);
+                const int l = level_at<MODE, LATTICE>(p, rowvox + b);
                 atomicAdd(&hin[l], ~0ull);
                 atomicAdd(&hout[l], 1ull);
             }
             m = a;
             while (m) {
                 const int b = __ffs(m) - 1; m &= m - 1;
-                const int l = level_at<MODE>(p, rowvox + b);
+                const int l = level_at<MODE, LATTICE>(p, rowvox + b);
                 atomicAdd(&hin[l], 1ull);
                 atomicAdd(&hout[l], ~0ull);
             }
@@ -384,7 +591,7 @@ __global__ void __launch_bounds__(BLOCK) k_flip(Params p) {
 // ---------------------------------------------------------------------------------------------
 // k_absorb: excluded voxels within 1 of any listed flip (executed or cancelled), or within 2 of an executed flip,
 // become outside (VRG:167-168, 177-179, 207-208).  Runs after k_cancel (and the F/C halo exchange).
-template <int MODE>
+template <int MODE, bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_absorb(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
     const int lane = threadIdx.x & 31;
@@ -404,7 +611,9 @@ __global__ void __launch_bounds__(BLOCK) k_absorb(Params p) {
             if (zz >= p.valid_lo && zz < p.valid_hi && yy >= 0 && yy < p.Y && ss >= 0 && ss < p.nseg)
                 near |= p.rowflag[((long long)zz * p.Y + yy) * p.nseg + ss] != 0;
         }
-        if (!__ballot_sync(FULL, near)) continue;
+        // halo planes beyond +-1 carry no row flags of their own (their F comes from the neighbour slab)
+        const bool halo_near = (zl - 2 < p.own_lo - 1 && zl - 2 >= p.valid_lo) || (zl + 2 > p.own_hi && zl + 2 < p.valid_hi);
+        if (!__ballot_sync(FULL, near) && !halo_near) continue;
         const int c = sg * WORDS_PER_WARP - 1 + lane;
         const bool inr = c >= 0 && c < p.XW;
         const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
@@ -433,7 +642,7 @@ __global__ void __launch_bounds__(BLOCK) k_absorb(Params p) {
         const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
         while (ab) {
             const int b = __ffs(ab) - 1; ab &= ab - 1;
-            atomicAdd(&hout[level_at<MODE>(p, rowvox + b)], 1ull);  // addedPoints, VRG:235,247
+            atomicAdd(&hout[level_at<MODE, LATTICE>(p, rowvox + b)], 1ull);  // addedPoints, VRG:235,247
         }
     }
     n_abs = warp_sum(n_abs);
@@ -464,7 +673,7 @@ __global__ void k_advance(Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// init branch of update(), VRG:129-145: bit-planes from the uint8 valueMap, 16 voxels per lane-load
+// init branch of update(), VRG:129-145: bit-planes from the uint8 valueMap, one word (32 voxels) per thread
 __global__ void __launch_bounds__(BLOCK) k_init_planes(Params p, const uint8_t *__restrict__ vm, uint32_t *eraw) {
     const long long nw = (long long)(p.valid_hi - p.valid_lo) * p.Y * p.XW;
     bool bad = false;
@@ -511,37 +720,30 @@ __global__ void __launch_bounds__(BLOCK) k_init_planes(Params p, const uint8_t *
 __global__ void __launch_bounds__(BLOCK) k_init_bands(Params p) {
     const int lane = threadIdx.x & 31;
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
-    const long long nrows = (long long)(zhi - zlo) * p.Y * p.nseg;
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
     const long long nwarps = (long long)gridDim.x * WARPS;
     long long nband = 0;
-    for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
-        const int sg = (int)(r % p.nseg);
-        const long long t = r / p.nseg;
-        const int y = (int)(t % p.Y), zl = zlo + (int)(t / p.Y);
-        const int c = sg * WORDS_PER_WARP - 1 + lane;
-        const bool inr = c >= 0 && c < p.XW;
-        const uint32_t vm = inr ? valid_mask(p, c) : 0u;
-        uint32_t vs = 0, vn = 0, s = 0;
-        if (inr) {
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int zz = zl + dz;
-                if (zz < p.valid_lo || zz >= p.valid_hi) continue;
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int yy = y + dy;
-                    if (yy < 0 || yy >= p.Y) continue;
-                    const uint32_t w = p.S[(long long)zz * p.plane_words + (long long)yy * p.WP + c];
-                    vs |= w; vn |= ~w & vm;
-                    if (dz == 0 && dy == 0) s = w;
-                }
+    Strip st;
+    for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+        const Unit un = decode_unit(p, u, zlo, nyb);
+        const int c = un.sg * WORDS_PER_WARP - 1 + lane;
+        const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
+        st.begin(p, un.zl, un.y0, c, lane);
+        for (int y = un.y0; y < un.y1; ++y) {
+            uint32_t s, inner, outer;
+            st.step(y, s, inner, outer);
+            if (!st.active) continue;
+            const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
+            if (p.E) {
+                const uint32_t eraw = p.E[widx];
+                // ~s & vm & dil_s == outer, so the excluded voxels next to a seed are eraw & outer
+                const uint32_t e = eraw & ~outer;
+                if (e != eraw) p.E[widx] = e;
+                outer &= ~e;
             }
+            if (own) nband += __popc(inner) + __popc(outer);
         }
-        const uint32_t dil_s = dilate_x1(vs), dil_n = dilate_x1(vn);
-        const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
-        if (!active) continue;
-        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
-        uint32_t e = 0;
-        if (p.E) { e = p.E[widx] & ~dil_s; p.E[widx] = e; }
-        if (zl >= p.own_lo && zl < p.own_hi) nband += __popc(s & dil_n) + __popc(~s & vm & ~e & dil_s);
     }
     nband = warp_sum(nband);
     if (lane == 0 && nband) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_BAND], (unsigned long long)nband);
@@ -549,7 +751,7 @@ __global__ void __launch_bounds__(BLOCK) k_init_bands(Params p) {
 
 // region histograms and sizes over own planes (VRG:49-52, 149-150 as integer counts).
 // Per-warp private shared histograms keep the shared-memory atomics off the few hot background levels.
-template <int MODE>
+template <int MODE, bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_init_hist(Params p, int copies) {
     extern __shared__ unsigned int s_h[];  // [copies][2L] when copies > 0
     for (int i = threadIdx.x; i < copies * 2 * p.L; i += BLOCK) s_h[i] = 0;
@@ -568,7 +770,7 @@ __global__ void __launch_bounds__(BLOCK) k_init_hist(Params p, int copies) {
         const uint32_t s = p.S[widx], e = p.E ? p.E[widx] : 0u;
         const int x = c * 32 + lane;
         if (x >= p.X) continue;
-        const int l = level_at<MODE>(p, (long long)zl * p.plane_vox + (long long)y * p.X + x);
+        const int l = level_at<MODE, LATTICE>(p, (long long)zl * p.plane_vox + (long long)y * p.X + x);
         const uint32_t bit = 1u << lane;
         if (s & bit) { n_in++; if (mine) atomicAdd(&mine[l], 1u); else atomicAdd(&hin[l], 1ull); }
         else if (!(e & bit)) { n_out++; if (mine) atomicAdd(&mine[p.L + l], 1u); else atomicAdd(&hout[l], 1ull); }
@@ -622,64 +824,53 @@ __global__ void __launch_bounds__(BLOCK) k_scan_levels(const double *__restrict_
     }
 }
 
+template <bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_build_index(Params p, const double *__restrict__ data, uint16_t *index, long long n) {
     for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK)
-        index[i] = (uint16_t)level_of(p, data[i]);
+        index[i] = (uint16_t)level_of<LATTICE>(p, data[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
 // outputs: canonical labels (VRG:21) or the 0/1 segmented map, one byte per voxel, own planes only
 __global__ void __launch_bounds__(BLOCK) k_labels(Params p, uint8_t *__restrict__ out, int seg_only) {
     const int lane = threadIdx.x & 31;
-    const long long nrows = (long long)(p.own_hi - p.own_lo) * p.Y * p.nseg;
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    const long long nunits = (long long)(p.own_hi - p.own_lo) * nyb * p.nseg;
     const long long nwarps = (long long)gridDim.x * WARPS;
-    for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
-        const int sg = (int)(r % p.nseg);
-        const long long t = r / p.nseg;
-        const int y = (int)(t % p.Y), zl = p.own_lo + (int)(t / p.Y);
-        const int c0 = sg * WORDS_PER_WARP - 1, c = c0 + lane;
-        const bool inr = c >= 0 && c < p.XW;
-        const uint32_t vm = inr ? valid_mask(p, c) : 0u;
-        uint32_t vs = 0, vn = 0, s = 0;
-        if (inr) {
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int zz = zl + dz;
-                if (zz < p.valid_lo || zz >= p.valid_hi) continue;
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int yy = y + dy;
-                    if (yy < 0 || yy >= p.Y) continue;
-                    const uint32_t w = p.S[(long long)zz * p.plane_words + (long long)yy * p.WP + c];
-                    vs |= w; vn |= ~w & vm;
-                    if (dz == 0 && dy == 0) s = w;
-                }
-            }
-        }
-        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
-        const uint32_t e = (p.E && inr) ? p.E[widx] : 0u;
-        const uint32_t dil_s = dilate_x1(vs), dil_n = dilate_x1(vn);
-        const uint32_t inner = s & dil_n, outer = ~s & ~e & dil_s;
-        // 4 voxels (bytes) per lane and store: a warp writes 128 consecutive voxels = 4 words per step
-        uint8_t *rowout = out + ((long long)(zl - p.own_lo) * p.Y + y) * p.X;
-        for (int j0 = 1; j0 <= WORDS_PER_WARP; j0 += 4) {
-            if (c0 + j0 >= p.XW) break;
-            const int src = j0 + (lane >> 3);  // lane that holds this lane's word
-            const uint32_t sj = __shfl_sync(FULL, s, src), ij = __shfl_sync(FULL, inner, src);
-            const uint32_t oj = __shfl_sync(FULL, outer, src), ej = __shfl_sync(FULL, e, src);
-            if (src > WORDS_PER_WARP) continue;
-            const int x = (c0 + src) * 32 + (lane & 7) * 4;
-            uint32_t pack = 0;
+    Strip st;
+    for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+        const Unit un = decode_unit(p, u, p.own_lo, nyb);
+        const int c0 = un.sg * WORDS_PER_WARP - 1, c = c0 + lane;
+        st.begin(p, un.zl, un.y0, c, lane);
+        for (int y = un.y0; y < un.y1; ++y) {
+            uint32_t s, inner, outer;
+            st.step(y, s, inner, outer);
+            const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
+            const uint32_t e = (p.E && st.active) ? p.E[widx] : 0u;
+            outer &= ~e;
+            // 4 voxels (bytes) per lane and store: a warp writes 128 consecutive voxels = 4 words per step
+            uint8_t *rowout = out + ((long long)(un.zl - p.own_lo) * p.Y + y) * p.X;
+            for (int j0 = 1; j0 <= WORDS_PER_WARP; j0 += 4) {
+                if (c0 + j0 >= p.XW) break;
+                const int src = j0 + (lane >> 3);  // lane that holds this lane's word
+                const uint32_t sj = __shfl_sync(FULL, s, src), ij = __shfl_sync(FULL, inner, src);
+                const uint32_t oj = __shfl_sync(FULL, outer, src), ej = __shfl_sync(FULL, e, src);
+                if (src > WORDS_PER_WARP) continue;
+                const int x = (c0 + src) * 32 + (lane & 7) * 4;
+                uint32_t pack = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t bit = 1u << ((lane & 7) * 4 + b);
-                uint32_t lab;
-                if (seg_only) lab = (sj & bit) ? 1u : 0u;
-                else lab = (sj & bit) ? ((ij & bit) ? 1u : 0u) : ((ej & bit) ? 4u : ((oj & bit) ? 2u : 3u));
-                pack |= lab << (8 * b);
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t bit = 1u << ((lane & 7) * 4 + b);
+                    uint32_t lab;
+                    if (seg_only) lab = (sj & bit) ? 1u : 0u;
+                    else lab = (sj & bit) ? ((ij & bit) ? 1u : 0u) : ((ej & bit) ? 4u : ((oj & bit) ? 2u : 3u));
+                    pack |= lab << (8 * b);
+                }
+                if (x + 3 < p.X && ((((uintptr_t)(rowout + x)) & 3) == 0)) *(uint32_t *)(rowout + x) = pack;
+                else
+                    for (int b = 0; b < 4; ++b)
+                        if (x + b < p.X) rowout[x + b] = (uint8_t)(pack >> (8 * b));
             }
-            if (x + 3 < p.X && ((((uintptr_t)(rowout + x)) & 3) == 0)) *(uint32_t *)(rowout + x) = pack;
-            else
-                for (int b = 0; b < 4; ++b)
-                    if (x + b < p.X) rowout[x + b] = (uint8_t)(pack >> (8 * b));
         }
     }
 }
