@@ -49,6 +49,7 @@ struct Params {
     // state
     uint32_t *S, *E, *F, *C;          // E, C: nullptr when the run never had label 4
     uint8_t *rowflag;                 // [nzl * Y * nseg]
+    int *front;                       // [1 + own rows * nseg]: front[0] = count, then the flagged own-plane rows of this sweep
     const double *data;               // fp64 intensities, local planes
     const uint16_t *index;            // level index volume (MODE_INDEX)
     // levels / table
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctrl[C_APPLY] = n_in < p.ctrl[C_MAX_SEG];  // cap is tested before the flips are applied, VRG:101
         p.lstats[2 * p.L + ST_N_FLIPS] = 0;
+        p.front[0] = 0;
     }
     __shared__ uint32_t s_bits[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,7 +217,9 @@ __device__ __forceinline__ Unit decode_unit(const Params &p, long long u, int zl
 }
 
 // writes the flip word of a row segment; rows away from the front cost no store (warp-uniform branch)
-__device__ __forceinline__ void store_flips(const Params &p, long long widx, long long ridx, uint32_t f, bool active, int lane) {
+// and appends own-plane rows that flip to the front list, which k_cancel / k_flip consume one row per warp
+// (rows at the front are spatially clustered; a list spreads them evenly over the machine).
+__device__ __forceinline__ void store_flips(const Params &p, long long widx, long long ridx, uint32_t f, bool active, bool own, int lane) {
     const bool any = __ballot_sync(FULL, f != 0u) != 0u;
     const uint8_t was = p.rowflag[ridx];
     if (any || was) {
@@ -223,7 +227,10 @@ __device__ __forceinline__ void store_flips(const Params &p, long long widx, lon
             p.F[widx] = f;
             if (p.C != nullptr) p.C[widx] = 0u;  // k_cancel refills it for rows that still flip
         }
-        if (lane == 0 && (any != (was != 0))) p.rowflag[ridx] = any ? 1 : 0;
+        if (lane == 0) {
+            if (any != (was != 0)) p.rowflag[ridx] = any ? 1 : 0;
+            if (any && own) p.front[1 + atomicAdd(&p.front[0], 1)] = (int)ridx;
+        }
     }
 }
 
@@ -282,7 +289,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
                 }
             }
             const uint32_t f = band & (D ^ s);  // inner band leaves iff in < out, outer band enters iff in >= out
-            store_flips(p, widx, ((long long)un.zl * p.Y + y) * p.nseg + un.sg, f, st.active, lane);
+            store_flips(p, widx, ((long long)un.zl * p.Y + y) * p.nseg + un.sg, f, st.active, own, lane);
             if (own) flips += __popc(f);
         }
     }
@@ -420,7 +427,7 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         }
         if (++stage == DENSE_STAGES) { stage = 0; parity ^= 1u; }
         const uint32_t f = band & (D ^ s);
-        store_flips(p, widx, ((long long)cur.un.zl * p.Y + y) * p.nseg + cur.un.sg, f, st.active, lane);
+        store_flips(p, widx, ((long long)cur.un.zl * p.Y + y) * p.nseg + cur.un.sg, f, st.active, own, lane);
         if (own) flips += __popc(f);
         cur.next(p);
     }
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_dense_ldg(Params p) {
                 }
             }
             const uint32_t f = band & (D ^ s);
-            store_flips(p, widx, ((long long)un.zl * p.Y + y) * p.nseg + un.sg, f, st.active, lane);
+            store_flips(p, widx, ((long long)un.zl * p.Y + y) * p.nseg + un.sg, f, st.active, own, lane);
             if (own) flips += __popc(f);
         }
     }
@@ -480,23 +487,15 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_dense_ldg(Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Rows whose flag is set, enumerated 32 at a time per warp: calls fn(zl, y, sg) warp-uniformly.
+// The front list: own-plane row segments whose flip word is non-zero; calls fn(zl, y, sg) warp-uniformly, one row per warp.
 template <typename Fn>
-__device__ __forceinline__ void for_flagged_rows(const Params &p, int zlo, int zhi, Fn fn) {
-    const int lane = threadIdx.x & 31;
-    const long long base = (long long)zlo * p.Y * p.nseg, nrows = (long long)(zhi - zlo) * p.Y * p.nseg;
-    const long long nchunks = (nrows + 31) / 32, nwarps = (long long)gridDim.x * WARPS;
-    for (long long k = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); k < nchunks; k += nwarps) {
-        const long long r = k * 32 + lane;
-        unsigned m = __ballot_sync(FULL, r < nrows && p.rowflag[base + r] != 0);
-        while (m) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1;
-            const long long rr = base + k * 32 + j;
-            const int sg = (int)(rr % p.nseg);
-            const long long t = rr / p.nseg;
-            fn((int)(t / p.Y), (int)(t % p.Y), sg);
-        }
+__device__ __forceinline__ void for_front_rows(const Params &p, Fn fn) {
+    const int n = p.front[0];
+    const int nwarps = gridDim.x * WARPS;
+    for (int k = blockIdx.x * WARPS + (threadIdx.x >> 5); k < n; k += nwarps) {
+        const int rr = p.front[1 + k];
+        const int sg = rr % p.nseg, t = rr / p.nseg;
+        fn(t / p.Y, t % p.Y, sg);
     }
 }
 
@@ -510,7 +509,7 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
     const int lane = threadIdx.x & 31;
     long long d_in = 0;
     unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
-    for_flagged_rows(p, p.own_lo, p.own_hi, [&](int zl, int y, int sg) {
+    for_front_rows(p, [&](int zl, int y, int sg) {
         const int c = sg * WORDS_PER_WARP - 1 + lane;
         const bool inr = c >= 0 && c < p.XW;
         const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
@@ -568,7 +567,7 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
 __global__ void __launch_bounds__(BLOCK) k_flip(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
     const int lane = threadIdx.x & 31;
-    for_flagged_rows(p, p.own_lo, p.own_hi, [&](int zl, int y, int sg) {
+    for_front_rows(p, [&](int zl, int y, int sg) {
         const int c = sg * WORDS_PER_WARP + lane;
         if (lane < WORDS_PER_WARP && c < p.XW) {
             const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;

@@ -10,9 +10,9 @@ for mode in f64_dense f64_band index; do
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${mode}.csv \
       python scripts/profile_step.py --workload c3 --intensity $mode --iters 10 > gpurun_out/prof_${mode}.log 2>&1
 done
-ncu --set full --clock-control none --import-source on -k regex:k_decide -s 4 -c 2 -f -o gpurun_out/decide_dense \
+ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 4 -c 2 -f -o gpurun_out/decide_dense \
     python scripts/profile_step.py --workload c3 --intensity f64_dense --iters 8 > gpurun_out/ncu_dense.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_decide -s 4 -c 2 -f -o gpurun_out/decide_band \
+ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 4 -c 2 -f -o gpurun_out/decide_band \
     python scripts/profile_step.py --workload c3 --intensity f64_band --iters 8 > gpurun_out/ncu_band.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_cancel -s 4 -c 1 -f -o gpurun_out/cancel \
     python scripts/profile_step.py --workload c3 --intensity f64_band --iters 8 > gpurun_out/ncu_cancel.log 2>&1
