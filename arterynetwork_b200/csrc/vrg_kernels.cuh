@@ -81,6 +81,18 @@ __device__ __forceinline__ uint32_t dilate_x2(uint32_t v) {
     return v | __funnelshift_l(l, v, 1) | __funnelshift_r(v, r, 1) | __funnelshift_l(l, v, 2) | __funnelshift_r(v, r, 2);
 }
 
+// 32x32 bit-matrix transpose across a warp: in = row `lane`, out = column `lane` (5 butterfly steps)
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+        const uint32_t m = k == 16 ? 0x0000FFFFu : k == 8 ? 0x00FF00FFu : k == 4 ? 0x0F0F0F0Fu : k == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(FULL, x, k);
+        // lanes with bit k clear keep their low half-blocks and take the partner's low half-blocks as high ones
+        x = (lane & k) ? ((x & ~m) | ((y >> k) & m)) : ((x & m) | ((y << k) & ~m));
+    }
+    return x;
+}
+
 // intensity -> table slot.  LATTICE: levels sit on lev0 + k*step, one DADD + one DFMA (round-to-nearest via the
 // 2^52+2^51 trick: the integer lands in the low word).  Otherwise a binary search over the sorted levels.
 template <bool LATTICE>
@@ -355,11 +367,14 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     for (int i = threadIdx.x; i < p.LW; i += DENSE_WARPS * 32) s_dbits[i] = p.dbits[i];
     uint64_t *mybar = bars + warp * DENSE_STAGES;
     double *mystage = stages + (size_t)warp * DENSE_STAGES * (STAGE_BYTES / 8);
+    // stages start out holding a valid intensity everywhere: a row shorter than 960 voxels leaves the rest untouched
+    for (int i = lane; i < DENSE_STAGES * (STAGE_BYTES / 8); i += 32) mystage[i] = p.lev0;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < DENSE_STAGES; ++s) mbar_init(mybar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy fill before the async-proxy copies
     __syncthreads();
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
     const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
@@ -401,25 +416,20 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         const long long widx = (long long)cur.un.zl * p.plane_words + (long long)y * p.WP + c0 + lane;
         if (p.E != nullptr && outer) outer &= ~p.E[widx];
         const uint32_t band = inner | outer;
-        // decision bit of every voxel of the row segment: word j of the segment ends up in lane j + 1
-        const int nvox = min(WORDS_PER_WARP * 32, p.X - (c0 + 1) * 32);
-        const int nfull = nvox >> 5;
+        // decision bit of every voxel of the row segment: word j of the segment ends up in lane j + 1.
+        // Branch-free over all 30 words (the stage beyond the row end holds valid intensities, see the fill above;
+        // their bits are masked by the band), so the compiler interleaves the words' dependency chains.
         const double *sv = mystage + (size_t)stage * (STAGE_BYTES / 8) + lane;
         mbar_wait(mybar + stage, parity);
-        uint32_t D = 0;
+        // phase 1 (no convergence points, so the 30 dependency chains overlap): bit j+1 of `mine` = decision of this
+        // lane's voxel in word j;  phase 2: 32x32 bit transpose across the warp, lane j+1 ends up with word j.
+        uint32_t mine = 0;
 #pragma unroll
         for (int j = 0; j < WORDS_PER_WARP; ++j) {
-            if (j >= nfull) break;  // warp-uniform
             const int l = level_of<LATTICE>(p, sv[j * 32]);
-            const unsigned word = __ballot_sync(FULL, (s_dbits[l >> 5] >> (l & 31)) & 1u);
-            if (lane == j + 1) D = word;
+            mine |= ((s_dbits[l >> 5] >> (l & 31)) & 1u) << (j + 1);
         }
-        if (nvox & 31) {  // ragged last word: lanes past the row end read nothing
-            const double v = lane < (nvox & 31) ? sv[nfull * 32] : p.lev0;
-            const int l = level_of<LATTICE>(p, v);
-            const unsigned word = __ballot_sync(FULL, (s_dbits[l >> 5] >> (l & 31)) & 1u);
-            if (lane == nfull + 1) D = word;
-        }
+        const uint32_t D = transpose32(mine, lane);
         __syncwarp();
         if (pre.valid()) {  // the stage is drained (values are in registers): re-arm it for a later row
             if (lane == 0) issue(pre, stage);
