@@ -43,7 +43,8 @@ struct vrg_handle {
     size_t plane_bytes = 0;                      // one bit-plane buffer (all local planes)
     size_t rowflag_bytes = 0;
     double *d_data = nullptr;
-    uint8_t *d_vm = nullptr, *d_rowflag = nullptr, *d_labels = nullptr;
+    uint8_t *d_vm = nullptr, *d_rowflag = nullptr, *d_labels = nullptr, *d_unitmap = nullptr;
+    size_t unitmap_bytes = 0;
     int *d_front = nullptr;
     uint16_t *d_index = nullptr;
     uint32_t *d_S = nullptr, *d_E = nullptr, *d_F = nullptr, *d_C = nullptr;
@@ -167,6 +168,8 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     alloc((void **)&h->d_F, h->plane_bytes);
     alloc((void **)&h->d_C, h->plane_bytes);
     alloc((void **)&h->d_rowflag, h->rowflag_bytes);
+    h->unitmap_bytes = (size_t)p.nzl * ((Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT) * p.nseg;
+    alloc((void **)&h->d_unitmap, h->unitmap_bytes);
     alloc((void **)&h->d_front, (1 + (size_t)h->nz_own * Y * p.nseg) * sizeof(int));
     alloc((void **)&h->d_ctrl, C_WORDS * sizeof(long long));
     alloc((void **)&h->d_trace, 3 * (cfg->iter_max + 2) * sizeof(long long));
@@ -181,7 +184,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     // planes outside the volume must read as neutral forever
     CK(cudaMemsetAsync(h->d_data, 0, nvox * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_vm, 3, nvox, h->stream));
-    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag; p.front = h->d_front;
+    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag; p.front = h->d_front; p.unitmap = h->d_unitmap;
     p.data = h->d_data;
     p.ctrl = h->d_ctrl; p.trace = h->d_trace;
     *out = h;
@@ -193,7 +196,7 @@ int vrg_destroy(vrg_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_data); cudaFree(h->d_vm); cudaFree(h->d_index); cudaFree(h->d_labels);
-    cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front);
+    cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap);
     cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
     free_levels(h);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -384,6 +387,7 @@ int vrg_init(vrg_handle *h) {
     CK(cudaMemsetAsync(h->d_C, 0, h->plane_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_rowflag, 0, h->rowflag_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_front, 0, sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_unitmap, 0, h->unitmap_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_lstats, 0, (size_t)(2 * p.L + ST_EXTRA) * sizeof(long long), h->stream));
     CK(cudaMemsetAsync(h->d_trace, 0, 3 * (h->cfg.iter_max + 2) * sizeof(long long), h->stream));
     long long c[C_WORDS];

@@ -49,6 +49,7 @@ struct Params {
     // state
     uint32_t *S, *E, *F, *C;          // E, C: nullptr when the run never had label 4
     uint8_t *rowflag;                 // [nzl * Y * nseg]
+    uint8_t *unitmap;                 // [nzl * nyb * nseg]: 1 if the sweep unit ever held a segmented voxel (never cleared)
     int *front;                       // [1 + own rows * nseg]: front[0] = count, then the flagged own-plane rows of this sweep
     const double *data;               // fp64 intensities, local planes
     const uint16_t *index;            // level index volume (MODE_INDEX)
@@ -217,6 +218,23 @@ struct Strip {
     }
 };
 
+__device__ __forceinline__ long long unit_index(const Params &p, int zl, int y, int c) {
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    return ((long long)zl * nyb + y / ROWS_PER_UNIT) * p.nseg + c / WORDS_PER_WARP;
+}
+// A unit can hold a band voxel only if it or one of its 26 neighbour units (z, y-block, x-segment) holds a segmented
+// voxel: far from every vessel the band sweep skips the unit after 27 byte loads.
+__device__ __forceinline__ bool unit_near_segmented(const Params &p, int zl, int y0, int sg, int lane) {
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    bool hit = false;
+    if (lane < 27) {
+        const int zz = zl + lane / 9 - 1, yb = y0 / ROWS_PER_UNIT + (lane / 3) % 3 - 1, ss = sg + lane % 3 - 1;
+        if (zz >= p.valid_lo && zz < p.valid_hi && yb >= 0 && yb < nyb && ss >= 0 && ss < p.nseg)
+            hit = p.unitmap[((long long)zz * nyb + yb) * p.nseg + ss] != 0;
+    }
+    return __ballot_sync(FULL, hit) != 0u;
+}
+
 struct Unit { int zl, y0, y1, sg; };
 __device__ __forceinline__ Unit decode_unit(const Params &p, long long u, int zlo, int nyb) {
     Unit r;
@@ -267,6 +285,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
     Strip st;
     for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
         const Unit un = decode_unit(p, u, zlo, nyb);
+        if (!unit_near_segmented(p, un.zl, un.y0, un.sg, lane)) continue;
         const int c0 = un.sg * WORDS_PER_WARP - 1, c = c0 + lane;
         const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
         st.begin(p, un.zl, un.y0, c, lane);
@@ -581,7 +600,11 @@ __global__ void __launch_bounds__(BLOCK) k_flip(Params p) {
         const int c = sg * WORDS_PER_WARP + lane;
         if (lane < WORDS_PER_WARP && c < p.XW) {
             const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
-            p.S[widx] ^= p.F[widx];
+            const uint32_t f = p.F[widx];
+            if (f) {
+                p.S[widx] ^= f;
+                p.unitmap[unit_index(p, zl, y, c)] = 1;
+            }
         }
     });
     const long long tid = (long long)blockIdx.x * BLOCK + threadIdx.x, nth = (long long)gridDim.x * BLOCK;
@@ -592,7 +615,12 @@ __global__ void __launch_bounds__(BLOCK) k_flip(Params p) {
         const long long b = (long long)zlo * p.plane_words, n = (long long)(zhi - zlo) * p.plane_words;
         for (long long i = tid; i < n; i += nth) {
             const uint32_t f = p.F[b + i];
-            if (f) p.S[b + i] ^= f;
+            if (f) {
+                p.S[b + i] ^= f;
+                const long long w = b + i;
+                const int zl = (int)(w / p.plane_words), y = (int)((w % p.plane_words) / p.WP), c = (int)(w % p.WP);
+                p.unitmap[unit_index(p, zl, y, c)] = 1;
+            }
         }
     }
 }
@@ -720,6 +748,7 @@ __global__ void __launch_bounds__(BLOCK) k_init_planes(Params p, const uint8_t *
         }
         const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
         p.S[widx] = s;
+        if (s) p.unitmap[unit_index(p, zl, y, c)] = 1;
         if (eraw) eraw[widx] = e;
     }
     if (bad) p.lstats[2 * p.L + ST_BAD_LABEL] = 1;
