@@ -45,7 +45,8 @@ struct vrg_handle {
     double *d_data = nullptr;
     uint8_t *d_vm = nullptr, *d_rowflag = nullptr, *d_labels = nullptr, *d_unitmap = nullptr;
     size_t unitmap_bytes = 0;
-    int *d_front = nullptr;
+    int *d_front = nullptr, *d_ulist = nullptr;
+    int sweep_units = 0;
     uint16_t *d_index = nullptr;
     uint32_t *d_S = nullptr, *d_E = nullptr, *d_F = nullptr, *d_C = nullptr;
     double *d_levels = nullptr, *d_pin = nullptr, *d_pout = nullptr;
@@ -170,6 +171,8 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     alloc((void **)&h->d_rowflag, h->rowflag_bytes);
     h->unitmap_bytes = (size_t)p.nzl * ((Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT) * p.nseg;
     alloc((void **)&h->d_unitmap, h->unitmap_bytes);
+    h->sweep_units = (int)(((size_t)h->nz_own + 2) * ((Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT) * p.nseg);
+    alloc((void **)&h->d_ulist, (1 + (size_t)h->sweep_units) * sizeof(int));
     alloc((void **)&h->d_front, (1 + (size_t)h->nz_own * Y * p.nseg) * sizeof(int));
     alloc((void **)&h->d_ctrl, C_WORDS * sizeof(long long));
     alloc((void **)&h->d_trace, 3 * (cfg->iter_max + 2) * sizeof(long long));
@@ -184,7 +187,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     // planes outside the volume must read as neutral forever
     CK(cudaMemsetAsync(h->d_data, 0, nvox * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_vm, 3, nvox, h->stream));
-    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag; p.front = h->d_front; p.unitmap = h->d_unitmap;
+    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag; p.front = h->d_front; p.unitmap = h->d_unitmap; p.ulist = h->d_ulist;
     p.data = h->d_data;
     p.ctrl = h->d_ctrl; p.trace = h->d_trace;
     *out = h;
@@ -196,7 +199,7 @@ int vrg_destroy(vrg_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_data); cudaFree(h->d_vm); cudaFree(h->d_index); cudaFree(h->d_labels);
-    cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap);
+    cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_ulist);
     cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
     free_levels(h);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -318,17 +321,21 @@ int vrg_set_levels(vrg_handle *h, const double *lv, int64_t n) {
     }
     h->levels = s;
     h->n_distinct = n;
-    free_levels(h);
-    h->separate_gstats = false;
+    // same table size as last time: keep every buffer (stable device pointers: hosts may hold CUDA graphs over them)
+    const bool keep = h->d_levels != nullptr && p.L == (int)table.size();
     p.L = (int)table.size();
     p.LW = (p.L + 31) / 32;
     const size_t sb = (size_t)(2 * p.L + ST_EXTRA) * sizeof(long long);
-    CK(cudaMalloc((void **)&h->d_levels, p.L * sizeof(double)));
-    CK(cudaMalloc((void **)&h->d_pin, p.L * sizeof(double)));
-    CK(cudaMalloc((void **)&h->d_pout, p.L * sizeof(double)));
-    CK(cudaMalloc((void **)&h->d_dbits, p.LW * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&h->d_lstats, sb));
-    h->d_gstats = h->d_lstats;
+    if (!keep) {
+        free_levels(h);
+        h->separate_gstats = false;
+        CK(cudaMalloc((void **)&h->d_levels, p.L * sizeof(double)));
+        CK(cudaMalloc((void **)&h->d_pin, p.L * sizeof(double)));
+        CK(cudaMalloc((void **)&h->d_pout, p.L * sizeof(double)));
+        CK(cudaMalloc((void **)&h->d_dbits, p.LW * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&h->d_lstats, sb));
+        h->d_gstats = h->d_lstats;
+    }
     CK(cudaMemcpyAsync(h->d_levels, table.data(), p.L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d_pin, 0, p.L * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_pout, 0, p.L * sizeof(double), h->stream));
@@ -388,6 +395,7 @@ int vrg_init(vrg_handle *h) {
     CK(cudaMemsetAsync(h->d_rowflag, 0, h->rowflag_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_front, 0, sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_unitmap, 0, h->unitmap_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_ulist, 0, sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_lstats, 0, (size_t)(2 * p.L + ST_EXTRA) * sizeof(long long), h->stream));
     CK(cudaMemsetAsync(h->d_trace, 0, 3 * (h->cfg.iter_max + 2) * sizeof(long long), h->stream));
     long long c[C_WORDS];
@@ -429,7 +437,7 @@ int vrg_init(vrg_handle *h) {
 int vrg_enqueue_decide(vrg_handle *h) {
     NEED_INIT();
     const Params &p = h->p;
-    k_table<<<p.LW, BLOCK, 0, h->stream>>>(p);
+    k_table<<<p.LW + (h->sweep_units + BLOCK - 1) / BLOCK, BLOCK, 0, h->stream>>>(p);
     const size_t smem = (size_t)p.LW * sizeof(uint32_t);
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     if (h->cfg.intensity_mode == VRG_INTENSITY_F64_DENSE) {

@@ -50,6 +50,7 @@ struct Params {
     uint32_t *S, *E, *F, *C;          // E, C: nullptr when the run never had label 4
     uint8_t *rowflag;                 // [nzl * Y * nseg]
     uint8_t *unitmap;                 // [nzl * nyb * nseg]: 1 if the sweep unit ever held a segmented voxel (never cleared)
+    int *ulist;                       // [1 + sweep units]: ulist[0] = count, then the units near a segmented voxel (band sweep)
     int *front;                       // [1 + own rows * nseg]: front[0] = count, then the flagged own-plane rows of this sweep
     const double *data;               // fp64 intensities, local planes
     const uint16_t *index;            // level index volume (MODE_INDEX)
@@ -120,11 +121,52 @@ __device__ __forceinline__ long long warp_sum(long long v) {
     return v;
 }
 
+__device__ __forceinline__ long long unit_index(const Params &p, int zl, int y, int c) {
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    return ((long long)zl * nyb + y / ROWS_PER_UNIT) * p.nseg + c / WORDS_PER_WARP;
+}
+// A sweep unit (one plane, ROWS_PER_UNIT rows, 30 words) can hold a band voxel only if it or one of its 26 neighbour
+// units (z, y-block, x-segment) holds a segmented voxel.  Thread `t` tests unit t of the sweep's unit space
+// (planes own-1 .. own+1) and appends it to the list the band sweep walks: far from every vessel costs nothing.
+__device__ __forceinline__ void build_unit_list(const Params &p, int t) {
+    const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
+    bool hit = false;
+    if (t < nunits) {
+        const int sg = t % p.nseg, yb = (t / p.nseg) % nyb, zl = zlo + (t / p.nseg) / nyb;
+        for (int dz = -1; dz <= 1 && !hit; ++dz) {
+            const int zz = zl + dz;
+            if (zz < p.valid_lo || zz >= p.valid_hi) continue;
+            for (int dy = -1; dy <= 1 && !hit; ++dy) {
+                const int yy = yb + dy;
+                if (yy < 0 || yy >= nyb) continue;
+                for (int ds = -1; ds <= 1; ++ds) {
+                    const int ss = sg + ds;
+                    if (ss >= 0 && ss < p.nseg && p.unitmap[((long long)zz * nyb + yy) * p.nseg + ss]) { hit = true; break; }
+                }
+            }
+        }
+    }
+    const unsigned m = __ballot_sync(FULL, hit);
+    if (m) {
+        int base = 0;
+        const int lane = threadIdx.x & 31;
+        if (lane == 0) base = atomicAdd(&p.ulist[0], __popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (hit) p.ulist[1 + base + __popc(m & ((1u << lane) - 1u))] = t;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_table: one block per 32 levels; a warp sums one level's two Parzen sums over all levels.
 // Fixed order: lane-strided partial sums, then an xor-shuffle tree -> deterministic.
 __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
+    if ((int)blockIdx.x >= p.LW) {  // spare blocks: list of sweep units that can hold a band voxel (see unit_is_active)
+        build_unit_list(p, ((int)blockIdx.x - p.LW) * BLOCK + threadIdx.x);
+        return;
+    }
     const long long *g = p.gstats;
     const long long n_in = g[2 * p.L + ST_N_IN], n_out = g[2 * p.L + ST_N_OUT];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -218,23 +260,6 @@ struct Strip {
     }
 };
 
-__device__ __forceinline__ long long unit_index(const Params &p, int zl, int y, int c) {
-    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
-    return ((long long)zl * nyb + y / ROWS_PER_UNIT) * p.nseg + c / WORDS_PER_WARP;
-}
-// A unit can hold a band voxel only if it or one of its 26 neighbour units (z, y-block, x-segment) holds a segmented
-// voxel: far from every vessel the band sweep skips the unit after 27 byte loads.
-__device__ __forceinline__ bool unit_near_segmented(const Params &p, int zl, int y0, int sg, int lane) {
-    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
-    bool hit = false;
-    if (lane < 27) {
-        const int zz = zl + lane / 9 - 1, yb = y0 / ROWS_PER_UNIT + (lane / 3) % 3 - 1, ss = sg + lane % 3 - 1;
-        if (zz >= p.valid_lo && zz < p.valid_hi && yb >= 0 && yb < nyb && ss >= 0 && ss < p.nseg)
-            hit = p.unitmap[((long long)zz * nyb + yb) * p.nseg + ss] != 0;
-    }
-    return __ballot_sync(FULL, hit) != 0u;
-}
-
 struct Unit { int zl, y0, y1, sg; };
 __device__ __forceinline__ Unit decode_unit(const Params &p, long long u, int zlo, int nyb) {
     Unit r;
@@ -283,9 +308,10 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
     const long long nwarps = (long long)gridDim.x * WARPS;
     long long flips = 0;
     Strip st;
-    for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
-        const Unit un = decode_unit(p, u, zlo, nyb);
-        if (!unit_near_segmented(p, un.zl, un.y0, un.sg, lane)) continue;
+    const int nactive = p.ulist[0];  // built by k_table's spare blocks
+    (void)nunits;
+    for (int i = blockIdx.x * WARPS + (threadIdx.x >> 5); i < nactive; i += (int)nwarps) {
+        const Unit un = decode_unit(p, p.ulist[1 + i], zlo, nyb);
         const int c0 = un.sg * WORDS_PER_WARP - 1, c = c0 + lane;
         const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
         st.begin(p, un.zl, un.y0, c, lane);
@@ -706,6 +732,7 @@ __global__ void k_advance(Params p) {
     c[C_TRACE_N] = t + 1;
     c[C_APPLIED] += 1;
     c[C_ITER] += 1;
+    p.ulist[0] = 0;  // the next k_table rebuilds the active-unit list
     if (c[C_ITER] > c[C_ITER_MAX]) c[C_STATUS] = 3;        // VRG:58,118
 }
 

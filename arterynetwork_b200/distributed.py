@@ -114,9 +114,15 @@ class GpuSlabEngine:
 
 
 class DistributedVRG:
-    """Runs the slab protocol over an initialised ``torch.distributed`` process group."""
+    """Runs the slab protocol over an initialised ``torch.distributed`` process group.
 
-    def __init__(self, engine, rank, world, check_every=4):
+    ``use_graph`` (GPU engines only): after one eager batch (NCCL sets up its channels lazily), a batch of
+    ``check_every`` iterations -- kernels, halo sends/receives and the all-reduce -- is captured once into a CUDA
+    graph and replayed, so the host costs one launch per batch instead of ~20 calls per iteration.  Kernels read
+    the device-side status word, so replays after the exit are no-ops.
+    """
+
+    def __init__(self, engine, rank, world, check_every=4, use_graph=False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -124,6 +130,8 @@ class DistributedVRG:
         self.check_every = check_every
         self.iters_enqueued = 0
         self.has_excl = True
+        self.use_graph = bool(use_graph)
+        self._graph, self._graph_key = None, None
 
     # -- collectives ----------------------------------------------------------------------------
     def _exchange(self, t):
@@ -185,10 +193,30 @@ class DistributedVRG:
         e.advance()
         self.iters_enqueued += 1
 
+    def _batch(self):
+        for _ in range(self.check_every):
+            self.iterate_once()
+
+    def _graph_for_current_buffers(self):
+        e, torch = self.e, self.torch
+        key = (self.has_excl, self.check_every) + tuple(int(t.data_ptr()) for t in (
+            e.seg, e.excl, e.flips, e.cancelled, e.local_stats, e.global_stats))
+        if self._graph is None or key != self._graph_key:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.current_stream(), capture_error_mode="thread_local"):
+                self._batch()
+            self._graph, self._graph_key = g, key
+        return self._graph
+
     def run(self):
+        first = True
         while True:
-            for _ in range(self.check_every):
-                self.iterate_once()
+            if self.use_graph and not first:
+                self._graph_for_current_buffers().replay()
+                self.iters_enqueued += self.check_every
+            else:
+                self._batch()
+            first = False
             res = self.e.poll()
             if res["exit_reason"] != nat.EXIT_RUNNING:
                 return res
@@ -219,45 +247,74 @@ def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
     z0, z1 = b[rank], b[rank + 1]
     e0, e1 = max(0, z0 - HALO), min(shape[0], z1 + HALO)
     d_data, d_vm = bench.device_phantom(shape, args.seed, e0, e1 - e0, local)
-    eng = VRGEngine(shape, max_segment_size=10 ** 15, intensity=args.intensity, device=local, z_begin=z0, z_end=z1)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    drv = DistributedVRG(GpuSlabEngine(eng, local), rank, world)
-
-    def step():
-        eng.upload_device(d_data.data_ptr(), d_vm.data_ptr())
-        drv.prepare_levels()
-        drv.init()
-        return drv.run()
-
-    for _ in range(args.warmup):
-        res = step()
-    sampler = bench.ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    eng.profile(True)
-    l0 = eng.poll()["kernel_launches"]
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
     torch.cuda.synchronize()
-    start.record()
-    sweeps = 0
-    for _ in range(args.steps):
-        res = step()
-        sweeps += res["sweeps"]
-    end.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([start.elapsed_time(end)], device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
-    ms = float(ms.item())
-    prof = eng.get_profile()
-    launches = eng.poll()["kernel_launches"] - l0
-    clocks = sampler.stop() if rank == 0 else None
-    # checksum of the result labels so runs at different N can be compared
-    lab = torch.empty((z1 - z0,) + tuple(shape[1:]), dtype=torch.uint8, device="cuda")
-    eng.labels_device(lab.data_ptr())
-    cs = torch.stack([(lab == k).sum() for k in range(5)]).to(torch.int64)
-    dist.all_reduce(cs)
+    side = torch.cuda.Stream()  # CUDA graphs cannot be captured on the default stream
+    use_graph = os.environ.get("VRG_NO_GRAPH") is None
+    with torch.cuda.stream(side):
+        eng = VRGEngine(shape, max_segment_size=10 ** 15, intensity=args.intensity, device=local, z_begin=z0, z_end=z1)
+        eng.set_stream(side.cuda_stream)
+        drv = DistributedVRG(GpuSlabEngine(eng, local), rank, world, check_every=8, use_graph=use_graph)
+
+        def step():
+            eng.upload_device(d_data.data_ptr(), d_vm.data_ptr())
+            drv.prepare_levels()
+            drv.init()
+            return drv.run()
+
+        def timed(fn, n):
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            start.record()
+            sweeps = 0
+            for _ in range(n):
+                sweeps += fn()["sweeps"]
+            end.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            ms = torch.tensor([start.elapsed_time(end)], device="cuda")
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
+            return float(ms.item()), sweeps
+
+        for _ in range(args.warmup):
+            res = step()
+        sampler = bench.ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = eng.poll()["kernel_launches"]
+        ms, sweeps = timed(step, args.steps)
+        launches = eng.poll()["kernel_launches"] - l0
+        clocks = sampler.stop() if rank == 0 else None
+        res = eng.poll()
+        # per-launch time of the sweep: one eager (un-graphed) step with CUDA events around every sweep launch
+        drv.use_graph = False
+        eng.profile(True)
+        step()
+        prof = eng.get_profile()
+        eng.profile(False)
+        drv.use_graph = use_graph
+        # end to end: every rank uploads its extended slab from pinned host memory and reads its labels back
+        h_data = torch.empty(d_data.shape, dtype=torch.float64, pin_memory=True)
+        h_vm = torch.empty(d_vm.shape, dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty((z1 - z0,) + tuple(shape[1:]), dtype=torch.uint8, pin_memory=True)
+        h_data.copy_(d_data); h_vm.copy_(d_vm)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            eng.upload(h_data.numpy(), h_vm.numpy())
+            drv.prepare_levels()
+            drv.init()
+            r = drv.run()
+            nat.check(eng.lib.vrg_download_labels(eng._h, h_out.data_ptr()))
+            return r
+        e2e_step()
+        e2e_ms, e2e_sweeps = timed(e2e_step, args.steps)
+        # checksum of the result labels so runs at different N can be compared
+        lab = torch.from_numpy(h_out.numpy()).to("cuda")
+        cs = torch.stack([(lab == k).sum() for k in range(5)]).to(torch.int64)
+        dist.all_reduce(cs)
+        h2d = torch.tensor([h_data.numel() * 8 + h_vm.numel(), h_out.numel()], device="cuda", dtype=torch.int64)
+        dist.all_reduce(h2d)
     value = nvox * sweeps / (ms * 1e-3) / 1e9
     if rank == 0:
         per_launch_ms = prof["decide_ms"] / max(1, prof["decide_launches"])
@@ -270,15 +327,18 @@ def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
             "config": {"workload": "%s %dx%dx%d vessel-forest phantom, seed %d" % (args.workload, shape[2], shape[1], shape[0], args.seed),
                        "intensity_mode": args.intensity, "partition": "z-slabs, %d planes per rank, halo %d" % (z1 - z0, HALO),
                        "sweeps_per_step": sweeps // args.steps, "segmented_voxels": res["n_in"],
-                       "label_histogram": [int(x) for x in cs.tolist()],
+                       "label_histogram": [int(x) for x in cs.tolist()], "cuda_graph": use_graph,
                        "l2": "inputs larger than L2; no flush",
                        "step": "upload_device (D2D) + level scan/all-gather + init + all iterations"},
             "clocks": clocks,
-            "e2e": None,
+            "e2e": {"value": nvox * e2e_sweeps / (e2e_ms * 1e-3) / 1e9, "unit": "Gvoxel-updates/s",
+                    "h2d_bytes_per_step": int(h2d[0].item()), "d2h_bytes_per_step": int(h2d[1].item()),
+                    "ms_per_step": e2e_ms / args.steps, "intensity_mode": args.intensity},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_decide", "achieved": achieved, "peak": peak[0], "peak_kind": peak[1],
+            "roofline": {"bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak[0], "peak_kind": peak[1],
                          "unit": "GB/s", "frac": achieved / peak[0], "traffic": None, "ms_per_launch": per_launch_ms,
-                         "note": "rank 0's slab (own planes +-1)"},
+                         "algorithmic_bytes_per_launch": algo_bytes * local_vox,
+                         "note": "rank 0's slab (own planes +-1), timed in a separate eager step"},
         }
         print(json.dumps(line))
     eng.close()
