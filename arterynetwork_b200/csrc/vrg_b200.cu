@@ -60,7 +60,7 @@ struct vrg_handle {
     bool have_data = false, have_levels = false, inited = false, separate_gstats = false;
     int64_t launches = 0;
     int grid = 148 * 8;
-    bool dense_attr_set = false, force_ldg = false;
+    bool dense_attr_set = false, force_ldg = false, hist_attr_set = false;
     // optional per-kernel timing (CUDA events on the launch stream), see vrg_profile
     bool prof = false;
     std::vector<cudaEvent_t> ev;   // 4 events per enqueued iteration: decide begin/end, cancel begin/end
@@ -369,11 +369,26 @@ int vrg_use_separate_global_stats(vrg_handle *h) {
 }
 
 // ---- init -------------------------------------------------------------------------------------
-static void launch_init_hist(vrg_handle *h) {
+static int launch_init_hist(vrg_handle *h) {
     const Params &p = h->p;
+    // lane-private shared histograms when at least 4 warps' worth fit (64 B per level per warp)
+    const size_t per_warp = (size_t)p.L * 32 * sizeof(uint16_t);
+    const int hw = (int)std::min<size_t>(16, (220 * 1024) / per_warp);
+    if (hw >= 4) {
+        if (!h->hist_attr_set) {
+            CK(cudaFuncSetAttribute(k_init_hist_private<MODE_INDEX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(cudaFuncSetAttribute(k_init_hist_private<MODE_INDEX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(cudaFuncSetAttribute(k_init_hist_private<MODE_F64_BAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            CK(cudaFuncSetAttribute(k_init_hist_private<MODE_F64_BAND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            h->hist_attr_set = true;
+        }
+        LAUNCH_ML(k_init_hist_private, h->sms, hw * 32, hw * per_warp, p, hw);
+        return VRG_OK;
+    }
     const size_t one = (size_t)2 * p.L * sizeof(unsigned int);
     const int copies = (int)std::min<size_t>(WARPS, (48 * 1024) / one);
     LAUNCH_ML(k_init_hist, h->grid, BLOCK, copies * one, p, copies);
+    return VRG_OK;
 }
 
 int vrg_init(vrg_handle *h) {
@@ -407,7 +422,7 @@ int vrg_init(vrg_handle *h) {
     p.E = h->d_E; p.C = h->d_C;
     k_init_planes<<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_vm, h->d_E);
     k_init_bands<<<h->grid, BLOCK, 0, h->stream>>>(p);
-    launch_init_hist(h);
+    { int rc_ = launch_init_hist(h); if (rc_ != VRG_OK) return rc_; }
     h->launches += 3;
     CK(cudaGetLastError());
     // the init row of the trace and the error checks need the counters on the host
