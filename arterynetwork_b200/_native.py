@@ -39,6 +39,7 @@ _SIGS = {
     "vrg_upload": [vp, vp, vp],
     "vrg_upload_device": [vp, vp, vp],
     "vrg_upload_value_map": [vp, vp],
+    "vrg_attach_device": [vp, vp, vp],
     "vrg_scan_levels": [vp, ctypes.POINTER(i64)],
     "vrg_get_levels": [vp, vp, i64],
     "vrg_set_levels": [vp, vp, i64],

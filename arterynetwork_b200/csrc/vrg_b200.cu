@@ -45,7 +45,7 @@ struct vrg_handle {
     double *d_data = nullptr;
     uint8_t *d_vm = nullptr, *d_rowflag = nullptr, *d_labels = nullptr, *d_unitmap = nullptr;
     size_t unitmap_bytes = 0;
-    int *d_front = nullptr, *d_ulist = nullptr;
+    int *d_front = nullptr, *d_ulist = nullptr, *d_stamp = nullptr;
     int sweep_units = 0;
     uint16_t *d_index = nullptr;
     uint32_t *d_S = nullptr, *d_E = nullptr, *d_F = nullptr, *d_C = nullptr;
@@ -60,7 +60,8 @@ struct vrg_handle {
     bool have_data = false, have_levels = false, inited = false, separate_gstats = false;
     int64_t launches = 0;
     int grid = 148 * 8;
-    bool dense_attr_set = false, force_ldg = false, hist_attr_set = false;
+    bool dense_attr_set = false, force_ldg = false, hist_attr_set = false, attached = false;
+    const uint8_t *vm_base = nullptr;  // valueMap as indexed by local plane (own buffer or attached)
     // optional per-kernel timing (CUDA events on the launch stream), see vrg_profile
     bool prof = false;
     std::vector<cudaEvent_t> ev;   // 4 events per enqueued iteration: decide begin/end, cancel begin/end
@@ -162,8 +163,6 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     const size_t nvox = (size_t)p.nzl * p.plane_vox;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void **ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
-    alloc((void **)&h->d_data, nvox * sizeof(double));
-    alloc((void **)&h->d_vm, nvox);
     alloc((void **)&h->d_S, h->plane_bytes);
     alloc((void **)&h->d_E, h->plane_bytes);
     alloc((void **)&h->d_F, h->plane_bytes);
@@ -173,7 +172,9 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     alloc((void **)&h->d_unitmap, h->unitmap_bytes);
     h->sweep_units = (int)(((size_t)h->nz_own + 2) * ((Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT) * p.nseg);
     alloc((void **)&h->d_ulist, (1 + (size_t)h->sweep_units) * sizeof(int));
-    alloc((void **)&h->d_front, (1 + (size_t)h->nz_own * Y * p.nseg) * sizeof(int));
+    p.front_cap = 1 + (int)((size_t)h->nz_own * Y * p.nseg);
+    alloc((void **)&h->d_front, 2 * (size_t)p.front_cap * sizeof(int));
+    alloc((void **)&h->d_stamp, h->rowflag_bytes * sizeof(int));
     alloc((void **)&h->d_ctrl, C_WORDS * sizeof(long long));
     alloc((void **)&h->d_trace, 3 * (cfg->iter_max + 2) * sizeof(long long));
     alloc((void **)&h->d_hash, (size_t)HASH_CAP * sizeof(unsigned long long));
@@ -184,10 +185,8 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
         vrg_destroy(h);
         return code;
     }
-    // planes outside the volume must read as neutral forever
-    CK(cudaMemsetAsync(h->d_data, 0, nvox * sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->d_vm, 3, nvox, h->stream));
-    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag; p.front = h->d_front; p.unitmap = h->d_unitmap; p.ulist = h->d_ulist;
+    (void)nvox;  // the input buffers are allocated on the first vrg_upload*; vrg_attach_device needs none
+    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag; p.front = h->d_front; p.unitmap = h->d_unitmap; p.ulist = h->d_ulist; p.stamp = h->d_stamp;
     p.data = h->d_data;
     p.ctrl = h->d_ctrl; p.trace = h->d_trace;
     *out = h;
@@ -199,7 +198,7 @@ int vrg_destroy(vrg_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_data); cudaFree(h->d_vm); cudaFree(h->d_index); cudaFree(h->d_labels);
-    cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_ulist);
+    cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_ulist); cudaFree(h->d_stamp);
     cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
     free_levels(h);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -218,11 +217,29 @@ int vrg_set_stream(vrg_handle *h, void *s) {
     return VRG_OK;
 }
 
+static int ensure_input_buffers(vrg_handle *h) {
+    const size_t nvox = (size_t)h->p.nzl * h->p.plane_vox;
+    if (!h->d_data) {
+        CK(cudaMalloc((void **)&h->d_data, nvox * sizeof(double)));
+        CK(cudaMemsetAsync(h->d_data, 0, nvox * sizeof(double), h->stream));
+    }
+    if (!h->d_vm) {
+        CK(cudaMalloc((void **)&h->d_vm, nvox));
+        CK(cudaMemsetAsync(h->d_vm, 3, nvox, h->stream));
+    }
+    return VRG_OK;
+}
+
 static int upload_impl(vrg_handle *h, const double *data, const uint8_t *vm, cudaMemcpyKind kind) {
     if (!h) return fail(VRG_ERR_ARG, "null handle");
     CK(cudaSetDevice(h->cfg.device));
-    const Params &p = h->p;
+    Params &p = h->p;
     const size_t off = (size_t)p.valid_lo * p.plane_vox, n = (size_t)(p.valid_hi - p.valid_lo) * p.plane_vox;
+    if (h->attached && !(data && vm)) return fail(VRG_ERR_ARG, "inputs are attached: upload both buffers or attach again");
+    { int rc_ = ensure_input_buffers(h); if (rc_ != VRG_OK) return rc_; }
+    h->attached = false;
+    p.data = h->d_data;
+    h->vm_base = h->d_vm;
     if (data) {
         CK(cudaMemcpyAsync(h->d_data + off, data, n * sizeof(double), kind, h->stream));
         h->have_data = true;
@@ -242,6 +259,20 @@ int vrg_upload_device(vrg_handle *h, const double *d, const uint8_t *vm) {
     if (!d && !vm) return fail(VRG_ERR_ARG, "null buffer");
     return upload_impl(h, d, vm, cudaMemcpyDeviceToDevice);
 }
+// Zero-copy: run on the caller's device-resident extended slab (read-only; must stay alive until the run ends).
+int vrg_attach_device(vrg_handle *h, const double *data_dev, const uint8_t *vm_dev) {
+    if (!h || !data_dev || !vm_dev) return fail(VRG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    Params &p = h->p;
+    const long long off = (long long)p.valid_lo * p.plane_vox;  // kernels index by local plane; only valid planes are read
+    p.data = (const double *)((uintptr_t)data_dev - (uintptr_t)off * sizeof(double));
+    h->vm_base = (const uint8_t *)((uintptr_t)vm_dev - (uintptr_t)off);
+    h->attached = true;
+    h->have_data = true;
+    h->have_levels = false;
+    h->inited = false;
+    return VRG_OK;
+}
 int vrg_upload_value_map(vrg_handle *h, const uint8_t *vm) {
     if (!vm) return fail(VRG_ERR_ARG, "null buffer");
     int rc = upload_impl(h, nullptr, vm, cudaMemcpyHostToDevice);
@@ -257,7 +288,7 @@ int vrg_scan_levels(vrg_handle *h, int64_t *n_levels) {
     CK(cudaMemsetAsync(h->d_hash, 0xFF, (size_t)HASH_CAP * sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->d_hcount, 0, 4 * sizeof(int), h->stream));
     const long long n = (long long)(p.valid_hi - p.valid_lo) * p.plane_vox;
-    k_scan_levels<<<h->grid, BLOCK, 0, h->stream>>>(h->d_data + (size_t)p.valid_lo * p.plane_vox, n, h->d_hash, HASH_CAP - 1,
+    k_scan_levels<<<h->grid, BLOCK, 0, h->stream>>>(p.data + (size_t)p.valid_lo * p.plane_vox, n, h->d_hash, HASH_CAP - 1,
                                                      h->d_hcount, VRG_MAX_LEVELS, h->d_hcount + 1);
     h->launches++;
     CK(cudaGetLastError());
@@ -345,10 +376,14 @@ int vrg_set_levels(vrg_handle *h, const double *lv, int64_t n) {
     h->have_levels = true;
     h->inited = false;
     if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) {
-        const size_t nvox = (size_t)p.nzl * p.plane_vox;
-        if (!h->d_index) CK(cudaMalloc((void **)&h->d_index, nvox * sizeof(uint16_t)));
-        if (p.lattice) k_build_index<true><<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_data, h->d_index, (long long)nvox);
-        else k_build_index<false><<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_data, h->d_index, (long long)nvox);
+        const size_t nvox = (size_t)p.nzl * p.plane_vox, voff = (size_t)p.valid_lo * p.plane_vox;
+        const long long nval = (long long)(p.valid_hi - p.valid_lo) * p.plane_vox;
+        if (!h->d_index) {
+            CK(cudaMalloc((void **)&h->d_index, nvox * sizeof(uint16_t)));
+            CK(cudaMemsetAsync(h->d_index, 0, nvox * sizeof(uint16_t), h->stream));
+        }
+        if (p.lattice) k_build_index<true><<<h->grid, BLOCK, 0, h->stream>>>(p, p.data + voff, h->d_index + voff, nval);
+        else k_build_index<false><<<h->grid, BLOCK, 0, h->stream>>>(p, p.data + voff, h->d_index + voff, nval);
         h->launches++;
         CK(cudaGetLastError());
         p.index = h->d_index;
@@ -408,7 +443,8 @@ int vrg_init(vrg_handle *h) {
     CK(cudaMemsetAsync(h->d_F, 0, h->plane_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_C, 0, h->plane_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_rowflag, 0, h->rowflag_bytes, h->stream));
-    CK(cudaMemsetAsync(h->d_front, 0, sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_front, 0, 2 * (size_t)p.front_cap * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_stamp, 0xFF, h->rowflag_bytes * sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_unitmap, 0, h->unitmap_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_ulist, 0, sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_lstats, 0, (size_t)(2 * p.L + ST_EXTRA) * sizeof(long long), h->stream));
@@ -417,10 +453,11 @@ int vrg_init(vrg_handle *h) {
     memset(c, 0, sizeof c);
     c[C_STATUS] = RUNNING; c[C_ITER] = 1; c[C_ITER_MAX] = h->cfg.iter_max; c[C_MAX_SEG] = h->cfg.max_segment_size;
     c[C_TRACE_N] = 1;
+    c[C_TABLE_CHANGED] = 1;  // the first sweep is a full one
     memcpy(h->h_ctrl, c, sizeof c);
     CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof c, cudaMemcpyHostToDevice, h->stream));
     p.E = h->d_E; p.C = h->d_C;
-    k_init_planes<<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_vm, h->d_E);
+    k_init_planes<<<h->grid, BLOCK, 0, h->stream>>>(p, h->vm_base, h->d_E);
     k_init_bands<<<h->grid, BLOCK, 0, h->stream>>>(p);
     { int rc_ = launch_init_hist(h); if (rc_ != VRG_OK) return rc_; }
     h->launches += 3;

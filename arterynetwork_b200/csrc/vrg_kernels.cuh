@@ -32,7 +32,7 @@ constexpr int DENSE_STAGES = 2;
 constexpr int STAGE_BYTES = WORDS_PER_WARP * 32 * 8;
 
 enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, ST_BAD_LABEL = 5, ST_NONFINITE = 6, ST_EXTRA = 8 };
-enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_WORDS = 16 };
+enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_TABLE_CHANGED = 8, C_WORDS = 16 };
 constexpr long long RUNNING = -1;
 
 enum { MODE_F64_DENSE = 0, MODE_F64_BAND = 1, MODE_INDEX = 2 };
@@ -51,7 +51,9 @@ struct Params {
     uint8_t *rowflag;                 // [nzl * Y * nseg]
     uint8_t *unitmap;                 // [nzl * nyb * nseg]: 1 if the sweep unit ever held a segmented voxel (never cleared)
     int *ulist;                       // [1 + sweep units]: ulist[0] = count, then the units near a segmented voxel (band sweep)
-    int *front;                       // [1 + own rows * nseg]: front[0] = count, then the flagged own-plane rows of this sweep
+    int *front;                       // 2 x [front_cap]: [0] = count, then the own-plane rows that flip in this sweep;
+    int front_cap;                    //   sweep k writes list k & 1, the next sweep reads it as its dirty seed
+    int *stamp;                       // [nzl * Y * nseg]: sweep number that last claimed the row (incremental pass)
     const double *data;               // fp64 intensities, local planes
     const uint16_t *index;            // level index volume (MODE_INDEX)
     // levels / table
@@ -68,6 +70,8 @@ struct Params {
     long long *ctrl;                  // [C_WORDS]
     long long *trace;                 // [3 * (iter_max + 2)]
 };
+
+__device__ __forceinline__ int *front_list(const Params &p, int which) { return p.front + (size_t)which * p.front_cap; }
 
 __device__ __forceinline__ uint32_t valid_mask(const Params &p, int c) {
     return c < p.XW - 1 ? 0xFFFFFFFFu : (c == p.XW - 1 ? p.tail_mask : 0u);
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctrl[C_APPLY] = n_in < p.ctrl[C_MAX_SEG];  // cap is tested before the flips are applied, VRG:101
         p.lstats[2 * p.L + ST_N_FLIPS] = 0;
-        p.front[0] = 0;
+        front_list(p, (int)(p.ctrl[C_SWEEPS] & 1))[0] = 0;
     }
     __shared__ uint32_t s_bits[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
     if (threadIdx.x == 0) {
         uint32_t w = 0;
         for (int i = 0; i < WARPS; ++i) w |= s_bits[i];
+        if (p.dbits[blockIdx.x] != w) p.ctrl[C_TABLE_CHANGED] = 1;  // the next sweep must look at every band voxel
         p.dbits[blockIdx.x] = w;
     }
 }
@@ -284,17 +289,61 @@ __device__ __forceinline__ void store_flips(const Params &p, long long widx, lon
         }
         if (lane == 0) {
             if (any != (was != 0)) p.rowflag[ridx] = any ? 1 : 0;
-            if (any && own) p.front[1 + atomicAdd(&p.front[0], 1)] = (int)ridx;
+            if (any && own) {
+                int *fl = front_list(p, (int)(p.ctrl[C_SWEEPS] & 1));
+                fl[1 + atomicAdd(&fl[0], 1)] = (int)ridx;
+            }
         }
     }
 }
 
-// k_sweep_band: the stencil sweep of the BAND / INDEX modes.  A warp owns a strip of ROWS_PER_UNIT rows x 30 words
-// of one plane and slides down it.  Bands:
+// Decision + flip word of one row segment of the BAND / INDEX modes: the decision bit D is looked up only for the
+// 32-voxel words that hold a band voxel (four gathers in flight); a band voxel flips iff D != S (VRG:87).
+template <int MODE, bool LATTICE>
+__device__ __forceinline__ int band_row(const Params &p, const uint32_t *s_dbits, int zl, int y, int sg, uint32_t s,
+                                        uint32_t inner, uint32_t outer, bool active, bool own, int lane) {
+    const int c0 = sg * WORDS_PER_WARP - 1;
+    const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c0 + lane;
+    if (p.E != nullptr && outer) outer &= ~p.E[widx];
+    const uint32_t band = inner | outer;
+    unsigned m = __ballot_sync(FULL, band != 0u);
+    uint32_t D = 0;
+    const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + lane;
+    while (m) {  // warp-uniform: only words that hold a band voxel, four at a time
+        int js[4], lv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            js[k] = -1; lv[k] = -1;
+            if (m) {
+                js[k] = __ffs(m) - 1;
+                m &= m - 1;
+                const int x = (c0 + js[k]) * 32 + lane;
+                if (x < p.X) lv[k] = level_at<MODE, LATTICE>(p, rowvox + (long long)(c0 + js[k]) * 32);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (js[k] < 0) break;
+            const int l = lv[k];
+            const uint32_t bit = l >= 0 ? (s_dbits[l >> 5] >> (l & 31)) & 1u : 0u;
+            const unsigned word = __ballot_sync(FULL, bit);
+            if (lane == js[k]) D = word;
+        }
+    }
+    const uint32_t f = band & (D ^ s);  // inner band leaves iff in < out, outer band enters iff in >= out
+    store_flips(p, widx, ((long long)zl * p.Y + y) * p.nseg + sg, f, active, own, lane);
+    return own ? __popc(f) : 0;
+}
+
+// k_sweep_band: the stencil sweep of the BAND / INDEX modes.  Bands:
 //   inner = S & dil26(~S in volume)      (segmented with an unsegmented in-bounds neighbour, VRG:139-142)
 //   outer = ~S & ~E & dil26(S)           (unsegmented, not excluded, with a segmented neighbour, VRG:143-145)
-// The decision bit D is looked up only for the 32-voxel words that hold a band voxel (four gathers in flight);
-// a band voxel flips iff D != S (VRG:87).
+// Full pass: a warp owns a strip of ROWS_PER_UNIT rows x 30 words of one plane and slides down it, over the units
+// near a segmented voxel (ulist).
+// Incremental pass (single slab, decision table unchanged since the last sweep): a voxel's flip flag can differ
+// from last time only if a voxel of its 26-neighbourhood flipped, so only the rows within one row / plane /
+// segment of last sweep's front rows are re-evaluated (each claimed once through `stamp`); every other row keeps
+// its all-zero flip word.  The work is then proportional to the moving front, like the reference's narrow band.
 template <int MODE, bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
@@ -304,50 +353,40 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
     const int lane = threadIdx.x & 31;
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
     const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
-    const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
     const long long nwarps = (long long)gridDim.x * WARPS;
+    const long long warp0 = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
     long long flips = 0;
     Strip st;
-    const int nactive = p.ulist[0];  // built by k_table's spare blocks
-    (void)nunits;
-    for (int i = blockIdx.x * WARPS + (threadIdx.x >> 5); i < nactive; i += (int)nwarps) {
-        const Unit un = decode_unit(p, p.ulist[1 + i], zlo, nyb);
-        const int c0 = un.sg * WORDS_PER_WARP - 1, c = c0 + lane;
-        const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
-        st.begin(p, un.zl, un.y0, c, lane);
-        for (int y = un.y0; y < un.y1; ++y) {
+    const bool single_slab = p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
+    if (single_slab && p.ctrl[C_TABLE_CHANGED] == 0) {
+        const int sweep = (int)p.ctrl[C_SWEEPS];
+        const int *prev = front_list(p, (sweep & 1) ^ 1);
+        const long long ncand = (long long)prev[0] * 27;
+        for (long long q = warp0; q < ncand; q += nwarps) {
+            const int rr = prev[1 + (int)(q / 27)], k = (int)(q % 27);
+            const int sg = rr % p.nseg + k % 3 - 1, t = rr / p.nseg;
+            const int y = t % p.Y + (k / 3) % 3 - 1, zl = t / p.Y + k / 9 - 1;
+            if (zl < zlo || zl >= zhi || y < 0 || y >= p.Y || sg < 0 || sg >= p.nseg) continue;
+            const int ridx = (zl * p.Y + y) * p.nseg + sg;
+            int old = sweep;
+            if (lane == 0) old = atomicExch(&p.stamp[ridx], sweep);
+            if (__shfl_sync(FULL, old, 0) == sweep) continue;  // another warp has this row
+            st.begin(p, zl, y, sg * WORDS_PER_WARP - 1 + lane, lane);
             uint32_t s, inner, outer;
             st.step(y, s, inner, outer);
-            const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
-            if (p.E != nullptr && outer) outer &= ~p.E[widx];
-            const uint32_t band = inner | outer;
-            unsigned m = __ballot_sync(FULL, band != 0u);
-            uint32_t D = 0;
-            const long long rowvox = (long long)un.zl * p.plane_vox + (long long)y * p.X + lane;
-            while (m) {  // warp-uniform: only words that hold a band voxel, four at a time
-                int js[4], lv[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    js[k] = -1; lv[k] = -1;
-                    if (m) {
-                        js[k] = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int x = (c0 + js[k]) * 32 + lane;
-                        if (x < p.X) lv[k] = level_at<MODE, LATTICE>(p, rowvox + (long long)(c0 + js[k]) * 32);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (js[k] < 0) break;
-                    const int l = lv[k];
-                    const uint32_t bit = l >= 0 ? (s_dbits[l >> 5] >> (l & 31)) & 1u : 0u;
-                    const unsigned word = __ballot_sync(FULL, bit);
-                    if (lane == js[k]) D = word;
-                }
+            flips += band_row<MODE, LATTICE>(p, s_dbits, zl, y, sg, s, inner, outer, st.active, true, lane);
+        }
+    } else {
+        const int nactive = p.ulist[0];  // built by k_table's spare blocks
+        for (int i = (int)warp0; i < nactive; i += (int)nwarps) {
+            const Unit un = decode_unit(p, p.ulist[1 + i], zlo, nyb);
+            const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
+            st.begin(p, un.zl, un.y0, un.sg * WORDS_PER_WARP - 1 + lane, lane);
+            for (int y = un.y0; y < un.y1; ++y) {
+                uint32_t s, inner, outer;
+                st.step(y, s, inner, outer);
+                flips += band_row<MODE, LATTICE>(p, s_dbits, un.zl, y, un.sg, s, inner, outer, st.active, own, lane);
             }
-            const uint32_t f = band & (D ^ s);  // inner band leaves iff in < out, outer band enters iff in >= out
-            store_flips(p, widx, ((long long)un.zl * p.Y + y) * p.nseg + un.sg, f, st.active, own, lane);
-            if (own) flips += __popc(f);
         }
     }
     flips = warp_sum(flips);
@@ -545,10 +584,11 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_dense_ldg(Params p) {
 // The front list: own-plane row segments whose flip word is non-zero; calls fn(zl, y, sg) warp-uniformly, one row per warp.
 template <typename Fn>
 __device__ __forceinline__ void for_front_rows(const Params &p, Fn fn) {
-    const int n = p.front[0];
+    const int *fl = front_list(p, (int)(p.ctrl[C_SWEEPS] & 1));
+    const int n = fl[0];
     const int nwarps = gridDim.x * WARPS;
     for (int k = blockIdx.x * WARPS + (threadIdx.x >> 5); k < n; k += nwarps) {
-        const int rr = p.front[1 + k];
+        const int rr = fl[1 + k];
         const int sg = rr % p.nseg, t = rr / p.nseg;
         fn(t / p.Y, t % p.Y, sg);
     }
@@ -732,6 +772,7 @@ __global__ void k_advance(Params p) {
     c[C_TRACE_N] = t + 1;
     c[C_APPLIED] += 1;
     c[C_ITER] += 1;
+    c[C_TABLE_CHANGED] = 0;  // k_table of the next iteration raises it again if a decision bit moves
     p.ulist[0] = 0;  // the next k_table rebuilds the active-unit list
     if (c[C_ITER] > c[C_ITER_MAX]) c[C_STATUS] = 3;        // VRG:58,118
 }
@@ -888,14 +929,26 @@ __global__ void k_init_hist_private(Params p, int hw) {
         const int y = r % p.Y, zl = p.own_lo + r / p.Y;
         const long long wbase = (long long)zl * p.plane_words + (long long)y * p.WP;
         const long long vbase = (long long)zl * p.plane_vox + (long long)y * p.X;
-        for (int c = 0; c < p.XW; ++c) {
-            const uint32_t s = p.S[wbase + c], e = p.E ? p.E[wbase + c] : 0u;
-            const int x = c * 32 + lane;
-            if (x < p.X) {
-                const int l = level_at<MODE, LATTICE>(p, vbase + x);
+        for (int cb = 0; cb < p.XW; cb += 8) {  // eight independent level loads in flight per lane
+            int lv[8];
+            uint32_t sw[8], ew[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = cb + k, x = c * 32 + lane;
+                lv[k] = -1; sw[k] = 0u; ew[k] = 0u;
+                if (c < p.XW) {
+                    sw[k] = p.S[wbase + c];
+                    ew[k] = p.E ? p.E[wbase + c] : 0u;
+                    if (x < p.X) lv[k] = level_at<MODE, LATTICE>(p, vbase + x);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int l = lv[k];
+                if (l < 0) continue;
                 const uint32_t bit = 1u << lane;
-                if (s & bit) { n_in++; atomicAdd(&hin[l], 1ull); }
-                else if (e & bit) n_ex++;
+                if (sw[k] & bit) { n_in++; atomicAdd(&hin[l], 1ull); }
+                else if (ew[k] & bit) n_ex++;
                 else { n_out++; mine[l * 32] += 1; }
             }
         }

@@ -256,7 +256,7 @@ def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
         drv = DistributedVRG(GpuSlabEngine(eng, local), rank, world, check_every=8, use_graph=use_graph)
 
         def step():
-            eng.upload_device(d_data.data_ptr(), d_vm.data_ptr())
+            eng.attach_device(d_data.data_ptr(), d_vm.data_ptr())
             drv.prepare_levels()
             drv.init()
             return drv.run()
@@ -329,7 +329,7 @@ def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
                        "sweeps_per_step": sweeps // args.steps, "segmented_voxels": res["n_in"],
                        "label_histogram": [int(x) for x in cs.tolist()], "cuda_graph": use_graph,
                        "l2": "inputs larger than L2; no flush",
-                       "step": "upload_device (D2D) + level scan/all-gather + init + all iterations"},
+                       "step": "attach resident slab (zero-copy) + level scan/all-gather + init + all iterations"},
             "clocks": clocks,
             "e2e": {"value": nvox * e2e_sweeps / (e2e_ms * 1e-3) / 1e9, "unit": "Gvoxel-updates/s",
                     "h2d_bytes_per_step": int(h2d[0].item()), "d2h_bytes_per_step": int(h2d[1].item()),

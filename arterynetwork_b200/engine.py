@@ -88,6 +88,10 @@ class VRGEngine:
     def upload_device(self, data_ptr: int, value_map_ptr: int):
         nat.check(self.lib.vrg_upload_device(self._h, nat.vp(data_ptr or None), nat.vp(value_map_ptr or None)))
 
+    def attach_device(self, data_ptr: int, value_map_ptr: int):
+        """Zero-copy: run on the caller's device-resident extended slab (fp64 data, uint8 valueMap)."""
+        nat.check(self.lib.vrg_attach_device(self._h, nat.vp(data_ptr), nat.vp(value_map_ptr)))
+
     # -- levels -----------------------------------------------------------------------------
     def scan_levels(self) -> np.ndarray:
         n = nat.i64(0)

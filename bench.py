@@ -161,9 +161,9 @@ def run_reference_arm(args):
 
 
 def bench_mode(eng, torch, mode_name, d_data, d_vm, steps, warmup, nvox):
-    """Resident-input timing of one intensity mode: step = upload_device (D2D) + init + run."""
+    """Resident-input timing of one intensity mode: step = attach (zero-copy) + level scan + init + run."""
     def step():
-        eng.upload_device(d_data.data_ptr(), d_vm.data_ptr())
+        eng.attach_device(d_data.data_ptr(), d_vm.data_ptr())
         eng.init()
         return eng.run()
 
@@ -282,7 +282,7 @@ def run_single(args):
                    "intensity_mode": args.intensity, "sweeps_per_step": prim["sweeps"] // args.steps,
                    "segmented_voxels": prim["res"]["n_in"], "levels": prim["res"]["n_levels"],
                    "l2": "inputs (%.1f GB) larger than L2; no flush" % (nvox * 9 / 1e9),
-                   "step": "upload_device (D2D of intensities+seeds) + level scan + init + all iterations"},
+                   "step": "attach resident inputs (zero-copy) + level scan + init + all iterations"},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": prim["launches"],

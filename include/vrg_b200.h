@@ -94,6 +94,8 @@ int vrg_set_stream(vrg_handle *h, void *cuda_stream);
 int vrg_upload(vrg_handle *h, const double *data_host, const uint8_t *value_map_host);
 int vrg_upload_device(vrg_handle *h, const double *data_dev, const uint8_t *value_map_dev);
 int vrg_upload_value_map(vrg_handle *h, const uint8_t *value_map_host); /* new seeds, same data */
+/* zero-copy: run on the caller's device-resident extended slab (read-only, must outlive the run) */
+int vrg_attach_device(vrg_handle *h, const double *data_dev, const uint8_t *value_map_dev);
 
 /* distinct intensity levels (the decision table's domain) ------------------- */
 int vrg_scan_levels(vrg_handle *h, int64_t *n_levels);             /* local slab */

@@ -21,7 +21,7 @@ def main():
     d, v = bench.device_phantom(shape, a.seed, 0, shape[0], 0)
     with VRGEngine(shape, max_segment_size=10 ** 15, intensity=a.intensity, iter_max=a.iters) as eng:
         eng.set_stream(torch.cuda.current_stream().cuda_stream)
-        eng.upload_device(d.data_ptr(), v.data_ptr())
+        eng.attach_device(d.data_ptr(), v.data_ptr())
         eng.init()
         print(eng.run())
 

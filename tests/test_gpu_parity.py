@@ -179,6 +179,29 @@ def test_iteration_cap():
     assert np.array_equal(o["labels"], ref["labels"]) and np.array_equal(o["trace"], ref["trace"])
 
 
+def test_attach_device_runs_in_place_and_can_rerun():
+    """Zero-copy resident inputs (vrg_attach_device): same result, inputs untouched, handle reusable with new seeds."""
+    import torch
+    from arterynetwork_b200.engine import VRGEngine
+    g = load_golden("forest40")
+    d = torch.from_numpy(np.ascontiguousarray(g["data"], dtype=np.float64)).cuda()
+    v = torch.from_numpy(g["value_map_in"].astype(np.uint8)).cuda()
+    d0, v0 = d.clone(), v.clone()
+    for mode in MODES:
+        with VRGEngine(g["data"].shape, max_segment_size=g["max_segment_size"], intensity=mode) as eng:
+            for _ in range(2):
+                eng.attach_device(d.data_ptr(), v.data_ptr())
+                eng.init()
+                res = eng.run()
+                assert res["iterations"] == g["iterations"]
+                assert np.array_equal(eng.labels(), g["labels"]) and np.array_equal(eng.trace(), g["trace"])
+            # host upload after an attach switches back to the handle's own buffers
+            eng.upload(g["data"], g["value_map_in"].astype(np.uint8))
+            eng.init()
+            assert eng.run()["iterations"] == g["iterations"]
+    assert torch.equal(d, d0) and torch.equal(v, v0)
+
+
 def test_device_phantom_equals_numpy_phantom():
     import ctypes
     import torch
