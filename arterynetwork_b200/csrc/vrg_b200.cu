@@ -49,7 +49,7 @@ struct vrg_handle {
     int sweep_units = 0;
     uint16_t *d_index = nullptr;
     uint32_t *d_S = nullptr, *d_E = nullptr, *d_F = nullptr, *d_C = nullptr;
-    double *d_levels = nullptr, *d_pin = nullptr, *d_pout = nullptr;
+    double *d_levels = nullptr, *d_pin = nullptr, *d_pout = nullptr, *d_kmat = nullptr;
     uint32_t *d_dbits = nullptr;
     long long *d_lstats = nullptr, *d_gstats = nullptr, *d_ctrl = nullptr, *d_trace = nullptr;
     long long *h_ctrl = nullptr;  // pinned
@@ -114,7 +114,8 @@ const char *vrg_last_error(void) { return g_err.c_str(); }
 int vrg_version(void) { return 101; }
 
 static void free_levels(vrg_handle *h) {
-    cudaFree(h->d_levels); cudaFree(h->d_pin); cudaFree(h->d_pout); cudaFree(h->d_dbits);
+    cudaFree(h->d_levels); cudaFree(h->d_pin); cudaFree(h->d_pout); cudaFree(h->d_dbits); cudaFree(h->d_kmat);
+    h->d_kmat = nullptr;
     cudaFree(h->d_lstats);
     if (h->separate_gstats) cudaFree(h->d_gstats);
     h->d_levels = h->d_pin = h->d_pout = nullptr; h->d_dbits = nullptr; h->d_lstats = h->d_gstats = nullptr;
@@ -366,6 +367,7 @@ int vrg_set_levels(vrg_handle *h, const double *lv, int64_t n) {
         CK(cudaMalloc((void **)&h->d_dbits, p.LW * sizeof(uint32_t)));
         CK(cudaMalloc((void **)&h->d_lstats, sb));
         h->d_gstats = h->d_lstats;
+        if (p.L <= 2048) CK(cudaMalloc((void **)&h->d_kmat, (size_t)p.L * p.L * sizeof(double)));
     }
     CK(cudaMemcpyAsync(h->d_levels, table.data(), p.L * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d_pin, 0, p.L * sizeof(double), h->stream));
@@ -373,6 +375,13 @@ int vrg_set_levels(vrg_handle *h, const double *lv, int64_t n) {
     CK(cudaStreamSynchronize(h->stream));  // `table` is a local
     p.levels = h->d_levels; p.pin = h->d_pin; p.pout = h->d_pout; p.dbits = h->d_dbits;
     p.lstats = h->d_lstats; p.gstats = h->d_gstats;
+    p.kmat = nullptr;
+    if (h->d_kmat) {
+        k_kmat<<<h->grid, BLOCK, 0, h->stream>>>(p, h->d_kmat);
+        h->launches++;
+        CK(cudaGetLastError());
+        p.kmat = h->d_kmat;
+    }
     h->have_levels = true;
     h->inited = false;
     if (h->cfg.intensity_mode == VRG_INTENSITY_INDEX) {

@@ -62,6 +62,7 @@ struct Params {
     int lattice;                      // 1: index = rint((v - lev0) * inv_step)
     double lev0, inv_step;
     const double *levels;             // [L]
+    const double *kmat;               // [L][L] Parzen kernel values A*exp(-0.5*H*(lev_b-lev_c)^2), or nullptr (L too large)
     uint32_t *dbits;                  // [LW]
     double *pin, *pout;               // [L] normalised Parzen sums of the last table
     double mhH;                       // -0.5 * H
@@ -162,6 +163,15 @@ __device__ __forceinline__ void build_unit_list(const Params &p, int t) {
     }
 }
 
+// Parzen kernel matrix of a level set (symmetric: (lev_c - lev_b)^2 is exact either way round)
+__global__ void __launch_bounds__(BLOCK) k_kmat(Params p, double *kmat) {
+    const long long n = (long long)p.L * p.L;
+    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) {
+        const double diff = p.levels[i % p.L] - p.levels[i / p.L];
+        kmat[i] = 0.3989422804014327 * exp(p.mhH * (diff * diff));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_table: one block per 32 levels; a warp sums one level's two Parzen sums over all levels.
 // Fixed order: lane-strided partial sums, then an xor-shuffle tree -> deterministic.
@@ -190,8 +200,12 @@ __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
         for (int c = lane; c < p.L; c += 32) {
             const long long hi = g[c], ho = g[p.L + c];
             if ((hi | ho) == 0) continue;
-            const double diff = p.levels[c] - lb;
-            const double kv = 0.3989422804014327 * exp(p.mhH * (diff * diff));  // A * exp(-0.5*H*d^2), VRG:7,154
+            double kv;
+            if (p.kmat != nullptr) kv = p.kmat[(size_t)b * p.L + c];  // same expression, evaluated once per level set
+            else {
+                const double diff = p.levels[c] - lb;
+                kv = 0.3989422804014327 * exp(p.mhH * (diff * diff));  // A * exp(-0.5*H*d^2), VRG:7,154
+            }
             si += (double)hi * kv;
             so += (double)ho * kv;
         }
@@ -361,20 +375,33 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
     if (single_slab && p.ctrl[C_TABLE_CHANGED] == 0) {
         const int sweep = (int)p.ctrl[C_SWEEPS];
         const int *prev = front_list(p, (sweep & 1) ^ 1);
-        const long long ncand = (long long)prev[0] * 27;
-        for (long long q = warp0; q < ncand; q += nwarps) {
-            const int rr = prev[1 + (int)(q / 27)], k = (int)(q % 27);
-            const int sg = rr % p.nseg + k % 3 - 1, t = rr / p.nseg;
-            const int y = t % p.Y + (k / 3) % 3 - 1, zl = t / p.Y + k / 9 - 1;
-            if (zl < zlo || zl >= zhi || y < 0 || y >= p.Y || sg < 0 || sg >= p.nseg) continue;
-            const int ridx = (zl * p.Y + y) * p.nseg + sg;
-            int old = sweep;
-            if (lane == 0) old = atomicExch(&p.stamp[ridx], sweep);
-            if (__shfl_sync(FULL, old, 0) == sweep) continue;  // another warp has this row
-            st.begin(p, zl, y, sg * WORDS_PER_WARP - 1 + lane, lane);
-            uint32_t s, inner, outer;
-            st.step(y, s, inner, outer);
-            flips += band_row<MODE, LATTICE>(p, s_dbits, zl, y, sg, s, inner, outer, st.active, true, lane);
+        // candidates = front rows x their (z, y, segment) neighbours; 32 candidates are claimed at once (one atomic
+        // per lane), then the warp walks the rows it won
+        const int nds = p.nseg > 1 ? 3 : 1, per = 9 * nds;
+        const long long ncand = (long long)prev[0] * per;
+        for (long long q0 = warp0 * 32; q0 < ncand; q0 += nwarps * 32) {
+            const long long q = q0 + lane;
+            int ridx = -1;
+            if (q < ncand) {
+                const int rr = prev[1 + (int)(q / per)], k = (int)(q % per);
+                const int sg = rr % p.nseg + (nds == 3 ? k % 3 - 1 : 0), t = rr / p.nseg;
+                const int y = t % p.Y + (k / nds) % 3 - 1, zl = t / p.Y + k / (3 * nds) - 1;
+                if (zl >= zlo && zl < zhi && y >= 0 && y < p.Y && sg >= 0 && sg < p.nseg) {
+                    ridx = (zl * p.Y + y) * p.nseg + sg;
+                    if (atomicExch(&p.stamp[ridx], sweep) == sweep) ridx = -1;  // another lane / warp has this row
+                }
+            }
+            unsigned won = __ballot_sync(FULL, ridx >= 0);
+            while (won) {
+                const int src = __ffs(won) - 1;
+                won &= won - 1;
+                const int r = __shfl_sync(FULL, ridx, src);
+                const int sg = r % p.nseg, t = r / p.nseg, y = t % p.Y, zl = t / p.Y;
+                st.begin(p, zl, y, sg * WORDS_PER_WARP - 1 + lane, lane);
+                uint32_t s, inner, outer;
+                st.step(y, s, inner, outer);
+                flips += band_row<MODE, LATTICE>(p, s_dbits, zl, y, sg, s, inner, outer, st.active, true, lane);
+            }
         }
     } else {
         const int nactive = p.ulist[0];  // built by k_table's spare blocks
