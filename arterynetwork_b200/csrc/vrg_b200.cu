@@ -45,8 +45,7 @@ struct vrg_handle {
     double *d_data = nullptr;
     uint8_t *d_vm = nullptr, *d_rowflag = nullptr, *d_labels = nullptr, *d_unitmap = nullptr;
     size_t unitmap_bytes = 0;
-    int *d_front = nullptr, *d_ulist = nullptr, *d_stamp = nullptr;
-    int sweep_units = 0;
+    int *d_front = nullptr, *d_dirty = nullptr, *d_stamp = nullptr;
     uint16_t *d_index = nullptr;
     uint32_t *d_S = nullptr, *d_E = nullptr, *d_F = nullptr, *d_C = nullptr;
     double *d_levels = nullptr, *d_pin = nullptr, *d_pout = nullptr, *d_kmat = nullptr;
@@ -171,10 +170,9 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     alloc((void **)&h->d_rowflag, h->rowflag_bytes);
     h->unitmap_bytes = (size_t)p.nzl * ((Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT) * p.nseg;
     alloc((void **)&h->d_unitmap, h->unitmap_bytes);
-    h->sweep_units = (int)(((size_t)h->nz_own + 2) * ((Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT) * p.nseg);
-    alloc((void **)&h->d_ulist, (1 + (size_t)h->sweep_units) * sizeof(int));
     p.front_cap = 1 + (int)((size_t)h->nz_own * Y * p.nseg);
     alloc((void **)&h->d_front, 2 * (size_t)p.front_cap * sizeof(int));
+    alloc((void **)&h->d_dirty, 2 * (size_t)p.front_cap * sizeof(int));
     alloc((void **)&h->d_stamp, h->rowflag_bytes * sizeof(int));
     alloc((void **)&h->d_ctrl, C_WORDS * sizeof(long long));
     alloc((void **)&h->d_trace, 3 * (cfg->iter_max + 2) * sizeof(long long));
@@ -187,7 +185,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
         return code;
     }
     (void)nvox;  // the input buffers are allocated on the first vrg_upload*; vrg_attach_device needs none
-    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag; p.front = h->d_front; p.unitmap = h->d_unitmap; p.ulist = h->d_ulist; p.stamp = h->d_stamp;
+    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag; p.front = h->d_front; p.unitmap = h->d_unitmap; p.dirty = h->d_dirty; p.stamp = h->d_stamp;
     p.data = h->d_data;
     p.ctrl = h->d_ctrl; p.trace = h->d_trace;
     *out = h;
@@ -199,7 +197,7 @@ int vrg_destroy(vrg_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_data); cudaFree(h->d_vm); cudaFree(h->d_index); cudaFree(h->d_labels);
-    cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_ulist); cudaFree(h->d_stamp);
+    cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_dirty); cudaFree(h->d_stamp);
     cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
     free_levels(h);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -455,7 +453,7 @@ int vrg_init(vrg_handle *h) {
     CK(cudaMemsetAsync(h->d_front, 0, 2 * (size_t)p.front_cap * sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_stamp, 0xFF, h->rowflag_bytes * sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_unitmap, 0, h->unitmap_bytes, h->stream));
-    CK(cudaMemsetAsync(h->d_ulist, 0, sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_dirty, 0, 2 * (size_t)p.front_cap * sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_lstats, 0, (size_t)(2 * p.L + ST_EXTRA) * sizeof(long long), h->stream));
     CK(cudaMemsetAsync(h->d_trace, 0, 3 * (h->cfg.iter_max + 2) * sizeof(long long), h->stream));
     long long c[C_WORDS];
@@ -498,7 +496,7 @@ int vrg_init(vrg_handle *h) {
 int vrg_enqueue_decide(vrg_handle *h) {
     NEED_INIT();
     const Params &p = h->p;
-    k_table<<<p.LW + (h->sweep_units + BLOCK - 1) / BLOCK, BLOCK, 0, h->stream>>>(p);
+    k_table<<<p.LW, BLOCK, 0, h->stream>>>(p);
     const size_t smem = (size_t)p.LW * sizeof(uint32_t);
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     if (h->cfg.intensity_mode == VRG_INTENSITY_F64_DENSE) {

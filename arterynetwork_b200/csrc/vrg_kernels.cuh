@@ -50,7 +50,7 @@ struct Params {
     uint32_t *S, *E, *F, *C;          // E, C: nullptr when the run never had label 4
     uint8_t *rowflag;                 // [nzl * Y * nseg]
     uint8_t *unitmap;                 // [nzl * nyb * nseg]: 1 if the sweep unit ever held a segmented voxel (never cleared)
-    int *ulist;                       // [1 + sweep units]: ulist[0] = count, then the units near a segmented voxel (band sweep)
+    int *dirty;                       // 2 x [front_cap]: rows the next incremental sweep must re-evaluate (built by k_flip)
     int *front;                       // 2 x [front_cap]: [0] = count, then the own-plane rows that flip in this sweep;
     int front_cap;                    //   sweep k writes list k & 1, the next sweep reads it as its dirty seed
     int *stamp;                       // [nzl * Y * nseg]: sweep number that last claimed the row (incremental pass)
@@ -73,6 +73,7 @@ struct Params {
 };
 
 __device__ __forceinline__ int *front_list(const Params &p, int which) { return p.front + (size_t)which * p.front_cap; }
+__device__ __forceinline__ int *dirty_list(const Params &p, int which) { return p.dirty + (size_t)which * p.front_cap; }
 
 __device__ __forceinline__ uint32_t valid_mask(const Params &p, int c) {
     return c < p.XW - 1 ? 0xFFFFFFFFu : (c == p.XW - 1 ? p.tail_mask : 0u);
@@ -131,36 +132,17 @@ __device__ __forceinline__ long long unit_index(const Params &p, int zl, int y, 
     return ((long long)zl * nyb + y / ROWS_PER_UNIT) * p.nseg + c / WORDS_PER_WARP;
 }
 // A sweep unit (one plane, ROWS_PER_UNIT rows, 30 words) can hold a band voxel only if it or one of its 26 neighbour
-// units (z, y-block, x-segment) holds a segmented voxel.  Thread `t` tests unit t of the sweep's unit space
-// (planes own-1 .. own+1) and appends it to the list the band sweep walks: far from every vessel costs nothing.
-__device__ __forceinline__ void build_unit_list(const Params &p, int t) {
-    const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
+// units (z, y-block, x-segment) holds a segmented voxel: far from every vessel the full band sweep skips the unit
+// after 27 byte loads (one per lane).
+__device__ __forceinline__ bool unit_near_segmented(const Params &p, int zl, int y0, int sg, int lane) {
     const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
-    const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
     bool hit = false;
-    if (t < nunits) {
-        const int sg = t % p.nseg, yb = (t / p.nseg) % nyb, zl = zlo + (t / p.nseg) / nyb;
-        for (int dz = -1; dz <= 1 && !hit; ++dz) {
-            const int zz = zl + dz;
-            if (zz < p.valid_lo || zz >= p.valid_hi) continue;
-            for (int dy = -1; dy <= 1 && !hit; ++dy) {
-                const int yy = yb + dy;
-                if (yy < 0 || yy >= nyb) continue;
-                for (int ds = -1; ds <= 1; ++ds) {
-                    const int ss = sg + ds;
-                    if (ss >= 0 && ss < p.nseg && p.unitmap[((long long)zz * nyb + yy) * p.nseg + ss]) { hit = true; break; }
-                }
-            }
-        }
+    if (lane < 27) {
+        const int zz = zl + lane / 9 - 1, yb = y0 / ROWS_PER_UNIT + (lane / 3) % 3 - 1, ss = sg + lane % 3 - 1;
+        if (zz >= p.valid_lo && zz < p.valid_hi && yb >= 0 && yb < nyb && ss >= 0 && ss < p.nseg)
+            hit = p.unitmap[((long long)zz * nyb + yb) * p.nseg + ss] != 0;
     }
-    const unsigned m = __ballot_sync(FULL, hit);
-    if (m) {
-        int base = 0;
-        const int lane = threadIdx.x & 31;
-        if (lane == 0) base = atomicAdd(&p.ulist[0], __popc(m));
-        base = __shfl_sync(FULL, base, 0);
-        if (hit) p.ulist[1 + base + __popc(m & ((1u << lane) - 1u))] = t;
-    }
+    return __ballot_sync(FULL, hit) != 0u;
 }
 
 // Parzen kernel matrix of a level set (symmetric: (lev_c - lev_b)^2 is exact either way round)
@@ -177,16 +159,13 @@ __global__ void __launch_bounds__(BLOCK) k_kmat(Params p, double *kmat) {
 // Fixed order: lane-strided partial sums, then an xor-shuffle tree -> deterministic.
 __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
-    if ((int)blockIdx.x >= p.LW) {  // spare blocks: list of sweep units that can hold a band voxel (see unit_is_active)
-        build_unit_list(p, ((int)blockIdx.x - p.LW) * BLOCK + threadIdx.x);
-        return;
-    }
     const long long *g = p.gstats;
     const long long n_in = g[2 * p.L + ST_N_IN], n_out = g[2 * p.L + ST_N_OUT];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctrl[C_APPLY] = n_in < p.ctrl[C_MAX_SEG];  // cap is tested before the flips are applied, VRG:101
         p.lstats[2 * p.L + ST_N_FLIPS] = 0;
         front_list(p, (int)(p.ctrl[C_SWEEPS] & 1))[0] = 0;
+        dirty_list(p, (int)((p.ctrl[C_SWEEPS] + 1) & 1))[0] = 0;  // k_flip of this iteration fills it for the next sweep
     }
     __shared__ uint32_t s_bits[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -353,7 +332,7 @@ __device__ __forceinline__ int band_row(const Params &p, const uint32_t *s_dbits
 //   inner = S & dil26(~S in volume)      (segmented with an unsegmented in-bounds neighbour, VRG:139-142)
 //   outer = ~S & ~E & dil26(S)           (unsegmented, not excluded, with a segmented neighbour, VRG:143-145)
 // Full pass: a warp owns a strip of ROWS_PER_UNIT rows x 30 words of one plane and slides down it, over the units
-// near a segmented voxel (ulist).
+// near a segmented voxel (unit occupancy map).
 // Incremental pass (single slab, decision table unchanged since the last sweep): a voxel's flip flag can differ
 // from last time only if a voxel of its 26-neighbourhood flipped, so only the rows within one row / plane /
 // segment of last sweep's front rows are re-evaluated (each claimed once through `stamp`); every other row keeps
@@ -373,40 +352,21 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
     Strip st;
     const bool single_slab = p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
     if (single_slab && p.ctrl[C_TABLE_CHANGED] == 0) {
-        const int sweep = (int)p.ctrl[C_SWEEPS];
-        const int *prev = front_list(p, (sweep & 1) ^ 1);
-        // candidates = front rows x their (z, y, segment) neighbours; 32 candidates are claimed at once (one atomic
-        // per lane), then the warp walks the rows it won
-        const int nds = p.nseg > 1 ? 3 : 1, per = 9 * nds;
-        const long long ncand = (long long)prev[0] * per;
-        for (long long q0 = warp0 * 32; q0 < ncand; q0 += nwarps * 32) {
-            const long long q = q0 + lane;
-            int ridx = -1;
-            if (q < ncand) {
-                const int rr = prev[1 + (int)(q / per)], k = (int)(q % per);
-                const int sg = rr % p.nseg + (nds == 3 ? k % 3 - 1 : 0), t = rr / p.nseg;
-                const int y = t % p.Y + (k / nds) % 3 - 1, zl = t / p.Y + k / (3 * nds) - 1;
-                if (zl >= zlo && zl < zhi && y >= 0 && y < p.Y && sg >= 0 && sg < p.nseg) {
-                    ridx = (zl * p.Y + y) * p.nseg + sg;
-                    if (atomicExch(&p.stamp[ridx], sweep) == sweep) ridx = -1;  // another lane / warp has this row
-                }
-            }
-            unsigned won = __ballot_sync(FULL, ridx >= 0);
-            while (won) {
-                const int src = __ffs(won) - 1;
-                won &= won - 1;
-                const int r = __shfl_sync(FULL, ridx, src);
-                const int sg = r % p.nseg, t = r / p.nseg, y = t % p.Y, zl = t / p.Y;
-                st.begin(p, zl, y, sg * WORDS_PER_WARP - 1 + lane, lane);
-                uint32_t s, inner, outer;
-                st.step(y, s, inner, outer);
-                flips += band_row<MODE, LATTICE>(p, s_dbits, zl, y, sg, s, inner, outer, st.active, true, lane);
-            }
+        const int *dl = dirty_list(p, (int)(p.ctrl[C_SWEEPS] & 1));  // built by the previous iteration's k_flip
+        const int n = dl[0];
+        for (int i = (int)warp0; i < n; i += (int)nwarps) {
+            const int r = dl[1 + i];
+            const int sg = r % p.nseg, t = r / p.nseg, y = t % p.Y, zl = t / p.Y;
+            st.begin(p, zl, y, sg * WORDS_PER_WARP - 1 + lane, lane);
+            uint32_t s, inner, outer;
+            st.step(y, s, inner, outer);
+            flips += band_row<MODE, LATTICE>(p, s_dbits, zl, y, sg, s, inner, outer, st.active, true, lane);
         }
     } else {
-        const int nactive = p.ulist[0];  // built by k_table's spare blocks
-        for (int i = (int)warp0; i < nactive; i += (int)nwarps) {
-            const Unit un = decode_unit(p, p.ulist[1 + i], zlo, nyb);
+        const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
+        for (long long u = warp0; u < nunits; u += nwarps) {
+            const Unit un = decode_unit(p, u, zlo, nyb);
+            if (!unit_near_segmented(p, un.zl, un.y0, un.sg, lane)) continue;
             const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
             st.begin(p, un.zl, un.y0, un.sg * WORDS_PER_WARP - 1 + lane, lane);
             for (int y = un.y0; y < un.y1; ++y) {
@@ -689,6 +649,10 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
 __global__ void __launch_bounds__(BLOCK) k_flip(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
     const int lane = threadIdx.x & 31;
+    const bool single_slab = p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
+    const int next = (int)p.ctrl[C_SWEEPS] + 1;  // the sweep that will read the dirty list
+    int *dl = dirty_list(p, next & 1);
+    const int nds = p.nseg > 1 ? 3 : 1;
     for_front_rows(p, [&](int zl, int y, int sg) {
         const int c = sg * WORDS_PER_WARP + lane;
         if (lane < WORDS_PER_WARP && c < p.XW) {
@@ -697,6 +661,23 @@ __global__ void __launch_bounds__(BLOCK) k_flip(Params p) {
             if (f) {
                 p.S[widx] ^= f;
                 p.unitmap[unit_index(p, zl, y, c)] = 1;
+            }
+        }
+        if (single_slab) {  // this row and its (z, y, segment) neighbours may change band status: claim each once
+            int ridx = -1;
+            if (lane < 9 * nds) {
+                const int ss = sg + (nds == 3 ? lane % 3 - 1 : 0), yy = y + (lane / nds) % 3 - 1, zz = zl + lane / (3 * nds) - 1;
+                if (zz >= p.own_lo && zz < p.own_hi && yy >= 0 && yy < p.Y && ss >= 0 && ss < p.nseg) {
+                    ridx = (zz * p.Y + yy) * p.nseg + ss;
+                    if (atomicExch(&p.stamp[ridx], next) == next) ridx = -1;
+                }
+            }
+            const unsigned won = __ballot_sync(FULL, ridx >= 0);
+            if (won) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&dl[0], __popc(won));
+                base = __shfl_sync(FULL, base, 0);
+                if (ridx >= 0) dl[1 + base + __popc(won & ((1u << lane) - 1u))] = ridx;
             }
         }
     });
@@ -800,7 +781,6 @@ __global__ void k_advance(Params p) {
     c[C_APPLIED] += 1;
     c[C_ITER] += 1;
     c[C_TABLE_CHANGED] = 0;  // k_table of the next iteration raises it again if a decision bit moves
-    p.ulist[0] = 0;  // the next k_table rebuilds the active-unit list
     if (c[C_ITER] > c[C_ITER_MAX]) c[C_STATUS] = 3;        // VRG:58,118
 }
 
