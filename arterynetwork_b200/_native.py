@@ -56,6 +56,7 @@ _SIGS = {
     "vrg_buffer_info": [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(i64)],
     "vrg_plane_geometry": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)],
     "vrg_use_separate_global_stats": [vp],
+    "vrg_params_signature": [vp, ctypes.POINTER(ctypes.c_uint64)],
     "vrg_download_labels": [vp, vp],
     "vrg_download_segmented_map": [vp, vp],
     "vrg_labels_device": [vp, vp],

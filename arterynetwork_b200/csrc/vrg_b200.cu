@@ -600,6 +600,16 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
     return VRG_OK;
 }
 
+// FNV-1a over the kernel parameter block: a host that replays captured launches (CUDA graphs) re-captures when it moves
+int vrg_params_signature(vrg_handle *h, uint64_t *sig) {
+    if (!h || !sig) return fail(VRG_ERR_ARG, "null argument");
+    uint64_t x = 1469598103934665603ull;
+    const unsigned char *b = (const unsigned char *)&h->p;
+    for (size_t i = 0; i < sizeof(Params); ++i) { x ^= b[i]; x *= 1099511628211ull; }
+    *sig = x ^ (uint64_t)h->cfg.intensity_mode;
+    return VRG_OK;
+}
+
 int vrg_profile(vrg_handle *h, int enable) {
     if (!h) return fail(VRG_ERR_ARG, "null handle");
     h->prof = enable != 0;

@@ -199,7 +199,7 @@ class DistributedVRG:
 
     def _graph_for_current_buffers(self):
         e, torch = self.e, self.torch
-        key = (self.has_excl, self.check_every) + tuple(int(t.data_ptr()) for t in (
+        key = (self.has_excl, self.check_every, e.eng.params_signature()) + tuple(int(t.data_ptr()) for t in (
             e.seg, e.excl, e.flips, e.cancelled, e.local_stats, e.global_stats))
         if self._graph is None or key != self._graph_key:
             g = torch.cuda.CUDAGraph()

@@ -149,6 +149,11 @@ class VRGEngine:
     def use_separate_global_stats(self):
         nat.check(self.lib.vrg_use_separate_global_stats(self._h))
 
+    def params_signature(self) -> int:
+        sig = ctypes.c_uint64(0)
+        nat.check(self.lib.vrg_params_signature(self._h, ctypes.byref(sig)))
+        return int(sig.value)
+
     def buffer(self, which):
         p, n = nat.vp(), nat.i64()
         nat.check(self.lib.vrg_buffer_info(self._h, which, ctypes.byref(p), ctypes.byref(n)))

@@ -136,6 +136,8 @@ int vrg_buffer_info(vrg_handle *h, int which, void **dev_ptr, int64_t *bytes);
 /* bit-plane geometry: words (uint32, 32 voxels along x) per row and rows*words per plane */
 int vrg_plane_geometry(vrg_handle *h, int64_t *words_per_row, int64_t *words_per_plane, int64_t *n_planes_local);
 int vrg_use_separate_global_stats(vrg_handle *h); /* multi-GPU: un-alias GLOBAL from LOCAL */
+/* hash of the kernel parameter block: hosts that replay captured launches (CUDA graphs) re-capture when it changes */
+int vrg_params_signature(vrg_handle *h, uint64_t *signature);
 
 /* outputs: the return values of VRG:96 -------------------------------------- */
 int vrg_download_labels(vrg_handle *h, uint8_t *value_map_out);   /* own planes, canonical labels 0..4 */
