@@ -16,6 +16,7 @@ EXIT_RUNNING, EXIT_CONVERGED, EXIT_MAX_TIME, EXIT_MAX_SEGMENT, EXIT_MAX_ITER = -
 INTENSITY_F64_DENSE, INTENSITY_F64_BAND, INTENSITY_INDEX = 0, 1, 2
 INTENSITY_MODES = {"f64_dense": 0, "f64_band": 1, "index": 2}
 HALO = 2
+P2P_HANDLE_BYTES = 192
 BUF_SEG, BUF_EXCL, BUF_FLIPS, BUF_CANCELLED, BUF_LOCAL_STATS, BUF_GLOBAL_STATS, BUF_CTRL = range(7)
 ST_N_IN, ST_N_OUT, ST_N_EXCL, ST_N_FLIPS, ST_N_BAND, ST_BAD_LABEL, ST_NONFINITE, ST_EXTRA = 0, 1, 2, 3, 4, 5, 6, 8
 C_STATUS, C_ITER, C_ITER_MAX, C_MAX_SEG, C_APPLY, C_APPLIED, C_TRACE_N, C_SWEEPS = range(8)
@@ -57,6 +58,10 @@ _SIGS = {
     "vrg_plane_geometry": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)],
     "vrg_use_separate_global_stats": [vp],
     "vrg_params_signature": [vp, ctypes.POINTER(ctypes.c_uint64)],
+    "vrg_p2p_export": [vp, ctypes.c_int, vp],
+    "vrg_p2p_connect": [vp, ctypes.c_int, ctypes.c_int, vp],
+    "vrg_enqueue_p2p_halo": [vp, ctypes.c_int],
+    "vrg_enqueue_p2p_stats": [vp],
     "vrg_download_labels": [vp, vp],
     "vrg_download_segmented_map": [vp, vp],
     "vrg_labels_device": [vp, vp],

@@ -2,6 +2,7 @@
 // every compute entry point launches the sm_100a kernels in vrg_kernels.cuh or fails).
 #include "../../include/vrg_b200.h"
 #include "vrg_kernels.cuh"
+#include "vrg_p2p.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -68,6 +69,14 @@ struct vrg_handle {
     int64_t prof_sweeps0 = 0;      // C_SWEEPS when the pending events started
     double prof_ms[2] = {0, 0};
     int64_t prof_n[2] = {0, 0};
+    // peer-memory transport (multi-GPU, see vrg_p2p.cuh)
+    bool p2p_on = false;
+    P2P q;
+    uint32_t *d_recv = nullptr;
+    unsigned long long *d_flags = nullptr;
+    long long *d_slots = nullptr;
+    std::vector<void *> ipc_opened;
+    long long epoch = 0;
 };
 
 static const int HASH_CAP = 1 << 18;
@@ -200,6 +209,8 @@ int vrg_destroy(vrg_handle *h) {
     cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_dirty); cudaFree(h->d_stamp);
     cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
     free_levels(h);
+    for (void *o : h->ipc_opened) cudaIpcCloseMemHandle(o);
+    cudaFree(h->d_recv); cudaFree(h->d_flags); cudaFree(h->d_slots);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -444,6 +455,7 @@ int vrg_init(vrg_handle *h) {
         rc = vrg_set_levels(h, lv.data(), (int64_t)lv.size());
         if (rc != VRG_OK) return rc;
     }
+    if (h->p2p_on) { int rc_ = vrg_use_separate_global_stats(h); if (rc_ != VRG_OK) return rc_; }
     Params &p = h->p;
     CK(cudaMemsetAsync(h->d_S, 0, h->plane_bytes, h->stream));
     CK(cudaMemsetAsync(h->d_E, 0, h->plane_bytes, h->stream));
@@ -461,6 +473,7 @@ int vrg_init(vrg_handle *h) {
     c[C_STATUS] = RUNNING; c[C_ITER] = 1; c[C_ITER_MAX] = h->cfg.iter_max; c[C_MAX_SEG] = h->cfg.max_segment_size;
     c[C_TRACE_N] = 1;
     c[C_TABLE_CHANGED] = 1;  // the first sweep is a full one
+    c[C_EPOCH] = ++h->epoch;  // same on every rank: sequence numbers of the peer exchanges
     memcpy(h->h_ctrl, c, sizeof c);
     CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof c, cudaMemcpyHostToDevice, h->stream));
     p.E = h->d_E; p.C = h->d_C;
@@ -469,16 +482,27 @@ int vrg_init(vrg_handle *h) {
     { int rc_ = launch_init_hist(h); if (rc_ != VRG_OK) return rc_; }
     h->launches += 3;
     CK(cudaGetLastError());
+    if (h->p2p_on) {  // slabs: excluded halo planes and the global statistics, over peer memory
+        k_p2p_push_halo<<<h->sms, BLOCK, 0, h->stream>>>(p, h->q, 1 << PK_E, 1);
+        k_p2p_wait_unpack_halo<<<h->sms, BLOCK, 0, h->stream>>>(p, h->q, 1 << PK_E, 1);
+        k_p2p_push_stats<<<8, BLOCK, 0, h->stream>>>(p, h->q, 1);
+        k_p2p_reduce_stats<<<8, BLOCK, 0, h->stream>>>(p, h->q, h->d_gstats, 1);
+        h->launches += 4;
+        CK(cudaGetLastError());
+    }
     // the init row of the trace and the error checks need the counters on the host
     std::vector<long long> ex(ST_EXTRA);
-    CK(cudaMemcpyAsync(ex.data(), h->d_lstats + 2 * p.L, ST_EXTRA * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    const long long *src_stats = h->p2p_on ? h->d_gstats : h->d_lstats;
+    CK(cudaMemcpyAsync(ex.data(), src_stats + 2 * p.L, ST_EXTRA * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->h_ctrl[C_STATUS] == EXIT_PEER_TIMEOUT) return fail(VRG_ERR_CUDA, "peer GPU did not answer during init (p2p timeout)");
     if (ex[ST_BAD_LABEL]) return fail(VRG_ERR_LABEL, "initial valueMap may only hold labels 0 (seed), 3 (outside) and 4 (excluded)");
-    if (ex[ST_N_EXCL] == 0 && !h->separate_gstats) { p.E = nullptr; p.C = nullptr; }  // no label 4: skip the absorb path
+    if (ex[ST_N_EXCL] == 0 && (!h->separate_gstats || h->p2p_on)) { p.E = nullptr; p.C = nullptr; }  // no label 4: skip the absorb path
     h->inited = true;
     h->ev_used = 0;
     h->prof_sweeps0 = 0;
-    if (!h->separate_gstats) {  // single slab: the global view is the local one
+    if (!h->separate_gstats || h->p2p_on) {  // the global view is known here (single slab, or slabs over peer memory)
         if (ex[ST_N_IN] == 0) return fail(VRG_ERR_EMPTY_SEED, "no seed voxel (label 0) in valueMap");
         if (ex[ST_N_BAND] == 0) return fail(VRG_ERR_NO_BAND, "seed has no boundary: every voxel is inside");
         long long row[3] = {-1, ex[ST_N_IN], ex[ST_N_OUT]};
@@ -551,6 +575,83 @@ int vrg_enqueue_advance(vrg_handle *h) {
     return VRG_OK;
 }
 
+// ---- peer-memory transport ---------------------------------------------------------------------------
+// phase 0: executed flips (and cancelled flips when label 4 is present) after cancel; phase 1: excluded plane after flip
+int vrg_enqueue_p2p_halo(vrg_handle *h, int phase) {
+    NEED_INIT();
+    if (!h->p2p_on) return fail(VRG_ERR_ARG, "p2p transport not connected");
+    const int kinds = phase == 0 ? ((1 << PK_F) | (h->p.E ? (1 << PK_C) : 0)) : (h->p.E ? (1 << PK_E) : 0);
+    if (!kinds) return VRG_OK;
+    k_p2p_push_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p, h->q, kinds, 0);
+    k_p2p_wait_unpack_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p, h->q, kinds, 0);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
+int vrg_enqueue_p2p_stats(vrg_handle *h) {
+    NEED_INIT();
+    if (!h->p2p_on) return fail(VRG_ERR_ARG, "p2p transport not connected");
+    k_p2p_push_stats<<<8, BLOCK, 0, h->stream>>>(h->p, h->q, 0);
+    k_p2p_reduce_stats<<<8, BLOCK, 0, h->stream>>>(h->p, h->q, h->d_gstats, 0);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
+
+// Allocates this rank's receive buffer, flag words and statistics mailbox and returns their three CUDA IPC handles
+// (3 x 64 bytes).  Every rank then passes all ranks' handles, in rank order, to vrg_p2p_connect.
+int vrg_p2p_export(vrg_handle *h, int world, void *handles_out) {
+    if (!h || !handles_out || world < 2 || world > P2P_MAX_WORLD) return fail(VRG_ERR_ARG, "world must be 2..%d", P2P_MAX_WORLD);
+    CK(cudaSetDevice(h->cfg.device));
+    const Params &p = h->p;
+    const int slot_words = 2 * VRG_MAX_LEVELS + ST_EXTRA;
+    if (!h->d_recv) {
+        const size_t rb = (size_t)P2P_KINDS * 2 * HALO * p.plane_words * sizeof(uint32_t);
+        const size_t sb = (size_t)2 * world * slot_words * sizeof(long long);
+        CK(cudaMalloc((void **)&h->d_recv, rb));
+        CK(cudaMalloc((void **)&h->d_flags, FLAG_WORDS * sizeof(unsigned long long)));
+        CK(cudaMalloc((void **)&h->d_slots, sb));
+        CK(cudaMemset(h->d_recv, 0, rb));
+        CK(cudaMemset(h->d_flags, 0, FLAG_WORDS * sizeof(unsigned long long)));
+        CK(cudaMemset(h->d_slots, 0, sb));
+    }
+    cudaIpcMemHandle_t *out = (cudaIpcMemHandle_t *)handles_out;
+    CK(cudaIpcGetMemHandle(&out[0], h->d_recv));
+    CK(cudaIpcGetMemHandle(&out[1], h->d_flags));
+    CK(cudaIpcGetMemHandle(&out[2], h->d_slots));
+    h->q.slot_words = slot_words;
+    h->q.world = world;
+    return VRG_OK;
+}
+
+int vrg_p2p_connect(vrg_handle *h, int rank, int world, const void *all_handles) {
+    if (!h || !all_handles || !h->d_recv || world != h->q.world || rank < 0 || rank >= world)
+        return fail(VRG_ERR_ARG, "export first, then connect with the same world size");
+    CK(cudaSetDevice(h->cfg.device));
+    const cudaIpcMemHandle_t *hs = (const cudaIpcMemHandle_t *)all_handles;
+    P2P &q = h->q;
+    q.rank = rank; q.world = world;
+    q.flags = h->d_flags; q.slots = h->d_slots; q.recv = h->d_recv;
+    q.peer_recv[0] = q.peer_recv[1] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { q.peer_flags[r] = h->d_flags; q.peer_slots[r] = h->d_slots; continue; }
+        void *pf = nullptr, *ps = nullptr;
+        CK(cudaIpcOpenMemHandle(&pf, hs[3 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&ps, hs[3 * r + 2], cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened.push_back(pf); h->ipc_opened.push_back(ps);
+        q.peer_flags[r] = (unsigned long long *)pf; q.peer_slots[r] = (long long *)ps;
+        if (r == rank - 1 || r == rank + 1) {
+            void *pr = nullptr;
+            CK(cudaIpcOpenMemHandle(&pr, hs[3 * r + 0], cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened.push_back(pr);
+            q.peer_recv[r == rank - 1 ? 0 : 1] = (uint32_t *)pr;
+        }
+    }
+    h->p2p_on = true;
+    h->inited = false;
+    return VRG_OK;
+}
+
 int vrg_poll(vrg_handle *h, vrg_result *res) {
     NEED_INIT();
     long long ex[ST_EXTRA];
@@ -579,12 +680,16 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
             int rc;
             if ((rc = vrg_enqueue_decide(h)) != VRG_OK) return rc;
             if ((rc = vrg_enqueue_cancel(h)) != VRG_OK) return rc;
+            if (h->p2p_on && (rc = vrg_enqueue_p2p_halo(h, 0)) != VRG_OK) return rc;
             if ((rc = vrg_enqueue_absorb(h)) != VRG_OK) return rc;
             if ((rc = vrg_enqueue_flip(h)) != VRG_OK) return rc;
+            if (h->p2p_on && (rc = vrg_enqueue_p2p_halo(h, 1)) != VRG_OK) return rc;
+            if (h->p2p_on && (rc = vrg_enqueue_p2p_stats(h)) != VRG_OK) return rc;
             if ((rc = vrg_enqueue_advance(h)) != VRG_OK) return rc;
         }
         int rc = vrg_poll(h, &r);
         if (rc != VRG_OK) return rc;
+        if (r.exit_reason == EXIT_PEER_TIMEOUT) return fail(VRG_ERR_CUDA, "peer GPU did not answer (p2p timeout)");
         if (r.exit_reason != VRG_EXIT_RUNNING) break;
         if (h->cfg.max_seconds > 0 &&
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= h->cfg.max_seconds) {

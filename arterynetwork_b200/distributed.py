@@ -122,7 +122,7 @@ class DistributedVRG:
     the device-side status word, so replays after the exit are no-ops.
     """
 
-    def __init__(self, engine, rank, world, check_every=4, use_graph=False):
+    def __init__(self, engine, rank, world, check_every=4, use_graph=False, transport="collective"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -132,6 +132,22 @@ class DistributedVRG:
         self.has_excl = True
         self.use_graph = bool(use_graph)
         self._graph, self._graph_key = None, None
+        # "collective": halo send/recv + all-reduce through torch.distributed (NCCL on GPUs, gloo on CPU), host-driven.
+        # "p2p": the library's own kernels move halos and statistics over NVLink peer memory (vrg_p2p.cuh); the host
+        #        only gathers the CUDA IPC handles once, then every rank calls vrg_init / vrg_run as on one GPU.
+        self.transport = transport
+        self._p2p_connected = False
+
+    def _connect_p2p(self):
+        if self._p2p_connected:
+            return
+
+        def gather(mine: bytes):
+            out = [None] * self.world
+            self.dist.all_gather_object(out, mine)
+            return out
+        self.e.eng.p2p_connect(self.rank, self.world, gather)
+        self._p2p_connected = True
 
     # -- collectives ----------------------------------------------------------------------------
     def _exchange(self, t):
@@ -163,6 +179,12 @@ class DistributedVRG:
         return levels
 
     def init(self):
+        if self.transport == "p2p":
+            self._connect_p2p()
+            self.dist.barrier()  # the init exchange spins on the peers: start together
+            self.e.eng.init()    # seeds, bands, histograms + device-side halo / statistics exchange and the error checks
+            self.init_row = tuple(int(x) for x in self.e.eng.trace()[0])
+            return
         self.e.init()
         self._exchange(self.e.excl)  # the 4->3 absorption around seeds (VRG:137) is computed for own planes +-1 only
         self._allreduce_stats()
@@ -209,6 +231,8 @@ class DistributedVRG:
         return self._graph
 
     def run(self):
+        if self.transport == "p2p":
+            return self.e.eng.run()  # the whole loop, exchanges included, is enqueued by the library
         first = True
         while True:
             if self.use_graph and not first:
@@ -249,11 +273,13 @@ def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
     d_data, d_vm = bench.device_phantom(shape, args.seed, e0, e1 - e0, local)
     torch.cuda.synchronize()
     side = torch.cuda.Stream()  # CUDA graphs cannot be captured on the default stream
-    use_graph = os.environ.get("VRG_NO_GRAPH") is None
+    transport = os.environ.get("VRG_TRANSPORT", "p2p")       # p2p: peer-memory kernels; collective: NCCL via torch
+    use_graph = os.environ.get("VRG_GRAPH") == "1"            # CUDA-graph replay of the collective path (experimental)
     with torch.cuda.stream(side):
         eng = VRGEngine(shape, max_segment_size=10 ** 15, intensity=args.intensity, device=local, z_begin=z0, z_end=z1)
         eng.set_stream(side.cuda_stream)
-        drv = DistributedVRG(GpuSlabEngine(eng, local), rank, world, check_every=8, use_graph=use_graph)
+        drv = DistributedVRG(GpuSlabEngine(eng, local), rank, world, check_every=8, use_graph=use_graph,
+                             transport=transport)
 
         def step():
             eng.attach_device(d_data.data_ptr(), d_vm.data_ptr())
@@ -327,7 +353,7 @@ def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
             "config": {"workload": "%s %dx%dx%d vessel-forest phantom, seed %d" % (args.workload, shape[2], shape[1], shape[0], args.seed),
                        "intensity_mode": args.intensity, "partition": "z-slabs, %d planes per rank, halo %d" % (z1 - z0, HALO),
                        "sweeps_per_step": sweeps // args.steps, "segmented_voxels": res["n_in"],
-                       "label_histogram": [int(x) for x in cs.tolist()], "cuda_graph": use_graph,
+                       "label_histogram": [int(x) for x in cs.tolist()], "transport": transport, "cuda_graph": use_graph,
                        "l2": "inputs larger than L2; no flush",
                        "step": "attach resident slab (zero-copy) + level scan/all-gather + init + all iterations"},
             "clocks": clocks,

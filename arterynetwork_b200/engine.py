@@ -149,6 +149,15 @@ class VRGEngine:
     def use_separate_global_stats(self):
         nat.check(self.lib.vrg_use_separate_global_stats(self._h))
 
+    def p2p_connect(self, rank: int, world: int, all_gather_bytes):
+        """Peer-memory transport: export this rank's IPC handles, gather everyone's with ``all_gather_bytes``
+        (a callable: bytes -> list of bytes in rank order), and map the peers' buffers."""
+        mine = ctypes.create_string_buffer(nat.P2P_HANDLE_BYTES)
+        nat.check(self.lib.vrg_p2p_export(self._h, int(world), ctypes.addressof(mine)))
+        everyone = all_gather_bytes(bytes(mine.raw))
+        blob = ctypes.create_string_buffer(b"".join(everyone), nat.P2P_HANDLE_BYTES * int(world))
+        nat.check(self.lib.vrg_p2p_connect(self._h, int(rank), int(world), ctypes.addressof(blob)))
+
     def params_signature(self) -> int:
         sig = ctypes.c_uint64(0)
         nat.check(self.lib.vrg_params_signature(self._h, ctypes.byref(sig)))

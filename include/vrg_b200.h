@@ -139,6 +139,17 @@ int vrg_use_separate_global_stats(vrg_handle *h); /* multi-GPU: un-alias GLOBAL 
 /* hash of the kernel parameter block: hosts that replay captured launches (CUDA graphs) re-capture when it changes */
 int vrg_params_signature(vrg_handle *h, uint64_t *signature);
 
+/* Peer-memory transport for z-slab runs on the GPUs of one box (one process per GPU): the halo planes and the
+ * statistics all-reduce move by this library's own kernels over NVLink (CUDA IPC mappings), so vrg_init / vrg_run
+ * drive a slab exactly like a single volume and every rank simply calls them at the same time.
+ *   1. every rank: vrg_p2p_export -> 3 CUDA IPC handles (192 bytes);  2. gather all ranks' handles in rank order;
+ *   3. every rank: vrg_p2p_connect;  4. host barrier;  5. vrg_init, vrg_run on every rank. */
+#define VRG_P2P_HANDLE_BYTES 192
+int vrg_p2p_export(vrg_handle *h, int world, void *handles_out /* VRG_P2P_HANDLE_BYTES */);
+int vrg_p2p_connect(vrg_handle *h, int rank, int world, const void *all_handles /* world * VRG_P2P_HANDLE_BYTES */);
+int vrg_enqueue_p2p_halo(vrg_handle *h, int phase); /* 0: flips (+cancelled) after cancel; 1: excluded plane after flip */
+int vrg_enqueue_p2p_stats(vrg_handle *h);           /* statistics all-reduce, before advance */
+
 /* outputs: the return values of VRG:96 -------------------------------------- */
 int vrg_download_labels(vrg_handle *h, uint8_t *value_map_out);   /* own planes, canonical labels 0..4 */
 int vrg_download_segmented_map(vrg_handle *h, uint8_t *seg_out);  /* own planes, 0/1 */

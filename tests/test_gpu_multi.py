@@ -1,4 +1,4 @@
-"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): the NCCL z-slab run must equal the
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): the z-slab run (peer-memory and NCCL transports) must equal the
 whole-volume C oracle and the single-GPU run bit for bit -- labels, iteration count and trace."""
 import os
 import socket
@@ -27,7 +27,7 @@ def _case(name):
     raise KeyError(name)
 
 
-def _worker(rank, world, port, name, mode, out_dir):
+def _worker(rank, world, port, name, mode, transport, out_dir):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch
@@ -41,7 +41,7 @@ def _worker(rank, world, port, name, mode, out_dir):
     eng = VRGEngine(data.shape, max_segment_size=max_seg, intensity=mode, device=rank, z_begin=b[rank], z_end=b[rank + 1])
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     eng.upload(data, vm)
-    drv = DistributedVRG(GpuSlabEngine(eng, rank), rank, world, check_every=3)
+    drv = DistributedVRG(GpuSlabEngine(eng, rank), rank, world, check_every=3, transport=transport)
     drv.prepare_levels()
     drv.init()
     res = drv.run()
@@ -52,8 +52,9 @@ def _worker(rank, world, port, name, mode, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["p2p", "collective"])
 @pytest.mark.parametrize("name,mode", [("forest", "f64_dense"), ("forest", "index"), ("excl", "f64_band")])
-def test_nccl_slabs_equal_oracle(name, mode, tmp_path):
+def test_slabs_equal_oracle(name, mode, transport, tmp_path):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
@@ -62,7 +63,7 @@ def test_nccl_slabs_equal_oracle(name, mode, tmp_path):
     from oracle.c_oracle import vrg_oracle_c
     data, vm, max_seg = _case(name)
     ref = vrg_oracle_c(data, vm, max_segment_size=max_seg)
-    mp.spawn(_worker, args=(world, _free_port(), name, mode, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), name, mode, transport, str(tmp_path)), nprocs=world, join=True)
     parts = [np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(world)]
     assert np.array_equal(np.concatenate([p["labels"] for p in parts]), ref["labels"])
     for p in parts:
