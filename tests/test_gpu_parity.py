@@ -179,6 +179,21 @@ def test_iteration_cap():
     assert np.array_equal(o["labels"], ref["labels"]) and np.array_equal(o["trace"], ref["trace"])
 
 
+def test_config_c2_matches_c_oracle():
+    """BASELINE.json configs[1]: 512x512x170 MRA-sized phantom, all three sweep modes against the C oracle."""
+    from arterynetwork_b200.phantom import make_phantom
+    from oracle.c_oracle import vrg_oracle_c
+    shape = (170, 512, 512)
+    data, vm, info = make_phantom(shape, seed=0)
+    ref = vrg_oracle_c(data, vm, max_segment_size=10 ** 15)
+    assert 20 <= ref["iterations"] <= 200 and int(ref["seg"].sum()) == info["tube_voxels"]
+    for mode in MODES:
+        o = run_engine(data, vm, 2.25, 10 ** 15, mode)
+        assert o["iterations"] == ref["iterations"]
+        assert np.array_equal(o["trace"], ref["trace"])
+        assert np.array_equal(o["labels"], ref["labels"])
+
+
 def test_attach_device_runs_in_place_and_can_rerun():
     """Zero-copy resident inputs (vrg_attach_device): same result, inputs untouched, handle reusable with new seeds."""
     import torch
