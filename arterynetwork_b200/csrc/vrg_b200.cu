@@ -77,6 +77,11 @@ struct vrg_handle {
     long long *d_slots = nullptr;
     std::vector<void *> ipc_opened;
     long long epoch = 0;
+    // CUDA graph of one batch of iterations (vrg_run)
+    cudaGraphExec_t gexec = nullptr;
+    uint64_t gsig = 0;
+    int64_t glaunches = 0;
+    bool graph_ok = true;
 };
 
 static const int HASH_CAP = 1 << 18;
@@ -147,7 +152,8 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     h->sms = prop.multiProcessorCount;
     h->grid = h->sms * 8;
-    h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;  // A/B switch: dense sweep with plain loads instead of the TMA ring
+    h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;
+    h->graph_ok = getenv("VRG_NO_GRAPH") == nullptr;  // A/B switch: dense sweep with plain loads instead of the TMA ring
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     Params &p = h->p;
@@ -209,6 +215,7 @@ int vrg_destroy(vrg_handle *h) {
     cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_dirty); cudaFree(h->d_stamp);
     cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
     free_levels(h);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (void *o : h->ipc_opened) cudaIpcCloseMemHandle(o);
     cudaFree(h->d_recv); cudaFree(h->d_flags); cudaFree(h->d_slots);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -224,6 +231,7 @@ int vrg_set_stream(vrg_handle *h, void *s) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
     h->stream = (cudaStream_t)s;
+    h->graph_ok = getenv("VRG_NO_GRAPH") == nullptr;
     return VRG_OK;
 }
 
@@ -520,7 +528,7 @@ int vrg_init(vrg_handle *h) {
 int vrg_enqueue_decide(vrg_handle *h) {
     NEED_INIT();
     const Params &p = h->p;
-    k_table<<<p.LW, BLOCK, 0, h->stream>>>(p);
+    k_table<<<p.LW, TABLE_BLOCK, 0, h->stream>>>(p);
     const size_t smem = (size_t)p.LW * sizeof(uint32_t);
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     if (h->cfg.intensity_mode == VRG_INTENSITY_F64_DENSE) {
@@ -562,7 +570,9 @@ int vrg_enqueue_absorb(vrg_handle *h) {
 }
 int vrg_enqueue_flip(vrg_handle *h) {
     NEED_INIT();
-    k_flip<<<h->grid, BLOCK, 0, h->stream>>>(h->p);
+    // own planes were flipped inside k_cancel; only a slab with neighbours has halo planes to follow
+    if (h->p.valid_lo == h->p.own_lo && h->p.valid_hi == h->p.own_hi) return VRG_OK;
+    k_flip_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p);
     h->launches++;
     CK(cudaGetLastError());
     return VRG_OK;
@@ -670,23 +680,75 @@ int vrg_poll(vrg_handle *h, vrg_result *res) {
     return VRG_OK;
 }
 
+static int enqueue_batch(vrg_handle *h, int n) {
+    for (int k = 0; k < n; ++k) {
+        int rc;
+        if ((rc = vrg_enqueue_decide(h)) != VRG_OK) return rc;
+        if ((rc = vrg_enqueue_cancel(h)) != VRG_OK) return rc;
+        if (h->p2p_on && (rc = vrg_enqueue_p2p_halo(h, 0)) != VRG_OK) return rc;
+        if ((rc = vrg_enqueue_absorb(h)) != VRG_OK) return rc;
+        if ((rc = vrg_enqueue_flip(h)) != VRG_OK) return rc;
+        if (h->p2p_on && (rc = vrg_enqueue_p2p_halo(h, 1)) != VRG_OK) return rc;
+        if (h->p2p_on && (rc = vrg_enqueue_p2p_stats(h)) != VRG_OK) return rc;
+        if ((rc = vrg_enqueue_advance(h)) != VRG_OK) return rc;
+    }
+    return VRG_OK;
+}
+
+static uint64_t run_signature(const vrg_handle *h) {
+    uint64_t x = 1469598103934665603ull;
+    auto mix = [&](const void *ptr, size_t n) {
+        const unsigned char *b = (const unsigned char *)ptr;
+        for (size_t i = 0; i < n; ++i) { x ^= b[i]; x *= 1099511628211ull; }
+    };
+    mix(&h->p, sizeof(Params));
+    if (h->p2p_on) mix(&h->q, sizeof(P2P));
+    const int64_t extra[3] = {h->cfg.intensity_mode, h->p2p_on, h->force_ldg};
+    mix(extra, sizeof extra);
+    return x;
+}
+
+// The loop of VRG:58-117.  The host enqueues batches of 8 iterations and reads the device-side status word after each;
+// kernels launched after the exit see the status and return at once.  From the second batch on the batch is a CUDA
+// graph (captured once per parameter set, replayed), which removes the launch gaps between the short kernels.
 int vrg_run(vrg_handle *h, vrg_result *res) {
     NEED_INIT();
     vrg_result r;
     const int check_every = 8;
     const auto t0 = std::chrono::steady_clock::now();
+    bool use_graph = !h->prof && h->graph_ok;
+    bool first = true;
     while (true) {
-        for (int k = 0; k < check_every; ++k) {
-            int rc;
-            if ((rc = vrg_enqueue_decide(h)) != VRG_OK) return rc;
-            if ((rc = vrg_enqueue_cancel(h)) != VRG_OK) return rc;
-            if (h->p2p_on && (rc = vrg_enqueue_p2p_halo(h, 0)) != VRG_OK) return rc;
-            if ((rc = vrg_enqueue_absorb(h)) != VRG_OK) return rc;
-            if ((rc = vrg_enqueue_flip(h)) != VRG_OK) return rc;
-            if (h->p2p_on && (rc = vrg_enqueue_p2p_halo(h, 1)) != VRG_OK) return rc;
-            if (h->p2p_on && (rc = vrg_enqueue_p2p_stats(h)) != VRG_OK) return rc;
-            if ((rc = vrg_enqueue_advance(h)) != VRG_OK) return rc;
+        bool launched = false;
+        if (use_graph && !first) {
+            const uint64_t sig = run_signature(h);
+            if (!h->gexec || h->gsig != sig) {
+                if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+                if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const int64_t l0 = h->launches;
+                    const int rc = enqueue_batch(h, check_every);
+                    cudaGraph_t g = nullptr;
+                    const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+                    h->glaunches = h->launches - l0;
+                    h->launches = l0;
+                    if (rc == VRG_OK && e == cudaSuccess && cudaGraphInstantiate(&h->gexec, g, 0) == cudaSuccess) h->gsig = sig;
+                    else { h->gexec = nullptr; h->graph_ok = false; }
+                    if (g) cudaGraphDestroy(g);
+                } else h->graph_ok = false;  // e.g. the legacy default stream cannot be captured: stay eager
+                cudaGetLastError();
+                use_graph = h->graph_ok;
+            }
+            if (use_graph && h->gexec) {
+                CK(cudaGraphLaunch(h->gexec, h->stream));
+                h->launches += h->glaunches;
+                launched = true;
+            }
         }
+        if (!launched) {
+            const int rc = enqueue_batch(h, check_every);
+            if (rc != VRG_OK) return rc;
+        }
+        first = false;
         int rc = vrg_poll(h, &r);
         if (rc != VRG_OK) return rc;
         if (r.exit_reason == EXIT_PEER_TIMEOUT) return fail(VRG_ERR_CUDA, "peer GPU did not answer (p2p timeout)");

@@ -10,9 +10,9 @@
 // Per iteration (reference: Code/variationalRegionGrowing.py, VRG:line):
 //   k_table   region histograms -> normalised Parzen sums per level -> decision bit      VRG:79-87,151-155
 //   k_sweep*  the stencil sweep: bands from S (26-neighbourhood), decision per voxel, F   VRG:87-88,139-145
-//   k_cancel  cancel rule on flagged rows, executed flips, integer histogram deltas       VRG:183-190,198,232-247
+//   k_cancel  front rows: cancel rule, executed flips applied to S in place, histogram deltas   VRG:173,183-190,198,201,232-247
 //   k_absorb  label 4 -> 3 around flips (only when the input holds label 4)               VRG:167-168,177-179
-//   k_flip    S ^= F on flagged rows                                                      VRG:173,201
+//   k_flip_halo  (slab runs) S ^= F on the halo planes after the flip exchange
 //   k_advance exit tests and trace row                                                    VRG:91-117
 #pragma once
 #include <cuda_runtime.h>
@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(BLOCK) k_kmat(Params p, double *kmat) {
 // ---------------------------------------------------------------------------------------------
 // k_table: one block per 32 levels; a warp sums one level's two Parzen sums over all levels.
 // Fixed order: lane-strided partial sums, then an xor-shuffle tree -> deterministic.
-__global__ void __launch_bounds__(BLOCK) k_table(Params p) {
+constexpr int TABLE_BLOCK = 1024;  // 32 warps: one level per warp, one decision word per block
+__global__ void __launch_bounds__(TABLE_BLOCK) k_table(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
     const long long *g = p.gstats;
     const long long n_in = g[2 * p.L + ST_N_IN], n_out = g[2 * p.L + ST_N_OUT];
@@ -165,15 +166,13 @@ __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
         p.ctrl[C_APPLY] = n_in < p.ctrl[C_MAX_SEG];  // cap is tested before the flips are applied, VRG:101
         p.lstats[2 * p.L + ST_N_FLIPS] = 0;
         front_list(p, (int)(p.ctrl[C_SWEEPS] & 1))[0] = 0;
-        dirty_list(p, (int)((p.ctrl[C_SWEEPS] + 1) & 1))[0] = 0;  // k_flip of this iteration fills it for the next sweep
+        dirty_list(p, (int)((p.ctrl[C_SWEEPS] + 1) & 1))[0] = 0;  // this iteration's flips fill it for the next sweep
     }
-    __shared__ uint32_t s_bits[WARPS];
+    __shared__ uint32_t s_bits[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t mybits = 0;
-    for (int k = 0; k < 32 / WARPS; ++k) {
-        const int b = blockIdx.x * 32 + warp * (32 / WARPS) + k;
-        if (b >= p.L) break;
-        if (g[b] + g[p.L + b] == 0) continue;  // level absent from both regions: never looked up
+    const int b = blockIdx.x * 32 + warp;
+    uint32_t mybit = 0;
+    if (b < p.L && g[b] + g[p.L + b] != 0) {  // a level absent from both regions is never looked up
         const double lb = p.levels[b];
         double si = 0.0, so = 0.0;
         for (int c = lane; c < p.L; c += 32) {
@@ -195,13 +194,13 @@ __global__ void __launch_bounds__(BLOCK) k_table(Params p) {
         }
         const double pi = si / (double)n_in, po = so / (double)n_out;  // VRG:81-82
         if (lane == 0) { p.pin[b] = pi; p.pout[b] = po; }
-        if (pi >= po) mybits |= 1u << (warp * (32 / WARPS) + k);  // ties go inside, VRG:87
+        if (pi >= po) mybit = 1u << warp;  // ties go inside, VRG:87
     }
-    if (lane == 0) s_bits[warp] = mybits;
+    if (lane == 0) s_bits[warp] = mybit;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t w = 0;
-        for (int i = 0; i < WARPS; ++i) w |= s_bits[i];
+        for (int i = 0; i < 32; ++i) w |= s_bits[i];
         if (p.dbits[blockIdx.x] != w) p.ctrl[C_TABLE_CHANGED] = 1;  // the next sweep must look at every band voxel
         p.dbits[blockIdx.x] = w;
     }
@@ -581,6 +580,29 @@ __device__ __forceinline__ void for_front_rows(const Params &p, Fn fn) {
     }
 }
 
+// A row that flips, and its (z, y, segment) neighbours, may change band status: each is claimed once (stamp) and
+// appended to the list the next incremental sweep walks.
+__device__ __forceinline__ void claim_dirty_rows(const Params &p, int zl, int y, int sg, int lane) {
+    const int next = (int)p.ctrl[C_SWEEPS] + 1;  // the sweep that will read the list
+    int *dl = dirty_list(p, next & 1);
+    const int nds = p.nseg > 1 ? 3 : 1;
+    int ridx = -1;
+    if (lane < 9 * nds) {
+        const int ss = sg + (nds == 3 ? lane % 3 - 1 : 0), yy = y + (lane / nds) % 3 - 1, zz = zl + lane / (3 * nds) - 1;
+        if (zz >= p.own_lo && zz < p.own_hi && yy >= 0 && yy < p.Y && ss >= 0 && ss < p.nseg) {
+            ridx = (zz * p.Y + yy) * p.nseg + ss;
+            if (atomicExch(&p.stamp[ridx], next) == next) ridx = -1;
+        }
+    }
+    const unsigned won = __ballot_sync(FULL, ridx >= 0);
+    if (won) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&dl[0], __popc(won));
+        base = __shfl_sync(FULL, base, 0);
+        if (ridx >= 0) dl[1 + base + __popc(won & ((1u << lane) - 1u))] = ridx;
+    }
+}
+
 // k_cancel: an outer-band voxel marked to enter is dropped when every segmented neighbour leaves in the same
 // iteration (VRG:183-190 then VRG:198).  Rewrites F to the executed flips (race-free: only non-segmented bits are
 // cleared, neighbours read F & S), keeps the cancelled ones in C for the absorb rule, and applies the integer
@@ -591,6 +613,7 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
     const int lane = threadIdx.x & 31;
     long long d_in = 0;
     unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
+    const bool single_slab = p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
     for_front_rows(p, [&](int zl, int y, int sg) {
         const int c = sg * WORDS_PER_WARP - 1 + lane;
         const bool inr = c >= 0 && c < p.XW;
@@ -619,6 +642,14 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
             if (active && a != a0) p.F[widx] = r | a;
         }
         if (p.C != nullptr && active) p.C[widx] = a0 & ~a;
+        // Flip in place right here.  Safe against the warps that are reading this row as a neighbour: they use
+        // S & ~F, and that value is the same before, between and after the two stores (executed flip: F = 1 both
+        // times -> 0; cancelled addition: S = 0 both times -> 0; everything else is untouched).
+        if (active && (r | a)) {
+            p.S[widx] = s ^ (r | a);
+            p.unitmap[unit_index(p, zl, y, c)] = 1;
+        }
+        if (single_slab) claim_dirty_rows(p, zl, y, sg, lane);
         if (active) {
             d_in += __popc(a) - __popc(r);
             const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
@@ -645,42 +676,10 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
     }
 }
 
-// k_flip: S ^= F.  Own planes: flagged rows only.  Halo planes (multi-GPU, after the F exchange): every row.
-__global__ void __launch_bounds__(BLOCK) k_flip(Params p) {
+// k_flip_halo (slab runs only, after the F exchange): S ^= F on the halo planes, so the halo copy of the segmented
+// plane follows the neighbour slab without ever being exchanged itself.  Own planes are flipped inside k_cancel.
+__global__ void __launch_bounds__(BLOCK) k_flip_halo(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
-    const int lane = threadIdx.x & 31;
-    const bool single_slab = p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
-    const int next = (int)p.ctrl[C_SWEEPS] + 1;  // the sweep that will read the dirty list
-    int *dl = dirty_list(p, next & 1);
-    const int nds = p.nseg > 1 ? 3 : 1;
-    for_front_rows(p, [&](int zl, int y, int sg) {
-        const int c = sg * WORDS_PER_WARP + lane;
-        if (lane < WORDS_PER_WARP && c < p.XW) {
-            const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
-            const uint32_t f = p.F[widx];
-            if (f) {
-                p.S[widx] ^= f;
-                p.unitmap[unit_index(p, zl, y, c)] = 1;
-            }
-        }
-        if (single_slab) {  // this row and its (z, y, segment) neighbours may change band status: claim each once
-            int ridx = -1;
-            if (lane < 9 * nds) {
-                const int ss = sg + (nds == 3 ? lane % 3 - 1 : 0), yy = y + (lane / nds) % 3 - 1, zz = zl + lane / (3 * nds) - 1;
-                if (zz >= p.own_lo && zz < p.own_hi && yy >= 0 && yy < p.Y && ss >= 0 && ss < p.nseg) {
-                    ridx = (zz * p.Y + yy) * p.nseg + ss;
-                    if (atomicExch(&p.stamp[ridx], next) == next) ridx = -1;
-                }
-            }
-            const unsigned won = __ballot_sync(FULL, ridx >= 0);
-            if (won) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&dl[0], __popc(won));
-                base = __shfl_sync(FULL, base, 0);
-                if (ridx >= 0) dl[1 + base + __popc(won & ((1u << lane) - 1u))] = ridx;
-            }
-        }
-    });
     const long long tid = (long long)blockIdx.x * BLOCK + threadIdx.x, nth = (long long)gridDim.x * BLOCK;
     for (int side = 0; side < 2; ++side) {
         const int zlo = side ? p.own_hi : max(p.valid_lo, p.own_lo - HALO);

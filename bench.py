@@ -209,6 +209,8 @@ def run_single(args):
     nvox = shape[0] * shape[1] * shape[2]
     peak, peak_kind = measured_peak()
     d_data, d_vm = device_phantom(shape, args.seed, 0, shape[0], dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.Stream())  # a capturable (non-default) stream: vrg_run replays CUDA graphs on it
     stream = torch.cuda.current_stream().cuda_stream
     modes = [args.intensity] + [m for m in ("f64_dense", "f64_band", "index") if m != args.intensity]
     results = {}

@@ -19,6 +19,8 @@ def main():
     from arterynetwork_b200.engine import VRGEngine
     shape = bench.WORKLOADS[a.workload]
     d, v = bench.device_phantom(shape, a.seed, 0, shape[0], 0)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.Stream())
     with VRGEngine(shape, max_segment_size=10 ** 15, intensity=a.intensity, iter_max=a.iters) as eng:
         eng.set_stream(torch.cuda.current_stream().cuda_stream)
         eng.attach_device(d.data_ptr(), v.data_ptr())
