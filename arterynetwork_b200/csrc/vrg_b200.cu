@@ -492,10 +492,9 @@ int vrg_init(vrg_handle *h) {
     CK(cudaGetLastError());
     if (h->p2p_on) {  // slabs: excluded halo planes and the global statistics, over peer memory
         k_p2p_push_halo<<<h->sms, BLOCK, 0, h->stream>>>(p, h->q, 1 << PK_E, 1);
-        k_p2p_wait_unpack_halo<<<h->sms, BLOCK, 0, h->stream>>>(p, h->q, 1 << PK_E, 1);
-        k_p2p_push_stats<<<8, BLOCK, 0, h->stream>>>(p, h->q, 1);
-        k_p2p_reduce_stats<<<8, BLOCK, 0, h->stream>>>(p, h->q, h->d_gstats, 1);
-        h->launches += 4;
+        k_p2p_wait_unpack_halo<<<h->sms, BLOCK, 0, h->stream>>>(p, h->q, 1 << PK_E, 1, 0);
+        k_p2p_stats<<<1, STATS_BLOCK, 0, h->stream>>>(p, h->q, h->d_gstats, 1);
+        h->launches += 3;
         CK(cudaGetLastError());
     }
     // the init row of the trace and the error checks need the counters on the host
@@ -593,7 +592,7 @@ int vrg_enqueue_p2p_halo(vrg_handle *h, int phase) {
     const int kinds = phase == 0 ? ((1 << PK_F) | (h->p.E ? (1 << PK_C) : 0)) : (h->p.E ? (1 << PK_E) : 0);
     if (!kinds) return VRG_OK;
     k_p2p_push_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p, h->q, kinds, 0);
-    k_p2p_wait_unpack_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p, h->q, kinds, 0);
+    k_p2p_wait_unpack_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p, h->q, kinds, 0, phase == 0);
     h->launches += 2;
     CK(cudaGetLastError());
     return VRG_OK;
@@ -601,9 +600,8 @@ int vrg_enqueue_p2p_halo(vrg_handle *h, int phase) {
 int vrg_enqueue_p2p_stats(vrg_handle *h) {
     NEED_INIT();
     if (!h->p2p_on) return fail(VRG_ERR_ARG, "p2p transport not connected");
-    k_p2p_push_stats<<<8, BLOCK, 0, h->stream>>>(h->p, h->q, 0);
-    k_p2p_reduce_stats<<<8, BLOCK, 0, h->stream>>>(h->p, h->q, h->d_gstats, 0);
-    h->launches += 2;
+    k_p2p_stats<<<1, STATS_BLOCK, 0, h->stream>>>(h->p, h->q, h->d_gstats, 0);  // includes the advance step
+    h->launches += 1;
     CK(cudaGetLastError());
     return VRG_OK;
 }
@@ -687,10 +685,13 @@ static int enqueue_batch(vrg_handle *h, int n) {
         if ((rc = vrg_enqueue_cancel(h)) != VRG_OK) return rc;
         if (h->p2p_on && (rc = vrg_enqueue_p2p_halo(h, 0)) != VRG_OK) return rc;
         if ((rc = vrg_enqueue_absorb(h)) != VRG_OK) return rc;
-        if ((rc = vrg_enqueue_flip(h)) != VRG_OK) return rc;
-        if (h->p2p_on && (rc = vrg_enqueue_p2p_halo(h, 1)) != VRG_OK) return rc;
-        if (h->p2p_on && (rc = vrg_enqueue_p2p_stats(h)) != VRG_OK) return rc;
-        if ((rc = vrg_enqueue_advance(h)) != VRG_OK) return rc;
+        if (h->p2p_on) {  // halo flips were applied while unpacking; the statistics kernel also advances the loop
+            if ((rc = vrg_enqueue_p2p_halo(h, 1)) != VRG_OK) return rc;
+            if ((rc = vrg_enqueue_p2p_stats(h)) != VRG_OK) return rc;
+        } else {
+            if ((rc = vrg_enqueue_flip(h)) != VRG_OK) return rc;
+            if ((rc = vrg_enqueue_advance(h)) != VRG_OK) return rc;
+        }
     }
     return VRG_OK;
 }

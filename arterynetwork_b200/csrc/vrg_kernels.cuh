@@ -764,8 +764,7 @@ __global__ void __launch_bounds__(BLOCK) k_absorb(Params p) {
 
 // ---------------------------------------------------------------------------------------------
 // k_advance: the exit tests of VRG:91-104 and the loop bookkeeping of VRG:113-117.
-__global__ void k_advance(Params p) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void advance_state(const Params &p) {
     long long *c = p.ctrl;
     if (c[C_STATUS] != RUNNING) return;
     const long long *g = p.gstats + 2 * p.L;
@@ -781,6 +780,9 @@ __global__ void k_advance(Params p) {
     c[C_ITER] += 1;
     c[C_TABLE_CHANGED] = 0;  // k_table of the next iteration raises it again if a decision bit moves
     if (c[C_ITER] > c[C_ITER_MAX]) c[C_STATUS] = 3;        // VRG:58,118
+}
+__global__ void k_advance(Params p) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) advance_state(p);
 }
 
 // ---------------------------------------------------------------------------------------------

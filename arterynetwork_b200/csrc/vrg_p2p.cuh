@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_push_halo(Params p, P2P q, int ki
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_p2p_wait_unpack_halo(Params p, P2P q, int kinds, int seq_zero) {
+// `flip`: the unpacked executed-flip words are applied to the halo copy of the segmented plane in the same pass
+// (what k_flip_halo does on the collective path).
+__global__ void __launch_bounds__(BLOCK) k_p2p_wait_unpack_halo(Params p, P2P q, int kinds, int seq_zero, int flip) {
     if (!seq_zero && (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY])) return;
     const unsigned long long seq = seq_zero ? ((unsigned long long)p.ctrl[C_EPOCH] << 32) : p2p_seq(p);
     __shared__ int ok;
@@ -134,32 +136,45 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_wait_unpack_halo(Params p, P2P q,
             if (q.peer_recv[side] == nullptr) continue;
             const uint32_t *src = q.recv + ((long long)kind * 2 + side) * n;
             uint32_t *dst = plane + (long long)(side == 0 ? p.own_lo - HALO : p.own_hi) * p.plane_words;
-            for (long long i = tid; i < n; i += nth) dst[i] = __ldcg(src + i);
+            if (kind == PK_F && flip) {
+                uint32_t *sdst = p.S + (long long)(side == 0 ? p.own_lo - HALO : p.own_hi) * p.plane_words;
+                const int z0 = side == 0 ? p.own_lo - HALO : p.own_hi;
+                for (long long i = tid; i < n; i += nth) {
+                    const uint32_t f = __ldcg(src + i);
+                    dst[i] = f;
+                    if (f) {
+                        sdst[i] ^= f;
+                        const int zl = z0 + (int)(i / p.plane_words), y = (int)((i % p.plane_words) / p.WP), c = (int)(i % p.WP);
+                        p.unitmap[unit_index(p, zl, y, c)] = 1;
+                    }
+                }
+            } else {
+                for (long long i = tid; i < n; i += nth) dst[i] = __ldcg(src + i);
+            }
         }
     }
 }
 
-// ---- statistics all-reduce -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK) k_p2p_push_stats(Params p, P2P q, int seq_zero) {
+// ---- statistics all-reduce (+ the loop bookkeeping) -----------------------------------------------------------------
+// One block: store my vector into every rank's mailbox, fence, raise the flags, wait for everybody's, sum the slots in
+// rank order (integers: any order gives the same bits) into the global statistics and, in the loop, run the exit
+// tests of k_advance right away -- the whole tail of an iteration is a single launch.
+constexpr int STATS_BLOCK = 1024;
+__device__ __forceinline__ void advance_state(const Params &p);  // defined with k_advance in vrg_kernels.cuh
+
+__global__ void __launch_bounds__(STATS_BLOCK) k_p2p_stats(Params p, P2P q, long long *gstats, int seq_zero) {
     if (!seq_zero && p.ctrl[C_STATUS] != RUNNING) return;
     const unsigned long long seq = seq_zero ? ((unsigned long long)p.ctrl[C_EPOCH] << 32) : p2p_seq(p);
     const int par = (int)(seq & 1ull), n = 2 * p.L + ST_EXTRA;
-    const int tid = blockIdx.x * BLOCK + threadIdx.x, nth = gridDim.x * BLOCK;
     for (int r = 0; r < q.world; ++r) {
         long long *dst = q.peer_slots[r] + ((long long)par * q.world + q.rank) * q.slot_words;
-        for (int i = tid; i < n; i += nth) dst[i] = p.lstats[i];
+        for (int i = threadIdx.x; i < n; i += STATS_BLOCK) dst[i] = p.lstats[i];
     }
-    if (p2p_last_block(q.flags + DONE_BASE + 1) && threadIdx.x == 0)
-        for (int r = 0; r < q.world; ++r) st_release_sys(q.peer_flags[r] + STATS_FLAGS + par * P2P_MAX_WORLD + q.rank, seq);
-}
-
-// every rank sums the slots in rank order (integers: any order gives the same bits) into its global statistics
-__global__ void __launch_bounds__(BLOCK) k_p2p_reduce_stats(Params p, P2P q, long long *gstats, int seq_zero) {
-    if (!seq_zero && p.ctrl[C_STATUS] != RUNNING) return;
-    const unsigned long long seq = seq_zero ? ((unsigned long long)p.ctrl[C_EPOCH] << 32) : p2p_seq(p);
-    const int par = (int)(seq & 1ull), n = 2 * p.L + ST_EXTRA;
+    __threadfence_system();
+    __syncthreads();
     __shared__ int ok;
     if (threadIdx.x == 0) ok = 1;
+    if (threadIdx.x < q.world) st_release_sys(q.peer_flags[threadIdx.x] + STATS_FLAGS + par * P2P_MAX_WORLD + q.rank, seq);
     __syncthreads();
     if (threadIdx.x < q.world && !p2p_wait(q.flags + STATS_FLAGS + par * P2P_MAX_WORLD + threadIdx.x, seq)) ok = 0;
     __threadfence_system();
@@ -169,11 +184,15 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_reduce_stats(Params p, P2P q, lon
         return;
     }
     const long long *base = q.slots + (long long)par * q.world * q.slot_words;
-    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
-        long long s = 0;
-        for (int r = 0; r < q.world; ++r) s += __ldcg(base + (long long)r * q.slot_words + i);
-        gstats[i] = s;
+    for (int i = threadIdx.x; i < n; i += STATS_BLOCK) {
+        long long sum = 0;
+        for (int r = 0; r < q.world; ++r) sum += __ldcg(base + (long long)r * q.slot_words + i);
+        gstats[i] = sum;
     }
+    if (seq_zero) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) advance_state(p);
 }
 
 }  // namespace vrg

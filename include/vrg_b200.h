@@ -147,8 +147,8 @@ int vrg_params_signature(vrg_handle *h, uint64_t *signature);
 #define VRG_P2P_HANDLE_BYTES 192
 int vrg_p2p_export(vrg_handle *h, int world, void *handles_out /* VRG_P2P_HANDLE_BYTES */);
 int vrg_p2p_connect(vrg_handle *h, int rank, int world, const void *all_handles /* world * VRG_P2P_HANDLE_BYTES */);
-int vrg_enqueue_p2p_halo(vrg_handle *h, int phase); /* 0: flips (+cancelled) after cancel; 1: excluded plane after flip */
-int vrg_enqueue_p2p_stats(vrg_handle *h);           /* statistics all-reduce, before advance */
+int vrg_enqueue_p2p_halo(vrg_handle *h, int phase); /* 0: flips (+cancelled) after cancel, applied to the halo planes (replaces vrg_enqueue_flip); 1: excluded plane after absorb */
+int vrg_enqueue_p2p_stats(vrg_handle *h);           /* statistics all-reduce + the advance step (replaces vrg_enqueue_advance) */
 
 /* outputs: the return values of VRG:96 -------------------------------------- */
 int vrg_download_labels(vrg_handle *h, uint8_t *value_map_out);   /* own planes, canonical labels 0..4 */
