@@ -433,7 +433,7 @@ int vrg_use_separate_global_stats(vrg_handle *h) {
 static int launch_init_hist(vrg_handle *h) {
     const Params &p = h->p;
     // lane-private shared histograms when at least 4 warps' worth fit (64 B per level per warp)
-    const size_t per_warp = (size_t)p.L * 32 * sizeof(uint16_t);
+    const size_t per_warp = (size_t)((p.L + 1) & ~1) * 32 * sizeof(uint16_t);
     const int hw = (int)std::min<size_t>(16, (220 * 1024) / per_warp);
     if (hw >= 4) {
         if (!h->hist_attr_set) {

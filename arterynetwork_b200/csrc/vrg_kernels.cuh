@@ -908,15 +908,17 @@ __global__ void __launch_bounds__(BLOCK) k_init_hist(Params p, int copies) {
 
 // k_init_hist_private: same result as k_init_hist, without shared-memory atomics (2 cycles per lane on this part).
 // Every lane of a warp owns a private uint16 histogram of the outside region in shared memory, laid out
-// [level][lane] so that a warp's 32 increments hit 32 different banks: a plain load / add / store per voxel.
+// [level / 2][lane][level & 1]: a lane's counters all live in "its" bank, so a warp's 32 increments never conflict
+// and each is a plain load / add / store.
 // The (tiny) inside region and the excluded count go through global atomics.  hw = warps per block that fit.
 template <int MODE, bool LATTICE>
 __global__ void k_init_hist_private(Params p, int hw) {
     extern __shared__ uint16_t s_hp[];  // [hw][L][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < hw * p.L * 32; i += blockDim.x) s_hp[i] = 0;
+    for (int i = threadIdx.x; i < hw * ((p.L + 1) & ~1) * 32; i += blockDim.x) s_hp[i] = 0;
     __syncthreads();
-    uint16_t *mine = s_hp + (size_t)warp * p.L * 32 + lane;
+    const int LP = (p.L + 1) & ~1;  // levels padded to an even count
+    uint16_t *mine = s_hp + (size_t)warp * LP * 32 + lane * 2;
     const int nrows = (p.own_hi - p.own_lo) * p.Y;
     const int nwarps = gridDim.x * hw;
     unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
@@ -925,8 +927,8 @@ __global__ void k_init_hist_private(Params p, int hw) {
     auto flush = [&]() {
         __syncwarp();
         for (int l = 0; l < p.L; ++l) {
-            unsigned int v = mine[l * 32];
-            mine[l * 32] = 0;
+            unsigned int v = mine[(l >> 1) * 64 + (l & 1)];
+            mine[(l >> 1) * 64 + (l & 1)] = 0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
             if (lane == 0 && v) atomicAdd(&hout[l], (unsigned long long)v);
@@ -957,7 +959,7 @@ __global__ void k_init_hist_private(Params p, int hw) {
                 const uint32_t bit = 1u << lane;
                 if (sw[k] & bit) { n_in++; atomicAdd(&hin[l], 1ull); }
                 else if (ew[k] & bit) n_ex++;
-                else { n_out++; mine[l * 32] += 1; }
+                else { n_out++; mine[(l >> 1) * 64 + (l & 1)] += 1; }
             }
         }
         pending += p.XW;
