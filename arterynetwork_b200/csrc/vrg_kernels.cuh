@@ -403,20 +403,29 @@ __device__ __forceinline__ void tma_bulk_load(void *smem_dst, const void *gmem_s
                  : "memory");
 }
 
-// the (unit, row) sequence of one warp, walked twice: once by the TMA prefetcher, once by the consumer
+// The rows of one warp of the dense sweep, walked twice (TMA prefetcher, consumer).  The flattened row space
+// (plane, segment, y) is cut into one contiguous range per warp, all of the same length +-1: perfectly balanced
+// however few planes a slab has, and the sliding window restarts only at the range start and at plane boundaries.
 struct RowCursor {
-    long long u, nunits, stride;
-    int zlo, nyb, y;
-    Unit un;
-    __device__ __forceinline__ void start(const Params &p, long long u0, long long n, long long s, int zlo_, int nyb_) {
-        u = u0; nunits = n; stride = s; zlo = zlo_; nyb = nyb_;
-        if (u < nunits) { un = decode_unit(p, u, zlo, nyb); y = un.y0; }
+    long long r, r_end;  // flattened row index: ((zl - zlo) * nseg + sg) * Y + y
+    int zlo, zl, sg, y;
+    bool fresh;          // first row of a (plane, segment) column or of the range: the window must be (re)started
+    __device__ __forceinline__ void start(const Params &p, long long r0, long long r1, int zlo_) {
+        r = r0; r_end = r1; zlo = zlo_; fresh = true;
+        if (r < r_end) {
+            y = (int)(r % p.Y);
+            const long long t = r / p.Y;
+            sg = (int)(t % p.nseg);
+            zl = zlo + (int)(t / p.nseg);
+        }
     }
-    __device__ __forceinline__ bool valid() const { return u < nunits; }
+    __device__ __forceinline__ bool valid() const { return r < r_end; }
     __device__ __forceinline__ void next(const Params &p) {
-        if (++y >= un.y1) {
-            u += stride;
-            if (u < nunits) { un = decode_unit(p, u, zlo, nyb); y = un.y0; }
+        ++r;
+        fresh = false;
+        if (++y >= p.Y) {
+            y = 0; fresh = true;
+            if (++sg >= p.nseg) { sg = 0; ++zl; }
         }
     }
 };
@@ -447,17 +456,17 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy fill before the async-proxy copies
     __syncthreads();
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
-    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
-    const long long nunits = (long long)(zhi - zlo) * nyb * p.nseg;
+    const long long nrows = (long long)(zhi - zlo) * p.nseg * p.Y;
     const long long nwarps = (long long)gridDim.x * DENSE_WARPS;
-    const long long u0 = (long long)blockIdx.x * DENSE_WARPS + warp;
+    const long long w = (long long)blockIdx.x * DENSE_WARPS + warp;
+    const long long r0 = nrows * w / nwarps, r1 = nrows * (w + 1) / nwarps;
     RowCursor pre, cur;
-    pre.start(p, u0, nunits, nwarps, zlo, nyb);
-    cur.start(p, u0, nunits, nwarps, zlo, nyb);
+    pre.start(p, r0, r1, zlo);
+    cur.start(p, r0, r1, zlo);
     auto issue = [&](const RowCursor &rc, int s) {  // lane 0 only
-        const int x0 = rc.un.sg * WORDS_PER_WARP * 32;
+        const int x0 = rc.sg * WORDS_PER_WARP * 32;
         const uint32_t bytes = (uint32_t)min(WORDS_PER_WARP * 32, p.X - x0) * 8u;
-        const double *src = p.data + (long long)rc.un.zl * p.plane_vox + (long long)rc.y * p.X + x0;
+        const double *src = p.data + (long long)rc.zl * p.plane_vox + (long long)rc.y * p.X + x0;
         mbar_expect_tx(mybar + s, bytes);
         tma_bulk_load(mystage + (size_t)s * (STAGE_BYTES / 8), src, bytes, mybar + s);
     };
@@ -476,14 +485,14 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     bool own = false;
     while (cur.valid()) {
         const int y = cur.y;
-        if (y == cur.un.y0) {  // new unit: (re)start the window
-            c0 = cur.un.sg * WORDS_PER_WARP - 1;
-            own = cur.un.zl >= p.own_lo && cur.un.zl < p.own_hi;
-            st.begin(p, cur.un.zl, cur.un.y0, c0 + lane, lane);
+        if (cur.fresh) {  // range start or new (plane, segment) column: (re)start the window
+            c0 = cur.sg * WORDS_PER_WARP - 1;
+            own = cur.zl >= p.own_lo && cur.zl < p.own_hi;
+            st.begin(p, cur.zl, y, c0 + lane, lane);
         }
         uint32_t s, inner, outer;
         st.step(y, s, inner, outer);
-        const long long widx = (long long)cur.un.zl * p.plane_words + (long long)y * p.WP + c0 + lane;
+        const long long widx = (long long)cur.zl * p.plane_words + (long long)y * p.WP + c0 + lane;
         if (p.E != nullptr && outer) outer &= ~p.E[widx];
         const uint32_t band = inner | outer;
         // decision bit of every voxel of the row segment: word j of the segment ends up in lane j + 1.
@@ -507,7 +516,7 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         }
         if (++stage == DENSE_STAGES) { stage = 0; parity ^= 1u; }
         const uint32_t f = band & (D ^ s);
-        store_flips(p, widx, ((long long)cur.un.zl * p.Y + y) * p.nseg + cur.un.sg, f, st.active, own, lane);
+        store_flips(p, widx, ((long long)cur.zl * p.Y + y) * p.nseg + cur.sg, f, st.active, own, lane);
         if (own) flips += __popc(f);
         cur.next(p);
     }
