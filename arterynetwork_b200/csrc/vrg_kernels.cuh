@@ -403,29 +403,48 @@ __device__ __forceinline__ void tma_bulk_load(void *smem_dst, const void *gmem_s
                  : "memory");
 }
 
-// The rows of one warp of the dense sweep, walked twice (TMA prefetcher, consumer).  The flattened row space
-// (plane, segment, y) is cut into one contiguous range per warp, all of the same length +-1: perfectly balanced
-// however few planes a slab has, and the sliding window restarts only at the range start and at plane boundaries.
+// The rows of one warp of the dense sweep, walked twice (TMA prefetcher, consumer).  Two partitions of the row space:
+//  * round-robin units of ROWS_PER_UNIT rows (large volumes: at any moment the whole machine streams one compact
+//    window of memory, which is kind to the TLB and the DRAM pages);
+//  * one contiguous range of rows per warp, all of the same length +-1 (slabs with few planes, where whole units
+//    would leave the warps with 2 or 3 units each and a 20-30 % tail).
+// `fresh` marks the rows at which the sliding window must be (re)started.
 struct RowCursor {
-    long long r, r_end;  // flattened row index: ((zl - zlo) * nseg + sg) * Y + y
-    int zlo, zl, sg, y;
-    bool fresh;          // first row of a (plane, segment) column or of the range: the window must be (re)started
-    __device__ __forceinline__ void start(const Params &p, long long r0, long long r1, int zlo_) {
-        r = r0; r_end = r1; zlo = zlo_; fresh = true;
-        if (r < r_end) {
-            y = (int)(r % p.Y);
-            const long long t = r / p.Y;
-            sg = (int)(t % p.nseg);
-            zl = zlo + (int)(t / p.nseg);
+    bool rr, fresh;
+    int zlo, nyb, zl, sg, y, y1;
+    long long u, nunits, stride;  // round-robin
+    long long r, r_end;           // contiguous: flattened row index ((zl - zlo) * nseg + sg) * Y + y
+    __device__ __forceinline__ void load_unit(const Params &p) {
+        if (u < nunits) { const Unit un = decode_unit(p, u, zlo, nyb); zl = un.zl; sg = un.sg; y = un.y0; y1 = un.y1; }
+    }
+    __device__ __forceinline__ void start(const Params &p, long long w, long long nwarps, int zlo_, int zhi_) {
+        zlo = zlo_; fresh = true;
+        nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+        nunits = (long long)(zhi_ - zlo_) * nyb * p.nseg;
+        rr = nunits >= 8 * nwarps;
+        if (rr) { u = w; stride = nwarps; load_unit(p); }
+        else {
+            const long long nrows = (long long)(zhi_ - zlo_) * p.nseg * p.Y;
+            r = nrows * w / nwarps; r_end = nrows * (w + 1) / nwarps;
+            if (r < r_end) {
+                y = (int)(r % p.Y);
+                const long long t = r / p.Y;
+                sg = (int)(t % p.nseg);
+                zl = zlo + (int)(t / p.nseg);
+            }
         }
     }
-    __device__ __forceinline__ bool valid() const { return r < r_end; }
+    __device__ __forceinline__ bool valid() const { return rr ? u < nunits : r < r_end; }
     __device__ __forceinline__ void next(const Params &p) {
-        ++r;
         fresh = false;
-        if (++y >= p.Y) {
-            y = 0; fresh = true;
-            if (++sg >= p.nseg) { sg = 0; ++zl; }
+        if (rr) {
+            if (++y >= y1) { u += stride; fresh = true; load_unit(p); }
+        } else {
+            ++r;
+            if (++y >= p.Y) {
+                y = 0; fresh = true;
+                if (++sg >= p.nseg) { sg = 0; ++zl; }
+            }
         }
     }
 };
@@ -456,13 +475,11 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy fill before the async-proxy copies
     __syncthreads();
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
-    const long long nrows = (long long)(zhi - zlo) * p.nseg * p.Y;
     const long long nwarps = (long long)gridDim.x * DENSE_WARPS;
     const long long w = (long long)blockIdx.x * DENSE_WARPS + warp;
-    const long long r0 = nrows * w / nwarps, r1 = nrows * (w + 1) / nwarps;
     RowCursor pre, cur;
-    pre.start(p, r0, r1, zlo);
-    cur.start(p, r0, r1, zlo);
+    pre.start(p, w, nwarps, zlo, zhi);
+    cur.start(p, w, nwarps, zlo, zhi);
     auto issue = [&](const RowCursor &rc, int s) {  // lane 0 only
         const int x0 = rc.sg * WORDS_PER_WARP * 32;
         const uint32_t bytes = (uint32_t)min(WORDS_PER_WARP * 32, p.X - x0) * 8u;
