@@ -163,6 +163,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     p.XW = (int)((X + 31) / 32);
     p.WP = (p.XW + 3) & ~3;
     p.nseg = (p.XW + WORDS_PER_WARP - 1) / WORDS_PER_WARP;
+    p.segw = (p.XW + p.nseg - 1) / p.nseg;  // equal-width segments
     p.nzl = (int)h->nz_own + 2 * HALO;
     p.own_lo = HALO; p.own_hi = HALO + (int)h->nz_own;
     h->ext_lo = std::max<int64_t>(0, cfg->z_begin - HALO);

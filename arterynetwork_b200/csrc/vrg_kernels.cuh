@@ -21,7 +21,8 @@
 namespace vrg {
 
 constexpr int HALO = 2;
-constexpr int WORDS_PER_WARP = 30;  // a warp covers 30 output words + 1 halo word on each side
+constexpr int WORDS_PER_WARP = 30;  // a warp covers up to 30 output words + 1 halo word on each side (rows are cut into
+                                    // nseg segments of equal width segw <= 30: 64 words are 22+22+20, not 30+30+4)
 constexpr int ROWS_PER_UNIT = 16;   // rows a warp slides over per work unit of the sweep
 constexpr int BLOCK = 256;
 constexpr int WARPS = BLOCK / 32;
@@ -39,7 +40,7 @@ enum { MODE_F64_DENSE = 0, MODE_F64_BAND = 1, MODE_INDEX = 2 };
 
 struct Params {
     // geometry
-    int Y, X, XW, WP, nseg;          // rows, voxels per row, words per row, word pitch, warp segments per row
+    int Y, X, XW, WP, nseg, segw;    // rows, voxels/row, words/row, word pitch, warp segments per row, words per segment (<= 30)
     int nzl;                          // local planes incl. halos
     int own_lo, own_hi;               // local plane range owned
     int valid_lo, valid_hi;           // local planes that lie inside the global volume
@@ -129,7 +130,7 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 
 __device__ __forceinline__ long long unit_index(const Params &p, int zl, int y, int c) {
     const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
-    return ((long long)zl * nyb + y / ROWS_PER_UNIT) * p.nseg + c / WORDS_PER_WARP;
+    return ((long long)zl * nyb + y / ROWS_PER_UNIT) * p.nseg + c / p.segw;
 }
 // A sweep unit (one plane, ROWS_PER_UNIT rows, 30 words) can hold a band voxel only if it or one of its 26 neighbour
 // units (z, y-block, x-segment) holds a segmented voxel: far from every vessel the full band sweep skips the unit
@@ -231,7 +232,7 @@ struct Strip {
     }
     __device__ __forceinline__ void begin(const Params &p, int zl, int y0, int c, int lane) {
         const bool inr = c >= 0 && c < p.XW;
-        active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
+        active = inr && lane >= 1 && lane <= p.segw;
         vm = inr ? valid_mask(p, c) : 0u;
         Y = p.Y; WP = p.WP;
         const uint32_t *col = p.S + (long long)zl * p.plane_words + c;
@@ -271,9 +272,10 @@ __device__ __forceinline__ Unit decode_unit(const Params &p, long long u, int zl
 // writes the flip word of a row segment; rows away from the front cost no store (warp-uniform branch)
 // and appends own-plane rows that flip to the front list, which k_cancel / k_flip consume one row per warp
 // (rows at the front are spatially clustered; a list spreads them evenly over the machine).
-__device__ __forceinline__ void store_flips(const Params &p, long long widx, long long ridx, uint32_t f, bool active, bool own, int lane) {
+// `was` = the row's flag, loaded by the caller early in the row so that its L2 latency hides behind the row's work.
+__device__ __forceinline__ void store_flips(const Params &p, long long widx, long long ridx, uint8_t was, uint32_t f, bool active,
+                                            bool own, int lane) {
     const bool any = __ballot_sync(FULL, f != 0u) != 0u;
-    const uint8_t was = p.rowflag[ridx];
     if (any || was) {
         if (active) {
             p.F[widx] = f;
@@ -294,8 +296,10 @@ __device__ __forceinline__ void store_flips(const Params &p, long long widx, lon
 template <int MODE, bool LATTICE>
 __device__ __forceinline__ int band_row(const Params &p, const uint32_t *s_dbits, int zl, int y, int sg, uint32_t s,
                                         uint32_t inner, uint32_t outer, bool active, bool own, int lane) {
-    const int c0 = sg * WORDS_PER_WARP - 1;
+    const int c0 = sg * p.segw - 1;
     const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c0 + lane;
+    const long long ridx = ((long long)zl * p.Y + y) * p.nseg + sg;
+    const uint8_t was = p.rowflag[ridx];
     if (p.E != nullptr && outer) outer &= ~p.E[widx];
     const uint32_t band = inner | outer;
     unsigned m = __ballot_sync(FULL, band != 0u);
@@ -323,7 +327,7 @@ __device__ __forceinline__ int band_row(const Params &p, const uint32_t *s_dbits
         }
     }
     const uint32_t f = band & (D ^ s);  // inner band leaves iff in < out, outer band enters iff in >= out
-    store_flips(p, widx, ((long long)zl * p.Y + y) * p.nseg + sg, f, active, own, lane);
+    store_flips(p, widx, ridx, was, f, active, own, lane);
     return own ? __popc(f) : 0;
 }
 
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
         for (int i = (int)warp0; i < n; i += (int)nwarps) {
             const int r = dl[1 + i];
             const int sg = r % p.nseg, t = r / p.nseg, y = t % p.Y, zl = t / p.Y;
-            st.begin(p, zl, y, sg * WORDS_PER_WARP - 1 + lane, lane);
+            st.begin(p, zl, y, sg * p.segw - 1 + lane, lane);
             uint32_t s, inner, outer;
             st.step(y, s, inner, outer);
             flips += band_row<MODE, LATTICE>(p, s_dbits, zl, y, sg, s, inner, outer, st.active, true, lane);
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
             const Unit un = decode_unit(p, u, zlo, nyb);
             if (!unit_near_segmented(p, un.zl, un.y0, un.sg, lane)) continue;
             const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
-            st.begin(p, un.zl, un.y0, un.sg * WORDS_PER_WARP - 1 + lane, lane);
+            st.begin(p, un.zl, un.y0, un.sg * p.segw - 1 + lane, lane);
             for (int y = un.y0; y < un.y1; ++y) {
                 uint32_t s, inner, outer;
                 st.step(y, s, inner, outer);
@@ -481,8 +485,8 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     pre.start(p, w, nwarps, zlo, zhi);
     cur.start(p, w, nwarps, zlo, zhi);
     auto issue = [&](const RowCursor &rc, int s) {  // lane 0 only
-        const int x0 = rc.sg * WORDS_PER_WARP * 32;
-        const uint32_t bytes = (uint32_t)min(WORDS_PER_WARP * 32, p.X - x0) * 8u;
+        const int x0 = rc.sg * p.segw * 32;
+        const uint32_t bytes = (uint32_t)min(p.segw * 32, p.X - x0) * 8u;
         const double *src = p.data + (long long)rc.zl * p.plane_vox + (long long)rc.y * p.X + x0;
         mbar_expect_tx(mybar + s, bytes);
         tma_bulk_load(mystage + (size_t)s * (STAGE_BYTES / 8), src, bytes, mybar + s);
@@ -503,13 +507,15 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     while (cur.valid()) {
         const int y = cur.y;
         if (cur.fresh) {  // range start or new (plane, segment) column: (re)start the window
-            c0 = cur.sg * WORDS_PER_WARP - 1;
+            c0 = cur.sg * p.segw - 1;
             own = cur.zl >= p.own_lo && cur.zl < p.own_hi;
             st.begin(p, cur.zl, y, c0 + lane, lane);
         }
         uint32_t s, inner, outer;
         st.step(y, s, inner, outer);
         const long long widx = (long long)cur.zl * p.plane_words + (long long)y * p.WP + c0 + lane;
+        const long long ridx = ((long long)cur.zl * p.Y + y) * p.nseg + cur.sg;
+        const uint8_t was = p.rowflag[ridx];
         if (p.E != nullptr && outer) outer &= ~p.E[widx];
         const uint32_t band = inner | outer;
         // decision bit of every voxel of the row segment: word j of the segment ends up in lane j + 1.
@@ -521,9 +527,13 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         // lane's voxel in word j;  phase 2: 32x32 bit transpose across the warp, lane j+1 ends up with word j.
         uint32_t mine = 0;
 #pragma unroll
-        for (int j = 0; j < WORDS_PER_WARP; ++j) {
-            const int l = level_of<LATTICE>(p, sv[j * 32]);
-            mine |= ((s_dbits[l >> 5] >> (l & 31)) & 1u) << (j + 1);
+        for (int jg = 0; jg < WORDS_PER_WARP; jg += 6) {
+            if (jg >= p.segw) break;  // warp-uniform; inside a group of 6 the chains stay branch-free
+#pragma unroll
+            for (int j = jg; j < jg + 6; ++j) {
+                const int l = level_of<LATTICE>(p, sv[j * 32]);
+                mine |= ((s_dbits[l >> 5] >> (l & 31)) & 1u) << (j + 1);
+            }
         }
         const uint32_t D = transpose32(mine, lane);
         __syncwarp();
@@ -533,7 +543,7 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         }
         if (++stage == DENSE_STAGES) { stage = 0; parity ^= 1u; }
         const uint32_t f = band & (D ^ s);
-        store_flips(p, widx, ((long long)cur.zl * p.Y + y) * p.nseg + cur.sg, f, st.active, own, lane);
+        store_flips(p, widx, ridx, was, f, st.active, own, lane);
         if (own) flips += __popc(f);
         cur.next(p);
     }
@@ -557,13 +567,15 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_dense_ldg(Params p) {
     Strip st;
     for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
         const Unit un = decode_unit(p, u, zlo, nyb);
-        const int c0 = un.sg * WORDS_PER_WARP - 1, c = c0 + lane;
+        const int c0 = un.sg * p.segw - 1, c = c0 + lane;
         const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
         st.begin(p, un.zl, un.y0, c, lane);
         for (int y = un.y0; y < un.y1; ++y) {
             uint32_t s, inner, outer;
             st.step(y, s, inner, outer);
             const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
+            const long long ridx = ((long long)un.zl * p.Y + y) * p.nseg + un.sg;
+            const uint8_t was = p.rowflag[ridx];
             if (p.E != nullptr && outer) outer &= ~p.E[widx];
             const uint32_t band = inner | outer;
             const int xlane = (c0 + 1) * 32 + lane;
@@ -572,7 +584,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_dense_ldg(Params p) {
             constexpr int U = 10;
 #pragma unroll
             for (int jb = 0; jb < WORDS_PER_WARP; jb += U) {
-                if (c0 + 1 + jb >= p.XW) break;  // warp-uniform
+                if (jb >= p.segw || c0 + 1 + jb >= p.XW) break;  // warp-uniform
                 double v[U];
 #pragma unroll
                 for (int k = 0; k < U; ++k) v[k] = (xlane + (jb + k) * 32 < p.X) ? drow[(jb + k) * 32] : p.lev0;
@@ -584,7 +596,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_dense_ldg(Params p) {
                 }
             }
             const uint32_t f = band & (D ^ s);
-            store_flips(p, widx, ((long long)un.zl * p.Y + y) * p.nseg + un.sg, f, st.active, own, lane);
+            store_flips(p, widx, ridx, was, f, st.active, own, lane);
             if (own) flips += __popc(f);
         }
     }
@@ -641,9 +653,9 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
     unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
     const bool single_slab = p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
     for_front_rows(p, [&](int zl, int y, int sg) {
-        const int c = sg * WORDS_PER_WARP - 1 + lane;
+        const int c = sg * p.segw - 1 + lane;
         const bool inr = c >= 0 && c < p.XW;
-        const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
+        const bool active = inr && lane >= 1 && lane <= p.segw;
         const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
         const uint32_t s = inr ? p.S[widx] : 0u, f = inr ? p.F[widx] : 0u;
         const uint32_t a0 = active ? (f & ~s) : 0u, r = active ? (f & s) : 0u;
@@ -750,9 +762,9 @@ __global__ void __launch_bounds__(BLOCK) k_absorb(Params p) {
         // halo planes beyond +-1 carry no row flags of their own (their F comes from the neighbour slab)
         const bool halo_near = (zl - 2 < p.own_lo - 1 && zl - 2 >= p.valid_lo) || (zl + 2 > p.own_hi && zl + 2 < p.valid_hi);
         if (!__ballot_sync(FULL, near) && !halo_near) continue;
-        const int c = sg * WORDS_PER_WARP - 1 + lane;
+        const int c = sg * p.segw - 1 + lane;
         const bool inr = c >= 0 && c < p.XW;
-        const bool active = inr && lane >= 1 && lane <= WORDS_PER_WARP;
+        const bool active = inr && lane >= 1 && lane <= p.segw;
         const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
         const uint32_t e = active ? p.E[widx] : 0u;
         if (!__ballot_sync(FULL, e != 0u)) continue;
@@ -867,7 +879,7 @@ __global__ void __launch_bounds__(BLOCK) k_init_bands(Params p) {
     Strip st;
     for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
         const Unit un = decode_unit(p, u, zlo, nyb);
-        const int c = un.sg * WORDS_PER_WARP - 1 + lane;
+        const int c = un.sg * p.segw - 1 + lane;
         const bool own = un.zl >= p.own_lo && un.zl < p.own_hi;
         st.begin(p, un.zl, un.y0, c, lane);
         for (int y = un.y0; y < un.y1; ++y) {
@@ -1048,7 +1060,7 @@ __global__ void __launch_bounds__(BLOCK) k_labels(Params p, uint8_t *__restrict_
     Strip st;
     for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
         const Unit un = decode_unit(p, u, p.own_lo, nyb);
-        const int c0 = un.sg * WORDS_PER_WARP - 1, c = c0 + lane;
+        const int c0 = un.sg * p.segw - 1, c = c0 + lane;
         st.begin(p, un.zl, un.y0, c, lane);
         for (int y = un.y0; y < un.y1; ++y) {
             uint32_t s, inner, outer;
@@ -1058,12 +1070,12 @@ __global__ void __launch_bounds__(BLOCK) k_labels(Params p, uint8_t *__restrict_
             outer &= ~e;
             // 4 voxels (bytes) per lane and store: a warp writes 128 consecutive voxels = 4 words per step
             uint8_t *rowout = out + ((long long)(un.zl - p.own_lo) * p.Y + y) * p.X;
-            for (int j0 = 1; j0 <= WORDS_PER_WARP; j0 += 4) {
+            for (int j0 = 1; j0 <= p.segw; j0 += 4) {
                 if (c0 + j0 >= p.XW) break;
                 const int src = j0 + (lane >> 3);  // lane that holds this lane's word
                 const uint32_t sj = __shfl_sync(FULL, s, src), ij = __shfl_sync(FULL, inner, src);
                 const uint32_t oj = __shfl_sync(FULL, outer, src), ej = __shfl_sync(FULL, e, src);
-                if (src > WORDS_PER_WARP) continue;
+                if (src > p.segw) continue;
                 const int x = (c0 + src) * 32 + (lane & 7) * 4;
                 uint32_t pack = 0;
 #pragma unroll

@@ -219,3 +219,66 @@ def vrg_oracle(data, value_map, H=2.25, max_segment_size=5000, iter_max=ITER_MAX
         "quirk_potential": quirk,
         "min_margin": float(min_margin),
     }
+
+
+def vrg_oracle_exact(data, value_map, H=2.25, max_segment_size=5000, iter_max=ITER_MAX, record_band=False):
+    """Same order-free restatement for CONTINUOUS intensities (no level table): the two Parzen sums of every band
+    voxel are evaluated exactly against the whole volume (VRG:151-155, 249-255), O(n_band * N) per iteration --
+    small volumes only.  This is the oracle of the brute-force mode.
+
+    ``record_band``: per decision, (flat voxel index, pin/n_in, pout/n_out) of every band voxel.
+    """
+    data = np.asarray(data, dtype=np.float64)
+    seg, excl = init_state(value_map)
+    n_in = int(seg.sum())
+    if n_in == 0:
+        raise ValueError("oracle: empty seed set (reference raises IndexError at VRG:88)")
+    lab = canonical_labels(seg, excl)
+    if not ((lab == 1) | (lab == 2)).any():
+        raise ValueError("oracle: seed has no boundary (reference raises IndexError at VRG:88)")
+    n_out = int((~seg & ~excl).sum())
+    trace = [(-1, n_in, n_out)]
+    bands = []
+    quirk = {"add_to_inside": 0, "remove_to_outside": 0, "cancel_repromoted": 0, "cancelled": 0}
+    min_margin = np.inf
+    flat = data.ravel()
+    iter_num, exit_code = 1, EXIT_MAX_ITER
+    while iter_num <= iter_max:
+        band = ((lab == 1) | (lab == 2)).ravel()
+        bidx = np.flatnonzero(band)
+        vin, vout = flat[seg.ravel()], flat[(~seg & ~excl).ravel()]
+        pin = np.empty(len(bidx))
+        pout = np.empty(len(bidx))
+        for i0 in range(0, len(bidx), 256):  # blocked to bound memory
+            v = flat[bidx[i0:i0 + 256]][:, None]
+            pin[i0:i0 + 256] = np.sum(A * np.exp(-0.5 * H * (vin[None, :] - v) ** 2), axis=1)
+            pout[i0:i0 + 256] = np.sum(A * np.exp(-0.5 * H * (vout[None, :] - v) ** 2), axis=1)
+        pin_n, pout_n = pin / n_in, pout / n_out
+        if record_band:
+            bands.append((bidx.copy(), pin_n.copy(), pout_n.copy()))
+        if len(bidx):
+            min_margin = min(min_margin, float(np.min(np.abs(pin_n - pout_n) / np.maximum(pin_n, pout_n))))
+        dvox = np.zeros(flat.shape, dtype=bool)
+        dvox[bidx] = pin_n >= pout_n
+        seg2, excl2, R, A0, Aex, absorbed = step(seg, excl, lab, dvox.reshape(seg.shape))
+        n_flips = int(R.sum() + A0.sum())
+        if n_flips == 0:
+            exit_code = EXIT_CONVERGED
+            break
+        if n_in >= max_segment_size:
+            exit_code = EXIT_MAX_SEGMENT
+            break
+        lab2 = canonical_labels(seg2, excl2)
+        cancelled = A0 & ~Aex
+        quirk["cancelled"] += int(cancelled.sum())
+        quirk["add_to_inside"] += int((Aex & (lab2 == 0)).sum())
+        quirk["remove_to_outside"] += int((R & (lab2 == 3)).sum())
+        quirk["cancel_repromoted"] += int((cancelled & dil3(Aex)).sum())
+        n_in += int(Aex.sum()) - int(R.sum())
+        n_out += int(R.sum()) - int(Aex.sum()) + int(absorbed.sum())
+        seg, excl, lab = seg2, excl2, lab2
+        trace.append((n_flips, n_in, n_out))
+        iter_num += 1
+    return {"labels": lab, "seg": seg, "iterations": iter_num, "exit": exit_code,
+            "trace": np.asarray(trace, dtype=np.int64), "bands": bands, "quirk_potential": quirk,
+            "min_margin": float(min_margin)}
