@@ -14,7 +14,7 @@ OK = 0
 ERR_CUDA, ERR_ARG, ERR_LEVELS, ERR_LABEL, ERR_EMPTY_SEED, ERR_NO_BAND, ERR_NOMEM, ERR_NONFINITE = range(-1, -9, -1)
 EXIT_RUNNING, EXIT_CONVERGED, EXIT_MAX_TIME, EXIT_MAX_SEGMENT, EXIT_MAX_ITER = -1, 0, 1, 2, 3
 INTENSITY_F64_DENSE, INTENSITY_F64_BAND, INTENSITY_INDEX = 0, 1, 2
-INTENSITY_MODES = {"f64_dense": 0, "f64_band": 1, "index": 2}
+INTENSITY_MODES = {"f64_dense": 0, "f64_band": 1, "index": 2, "continuous": 3}
 HALO = 2
 P2P_HANDLE_BYTES = 192
 BUF_SEG, BUF_EXCL, BUF_FLIPS, BUF_CANCELLED, BUF_LOCAL_STATS, BUF_GLOBAL_STATS, BUF_CTRL = range(7)
@@ -69,6 +69,7 @@ _SIGS = {
     "vrg_get_trace": [vp, vp, i64, ctypes.POINTER(i64)],
     "vrg_get_table": [vp, vp, vp, i64],
     "vrg_get_table_levels": [vp, vp, i64],
+    "vrg_get_band_sums": [vp, vp, vp, vp, i64, ctypes.POINTER(i64)],
     "vrg_phantom_device": [ctypes.c_int, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, ctypes.c_int, vp, vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["vrg_last_error", "vrg_version"])

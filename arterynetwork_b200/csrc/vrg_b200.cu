@@ -3,6 +3,7 @@
 #include "../../include/vrg_b200.h"
 #include "vrg_kernels.cuh"
 #include "vrg_p2p.cuh"
+#include "vrg_parzen.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -77,6 +78,9 @@ struct vrg_handle {
     long long *d_slots = nullptr;
     std::vector<void *> ipc_opened;
     long long epoch = 0;
+    // continuous-intensity mode (vrg_parzen.cuh)
+    Cont cq;
+    bool cont_alloc = false;
     // CUDA graph of one batch of iterations (vrg_run)
     cudaGraphExec_t gexec = nullptr;
     uint64_t gsig = 0;
@@ -140,7 +144,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     if (Z <= 0 || Y <= 0 || X <= 0 || cfg->z_begin < 0 || cfg->z_end > Z || cfg->z_begin >= cfg->z_end)
         return fail(VRG_ERR_ARG, "bad shape or slab [%lld,%lld) of Z=%lld", (long long)cfg->z_begin, (long long)cfg->z_end, (long long)Z);
     if (Y > 0x7FFFFFF0 || X > 0x7FFFFFF0) return fail(VRG_ERR_ARG, "axis too long");
-    if (cfg->intensity_mode < 0 || cfg->intensity_mode > 2) return fail(VRG_ERR_ARG, "bad intensity_mode");
+    if (cfg->intensity_mode < 0 || cfg->intensity_mode > 3) return fail(VRG_ERR_ARG, "bad intensity_mode");
     if (!(cfg->H > 0) || cfg->iter_max < 1) return fail(VRG_ERR_ARG, "bad H or iter_max");
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
@@ -216,6 +220,10 @@ int vrg_destroy(vrg_handle *h) {
     cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_dirty); cudaFree(h->d_stamp);
     cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
     free_levels(h);
+    if (h->cont_alloc) {
+        cudaFree(h->cq.pin); cudaFree(h->cq.pout); cudaFree(h->cq.B); cudaFree(h->cq.newlist); cudaFree(h->cq.oldlist);
+        cudaFree(h->cq.rowlist); cudaFree(h->cq.count); cudaFree(h->cq.partial);
+    }
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (void *o : h->ipc_opened) cudaIpcCloseMemHandle(o);
     cudaFree(h->d_recv); cudaFree(h->d_flags); cudaFree(h->d_slots);
@@ -453,9 +461,115 @@ static int launch_init_hist(vrg_handle *h) {
     return VRG_OK;
 }
 
+static int cont_alloc(vrg_handle *h) {
+    if (h->cont_alloc) return VRG_OK;
+    const Params &p = h->p;
+    const size_t nvox = (size_t)p.nzl * p.plane_vox;
+    if (nvox >= 0x7FFFFFFFull) return fail(VRG_ERR_ARG, "continuous mode: volume too large (%zu voxels)", nvox);
+    Cont &q = h->cq;
+    memset(&q, 0, sizeof q);
+    q.cap = (int)std::min<size_t>(nvox, (size_t)1 << 18);
+    const size_t ntiles = ((size_t)q.cap + CONT_TILE - 1) / CONT_TILE;
+    CK(cudaMalloc((void **)&q.pin, nvox * sizeof(double)));
+    CK(cudaMalloc((void **)&q.pout, nvox * sizeof(double)));
+    CK(cudaMalloc((void **)&q.B, h->plane_bytes));
+    CK(cudaMalloc((void **)&q.newlist, (size_t)q.cap * sizeof(int)));
+    CK(cudaMalloc((void **)&q.oldlist, (size_t)q.cap * sizeof(int)));
+    CK(cudaMalloc((void **)&q.rowlist, h->rowflag_bytes * sizeof(int)));
+    CK(cudaMalloc((void **)&q.count, CC_WORDS * sizeof(int)));
+    CK(cudaMalloc((void **)&q.partial, ntiles * CONT_SPLIT * CONT_TILE * 2 * sizeof(double)));
+    h->cont_alloc = true;
+    return VRG_OK;
+}
+
+// init of the continuous mode: no level table; region sizes by counting, every band voxel gets its full sums
+static int cont_init(vrg_handle *h) {
+    Params &p = h->p;
+    if (p.valid_lo != p.own_lo || p.valid_hi != p.own_hi) return fail(VRG_ERR_ARG, "continuous mode runs on a single slab");
+    if (!h->d_lstats || p.L != 0) {
+        free_levels(h);
+        h->separate_gstats = false;
+        p.L = 0; p.LW = 0; p.lattice = 0; p.levels = nullptr; p.kmat = nullptr; p.dbits = nullptr; p.pin = p.pout = nullptr;
+        CK(cudaMalloc((void **)&h->d_lstats, ST_EXTRA * sizeof(long long)));
+        h->d_gstats = h->d_lstats;
+        p.lstats = h->d_lstats; p.gstats = h->d_gstats;
+    }
+    { int rc_ = cont_alloc(h); if (rc_ != VRG_OK) return rc_; }
+    Cont &q = h->cq;
+    const size_t nvox = (size_t)p.nzl * p.plane_vox;
+    CK(cudaMemsetAsync(h->d_S, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_E, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_F, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(q.B, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(q.pin, 0, nvox * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(q.pout, 0, nvox * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(q.count, 0, CC_WORDS * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_rowflag, 0, h->rowflag_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_front, 0, 2 * (size_t)p.front_cap * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_dirty, 0, 2 * (size_t)p.front_cap * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_stamp, 0xFF, h->rowflag_bytes * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_unitmap, 0, h->unitmap_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_lstats, 0, ST_EXTRA * sizeof(long long), h->stream));
+    CK(cudaMemsetAsync(h->d_trace, 0, 3 * (h->cfg.iter_max + 2) * sizeof(long long), h->stream));
+    long long c[C_WORDS];
+    memset(c, 0, sizeof c);
+    c[C_STATUS] = RUNNING; c[C_ITER] = 1; c[C_ITER_MAX] = h->cfg.iter_max; c[C_MAX_SEG] = h->cfg.max_segment_size;
+    c[C_TRACE_N] = 1; c[C_TABLE_CHANGED] = 1; c[C_EPOCH] = ++h->epoch;
+    memcpy(h->h_ctrl, c, sizeof c);
+    CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    p.E = h->d_E; p.C = nullptr;
+    k_init_planes<<<h->grid, BLOCK, 0, h->stream>>>(p, h->vm_base, h->d_E);
+    k_init_bands<<<h->grid, BLOCK, 0, h->stream>>>(p);
+    k_cont_count<<<h->grid, BLOCK, 0, h->stream>>>(p);
+    p.E = nullptr;
+    k_cont_band<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
+    k_cont_full1<<<dim3(h->sms, CONT_SPLIT), BLOCK, 0, h->stream>>>(p, q);
+    k_cont_full2<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
+    h->launches += 6;
+    CK(cudaGetLastError());
+    long long ex[ST_EXTRA];
+    int cc[CC_WORDS];
+    std::vector<uint32_t> eplane(h->plane_bytes / sizeof(uint32_t));
+    CK(cudaMemcpyAsync(ex, h->d_lstats, sizeof ex, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cc, q.count, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(eplane.data(), h->d_E, h->plane_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (ex[ST_BAD_LABEL]) return fail(VRG_ERR_LABEL, "initial valueMap may only hold labels 0 (seed), 3 (outside) and 4 (excluded)");
+    for (uint32_t w : eplane)
+        if (w) return fail(VRG_ERR_ARG, "continuous mode does not support excluded voxels (label 4) yet");
+    if (ex[ST_N_IN] == 0) return fail(VRG_ERR_EMPTY_SEED, "no seed voxel (label 0) in valueMap");
+    if (ex[ST_N_BAND] == 0) return fail(VRG_ERR_NO_BAND, "seed has no boundary: every voxel is inside");
+    if (cc[CC_OVERFLOW]) return fail(VRG_ERR_ARG, "continuous mode: more than %d band voxels entered at once", q.cap);
+    long long row[3] = {-1, ex[ST_N_IN], ex[ST_N_OUT]};
+    CK(cudaMemcpyAsync(h->d_trace, row, sizeof row, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->inited = true;
+    h->ev_used = 0;
+    h->prof_sweeps0 = 0;
+    return VRG_OK;
+}
+
+static int cont_enqueue_iteration(vrg_handle *h) {
+    const Params &p = h->p;
+    const Cont &q = h->cq;
+    k_cont_begin<<<1, 32, 0, h->stream>>>(p, q);
+    k_cont_decide<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
+    k_cancel<MODE_CONT, false><<<h->grid, BLOCK, 0, h->stream>>>(p);
+    k_advance<<<1, 32, 0, h->stream>>>(p);
+    k_cont_rows<<<1, 1024, 0, h->stream>>>(p, q);
+    k_cont_band<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
+    k_cont_incr<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
+    k_cont_full1<<<dim3(h->sms, CONT_SPLIT), BLOCK, 0, h->stream>>>(p, q);
+    k_cont_full2<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
+    h->launches += 9;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
+
 int vrg_init(vrg_handle *h) {
     if (!h || !h->have_data) return fail(VRG_ERR_ARG, "upload first");
     CK(cudaSetDevice(h->cfg.device));
+    if (h->cfg.intensity_mode == VRG_INTENSITY_CONTINUOUS) return cont_init(h);
     if (!h->have_levels) {
         int64_t n = 0;
         int rc = vrg_scan_levels(h, &n);
@@ -682,6 +796,10 @@ int vrg_poll(vrg_handle *h, vrg_result *res) {
 static int enqueue_batch(vrg_handle *h, int n) {
     for (int k = 0; k < n; ++k) {
         int rc;
+        if (h->cfg.intensity_mode == VRG_INTENSITY_CONTINUOUS) {
+            if ((rc = cont_enqueue_iteration(h)) != VRG_OK) return rc;
+            continue;
+        }
         if ((rc = vrg_enqueue_decide(h)) != VRG_OK) return rc;
         if ((rc = vrg_enqueue_cancel(h)) != VRG_OK) return rc;
         if (h->p2p_on && (rc = vrg_enqueue_p2p_halo(h, 0)) != VRG_OK) return rc;
@@ -754,6 +872,7 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
         int rc = vrg_poll(h, &r);
         if (rc != VRG_OK) return rc;
         if (r.exit_reason == EXIT_PEER_TIMEOUT) return fail(VRG_ERR_CUDA, "peer GPU did not answer (p2p timeout)");
+        if (r.exit_reason == EXIT_CONT_OVERFLOW) return fail(VRG_ERR_ARG, "continuous mode: band list overflow (%d voxels)", h->cq.cap);
         if (r.exit_reason != VRG_EXIT_RUNNING) break;
         if (h->cfg.max_seconds > 0 &&
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= h->cfg.max_seconds) {
@@ -886,6 +1005,40 @@ int vrg_get_table(vrg_handle *h, double *pin, double *pout, int64_t cap) {
     CK(cudaStreamSynchronize(h->stream));
     if (pin) CK(cudaMemcpy(pin, h->d_pin, h->p.L * sizeof(double), cudaMemcpyDeviceToHost));
     if (pout) CK(cudaMemcpy(pout, h->d_pout, h->p.L * sizeof(double), cudaMemcpyDeviceToHost));
+    return VRG_OK;
+}
+
+// continuous mode: the normalised Parzen sums the last decision used, at every band voxel (own planes, C order)
+int vrg_get_band_sums(vrg_handle *h, int64_t *vox_out, double *pin_out, double *pout_out, int64_t cap, int64_t *n_out) {
+    NEED_INIT();
+    if (h->cfg.intensity_mode != VRG_INTENSITY_CONTINUOUS || !n_out) return fail(VRG_ERR_ARG, "continuous mode only");
+    const Params &p = h->p;
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t words = (size_t)h->nz_own * p.plane_words, nvox = (size_t)h->nz_own * p.plane_vox;
+    std::vector<uint32_t> B(words);
+    std::vector<double> pin(nvox), pout(nvox);
+    long long ex[ST_EXTRA];
+    CK(cudaMemcpy(B.data(), h->cq.B + (size_t)p.own_lo * p.plane_words, words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pin.data(), h->cq.pin + (size_t)p.own_lo * p.plane_vox, nvox * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pout.data(), h->cq.pout + (size_t)p.own_lo * p.plane_vox, nvox * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ex, h->d_lstats, sizeof ex, cudaMemcpyDeviceToHost));
+    int64_t n = 0;
+    for (int64_t zl = 0; zl < h->nz_own; ++zl)
+        for (int64_t y = 0; y < p.Y; ++y)
+            for (int c = 0; c < p.XW; ++c) {
+                uint32_t w = B[(size_t)zl * p.plane_words + (size_t)y * p.WP + c];
+                while (w) {
+                    const int b = __builtin_ctz(w); w &= w - 1;
+                    const int64_t v = (zl * p.Y + y) * p.X + (int64_t)c * 32 + b;
+                    if (n < cap) {
+                        if (vox_out) vox_out[n] = v;
+                        if (pin_out) pin_out[n] = pin[v] / (double)ex[ST_N_IN];
+                        if (pout_out) pout_out[n] = pout[v] / (double)ex[ST_N_OUT];
+                    }
+                    ++n;
+                }
+            }
+    *n_out = n;
     return VRG_OK;
 }
 

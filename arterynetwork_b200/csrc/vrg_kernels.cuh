@@ -36,7 +36,7 @@ enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, 
 enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_TABLE_CHANGED = 8, C_WORDS = 16 };
 constexpr long long RUNNING = -1;
 
-enum { MODE_F64_DENSE = 0, MODE_F64_BAND = 1, MODE_INDEX = 2 };
+enum { MODE_F64_DENSE = 0, MODE_F64_BAND = 1, MODE_INDEX = 2, MODE_CONT = 3 };  // MODE_CONT: no level table (vrg_parzen.cuh)
 
 struct Params {
     // geometry
@@ -526,14 +526,23 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         // phase 1 (no convergence points, so the 30 dependency chains overlap): bit j+1 of `mine` = decision of this
         // lane's voxel in word j;  phase 2: 32x32 bit transpose across the warp, lane j+1 ends up with word j.
         uint32_t mine = 0;
+        // batches of 10 words: loads first, then the level arithmetic, then the table look-ups, so that ten
+        // dependency chains are in flight at once whatever the register allocator would prefer
+        const int nbatch = p.segw > 20 ? 3 : (p.segw > 10 ? 2 : 1);
 #pragma unroll
-        for (int jg = 0; jg < WORDS_PER_WARP; jg += 6) {
-            if (jg >= p.segw) break;  // warp-uniform; inside a group of 6 the chains stay branch-free
+        for (int jb = 0; jb < WORDS_PER_WARP; jb += 10) {
+            if (jb / 10 >= nbatch) break;  // warp-uniform (words past segw hold valid stale data, masked by the band)
+            double v[10];
+            int l[10];
+            uint32_t w[10];
 #pragma unroll
-            for (int j = jg; j < jg + 6; ++j) {
-                const int l = level_of<LATTICE>(p, sv[j * 32]);
-                mine |= ((s_dbits[l >> 5] >> (l & 31)) & 1u) << (j + 1);
-            }
+            for (int k = 0; k < 10; ++k) v[k] = sv[(jb + k) * 32];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) l[k] = level_of<LATTICE>(p, v[k]);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) w[k] = s_dbits[l[k] >> 5];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) mine |= ((w[k] >> (l[k] & 31)) & 1u) << (jb + k + 1);
         }
         const uint32_t D = transpose32(mine, lane);
         __syncwarp();
@@ -691,14 +700,14 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
         if (active) {
             d_in += __popc(a) - __popc(r);
             const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
-            uint32_t m = r;
+            uint32_t m = MODE == MODE_CONT ? 0u : r;  // the continuous mode has no histograms: see k_cont_incr
             while (m) {
                 const int b = __ffs(m) - 1; m &= m - 1;
                 const int l = level_at<MODE, LATTICE>(p, rowvox + b);
                 atomicAdd(&hin[l], ~0ull);
                 atomicAdd(&hout[l], 1ull);
             }
-            m = a;
+            m = MODE == MODE_CONT ? 0u : a;
             while (m) {
                 const int b = __ffs(m) - 1; m &= m - 1;
                 const int l = level_at<MODE, LATTICE>(p, rowvox + b);

@@ -202,6 +202,17 @@ class VRGEngine:
         nat.check(self.lib.vrg_get_trace(self._h, out.ctypes.data, cap, ctypes.byref(n)))
         return out[: n.value].copy()
 
+    def band_sums(self):
+        """Continuous mode: (flat voxel index, pin/n_in, pout/n_out) of every band voxel at the last decision."""
+        n = nat.i64(0)
+        nat.check(self.lib.vrg_get_band_sums(self._h, None, None, None, 0, ctypes.byref(n)))
+        vox = np.empty(n.value, dtype=np.int64)
+        pin, pout = np.empty(n.value), np.empty(n.value)
+        if n.value:
+            nat.check(self.lib.vrg_get_band_sums(self._h, vox.ctypes.data, pin.ctypes.data, pout.ctypes.data, n.value,
+                                                 ctypes.byref(n)))
+        return vox, pin, pout
+
     def table(self):
         """(levels, pin, pout) of the most recent decision table (VRG:79-82)."""
         r = self.poll()

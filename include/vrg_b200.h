@@ -50,7 +50,9 @@ typedef enum {
 typedef enum {
     VRG_INTENSITY_F64_DENSE = 0, /* stream the fp64 volume: every voxel's decision, every iteration (reference dtype) */
     VRG_INTENSITY_F64_BAND = 1,  /* fp64 volume, but only 32-voxel words that hold a band voxel */
-    VRG_INTENSITY_INDEX = 2      /* uint16 level-index volume built once; band words only */
+    VRG_INTENSITY_INDEX = 2,     /* uint16 level-index volume built once; band words only */
+    VRG_INTENSITY_CONTINUOUS = 3 /* no level table: brute-force Parzen sums per band voxel (VRG:151-155,232-255), for data
+                                    with more than VRG_MAX_LEVELS distinct intensities; single GPU, small volumes, no label 4 */
 } vrg_intensity_mode;
 
 #define VRG_MAX_LEVELS 65536
@@ -160,6 +162,8 @@ int vrg_get_trace(vrg_handle *h, int64_t *rows_out, int64_t cap_rows, int64_t *n
 /* last decision table: in/out normalised Parzen sums per level (VRG:79-82), for parity checks */
 int vrg_get_table(vrg_handle *h, double *pin_out, double *pout_out, int64_t cap);
 int vrg_get_table_levels(vrg_handle *h, double *levels_out, int64_t cap); /* the table's level of each slot */
+/* continuous mode: flat voxel index (own planes) and the normalised sums of the last decision at every band voxel */
+int vrg_get_band_sums(vrg_handle *h, int64_t *vox_out, double *pin_out, double *pout_out, int64_t cap, int64_t *n);
 
 /* synthetic phantom generated on the device (bench configs that exceed host RAM) */
 int vrg_phantom_device(int device, const int64_t *shape, int64_t z0, int64_t nz, const int64_t *segments,
