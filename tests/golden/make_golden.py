@@ -118,6 +118,21 @@ def case_excl32():  # label-4 voxels and the 4->3 absorption (VRG:137,167-168,17
     return np.rint(data * 256).astype(np.int64), 256, vm.astype(np.int64), dict(H=2.25, max_segment_size=None)
 
 
+def case_tube_cont():  # continuous intensities (no lattice): the brute-force Parzen path, SURVEY.md section 8(f) N1
+    data = np.zeros((16, 16, 28))
+    data[6:10, 6:10, 4:24] = 1.0
+    data = data + np.random.default_rng(0).normal(0, 0.12, data.shape)
+    vm = np.full(data.shape, 3)
+    vm[7:9, 7:9, 13:15] = 0
+    return data, 0, vm, dict(H=2.25, max_segment_size=None)
+
+
+def case_forest_cont():
+    data, vm, _ = make_phantom((24, 24, 24), seed=0, cell=(24, 24, 24), margin=3, depth=2, root_r2=4, min_len=6, max_len=9)
+    data = data + np.random.default_rng(5).normal(0, 1e-3, data.shape)  # break the lattice: 13824 distinct values
+    return data, 0, vm.astype(np.int64), dict(H=2.25, max_segment_size=None)
+
+
 C1_KW = dict(cell=(128, 128, 128), margin=8, depth=4, root_r2=16, min_len=16, max_len=34)
 
 
@@ -138,6 +153,8 @@ CASES = {
     "cancel32": case_cancel32,
     "excl32": case_excl32,
     "c1_128": case_c1_128,
+    "tube_cont": case_tube_cont,
+    "forest_cont": case_forest_cont,
 }
 SMALL = [c for c in CASES if c != "c1_128"]
 
@@ -160,7 +177,8 @@ def level_tables(res, data, max_levels=None):
 
 def generate(name):
     k, q, vm, kw = CASES[name]()
-    data = k if q == 1 else k.astype(np.float64) / q
+    continuous = q == 0  # the case returns float64 data itself
+    data = k if q in (0, 1) else k.astype(np.float64) / q
     t0 = time.time()
     res = run_reference(data, vm, H=kw["H"], max_segment_size=kw["max_segment_size"],
                         check_drift=(name != "c1_128"))
@@ -171,7 +189,8 @@ def generate(name):
                             np.flatnonzero(res["segmented_map"].ravel() == 1))
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),
-        k=k.astype(np.int16), quantum=np.int64(q), data_is_int=np.bool_(q == 1),
+        k=(np.zeros(1, np.int16) if continuous else k.astype(np.int16)), quantum=np.int64(q), data_is_int=np.bool_(q == 1),
+        data_f64=(data.astype(np.float64) if continuous else np.zeros(1)),
         value_map_in=np.asarray(vm, dtype=np.uint8),
         H=np.float64(kw["H"]),
         max_segment_size=np.int64(-1 if kw["max_segment_size"] is None else kw["max_segment_size"]),

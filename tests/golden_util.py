@@ -14,9 +14,13 @@ def golden_names():
 def load_golden(name):
     f = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     g = {k: f[k] for k in f.files}
-    k = g["k"].astype(np.int64)
     q = int(g["quantum"])
-    g["data"] = k if bool(g["data_is_int"]) else k.astype(np.float64) / q
+    if q == 0:  # continuous intensities are stored as they are
+        k = g["data_f64"]
+        g["data"] = k.astype(np.float64)
+    else:
+        k = g["k"].astype(np.int64)
+        g["data"] = k if bool(g["data_is_int"]) else k.astype(np.float64) / q
     g["value_map_in"] = g["value_map_in"].astype(np.int64)
     ms = int(g["max_segment_size"])
     g["max_segment_size"] = (k.size + 1) if ms < 0 else ms

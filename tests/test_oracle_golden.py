@@ -12,7 +12,8 @@ from oracle.c_oracle import vrg_oracle_c
 from oracle.vrg_oracle import vrg_oracle
 
 NAMES = golden_names()
-SMALL = [n for n in NAMES if n != "c1_128"]
+CONT = [n for n in NAMES if n.endswith("_cont")]  # continuous intensities: exact-sum oracle (no level table)
+SMALL = [n for n in NAMES if n != "c1_128" and n not in CONT]
 TABLE_RTOL = 1e-12  # normalised Parzen sums at band voxels
 
 
@@ -64,6 +65,28 @@ def test_c_oracle_matches_reference(name):
     g = load_golden(name)
     o = vrg_oracle_c(g["data"], g["value_map_in"], H=g["H"], max_segment_size=g["max_segment_size"])
     _check(g, o)
+
+
+@pytest.mark.parametrize("name", CONT)
+def test_exact_oracle_matches_reference_on_continuous_data(name):
+    """no two voxels share an intensity, the sums are taken against the whole volume."""
+    from oracle.vrg_oracle import vrg_oracle_exact
+    g = load_golden(name)
+    o = vrg_oracle_exact(g["data"], g["value_map_in"], H=g["H"], max_segment_size=g["max_segment_size"], record_band=True)
+    _check(g, o)
+    assert int(g["Q2_voxels"]) == 0 and o["min_margin"] > 1e-6
+    # normalised sums at band voxels, decision by decision (the fixture keys them by the voxel's intensity)
+    flat = g["data"].ravel()
+    worst = 0.0
+    for it, lv, pin, pout in zip(g["tb_iter"], g["tb_level"], g["tb_pin"], g["tb_pout"]):
+        if it >= len(o["bands"]):
+            continue
+        bidx, opin, opout = o["bands"][it]
+        k = np.flatnonzero(flat[bidx] == lv)
+        assert len(k) == 1
+        worst = max(worst, abs(opin[k[0]] - pin) / abs(pin), abs(opout[k[0]] - pout) / abs(pout))
+    tol = TABLE_RTOL if int(g["Q3_dropped"]) == 0 else 2.0 * float(g["max_drift"]) + TABLE_RTOL
+    assert worst <= tol, (worst, tol)
 
 
 def test_c_oracle_tables_match_numpy():
