@@ -102,6 +102,10 @@ def load(build_if_missing: bool = True):
     return lib
 
 
+class LevelsError(ValueError):
+    """More than 65536 distinct intensities: the level-table modes cannot run (VRG_ERR_LEVELS)."""
+
+
 class VRGError(RuntimeError):
     def __init__(self, code, text):
         super().__init__("vrg_b200 error %d: %s" % (code, text))
@@ -111,7 +115,9 @@ class VRGError(RuntimeError):
 def check(rc: int):
     if rc != OK:
         text = load().vrg_last_error().decode("utf-8", "replace")
-        if rc in (ERR_ARG, ERR_LEVELS, ERR_LABEL, ERR_EMPTY_SEED, ERR_NO_BAND, ERR_NONFINITE):
+        if rc == ERR_LEVELS:
+            raise LevelsError("vrg_b200: " + text)
+        if rc in (ERR_ARG, ERR_LABEL, ERR_EMPTY_SEED, ERR_NO_BAND, ERR_NONFINITE):
             raise ValueError("vrg_b200: " + text)
         if rc == ERR_NOMEM:
             raise MemoryError("vrg_b200: " + text)

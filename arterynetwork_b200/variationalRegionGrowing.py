@@ -37,7 +37,8 @@ A = (2 * np.pi) ** (-0.5)  # VRG:7
 MAX_SECONDS = 120.0  # VRG:97
 ITER_MAX = 200  # VRG:56
 DEVICE = 0
-INTENSITY = "f64_band"  # how the decide kernel reads intensities: f64_dense | f64_band | index
+INTENSITY = "index"  # how the sweep reads intensities: f64_dense | f64_band | index | continuous
+CONTINUOUS_MAX_VOXELS = 1 << 24  # fall back to the brute-force Parzen mode (continuous data) up to this volume size
 
 _EXIT_SUFFIX = {nat.EXIT_CONVERGED: "", nat.EXIT_MAX_TIME: " (Max time reached)",
                 nat.EXIT_MAX_SEGMENT: " (Max segment size reached)"}
@@ -66,18 +67,25 @@ def variationalRegionGrowing(dataArray, valueMap, H=2.25, maxSegmentSize=5000):
     vm3 = np.ascontiguousarray(vm_view).reshape(data3.shape)
     if vm3.size and (vm3.min() < 0 or vm3.max() > 255):
         raise ValueError("valueMap may only hold labels 0, 3 and 4")
-    with VRGEngine(data3.shape, H=H, max_segment_size=maxSegmentSize, iter_max=ITER_MAX, device=DEVICE,
-                   intensity=INTENSITY, max_seconds=MAX_SECONDS or 0.0) as eng:
-        eng.upload(np.ascontiguousarray(data3, dtype=np.float64), vm3.astype(np.uint8))
-        eng.init()
-        res = eng.run()
-        labels = eng.labels()
-        if transposed or data3.shape != dataArray.shape:
-            seg_u8 = eng.segmented_map()
-            segmented = None
-        else:
-            seg_u8 = None
-            segmented = eng.segmented()
+    def run(mode):
+        with VRGEngine(data3.shape, H=H, max_segment_size=maxSegmentSize, iter_max=ITER_MAX, device=DEVICE,
+                       intensity=mode, max_seconds=MAX_SECONDS or 0.0) as eng:
+            eng.upload(np.ascontiguousarray(data3, dtype=np.float64), vm3.astype(np.uint8))
+            eng.init()
+            res = eng.run()
+            labels = eng.labels()
+            if transposed or data3.shape != dataArray.shape:
+                return res, labels, eng.segmented_map(), None
+            return res, labels, None, eng.segmented()
+
+    try:
+        res, labels, seg_u8, segmented = run(INTENSITY)
+    except nat.LevelsError:
+        # more than 65536 distinct intensities: no level table.  Small volumes take the brute-force path, which is the
+        # reference's own arithmetic (VRG:151-155, 232-255); large ones are as infeasible here as in the reference.
+        if data3.size > CONTINUOUS_MAX_VOXELS:
+            raise
+        res, labels, seg_u8, segmented = run("continuous")
     lab_user = labels.reshape(vm_view.shape)
     lab_user = lab_user.T if transposed else lab_user
     valueMap[...] = lab_user  # in place, VRG:137-228

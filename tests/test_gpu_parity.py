@@ -127,10 +127,30 @@ def test_errors_are_value_errors():
     vm = np.full(data.shape, 3); vm[2, 2, 2] = 0
     with pytest.raises(ValueError):
         mod.variationalRegionGrowing(bad, vm)
-    cont = np.random.default_rng(0).normal(size=(48, 48, 48))  # > 65536 distinct levels
+    cont = np.random.default_rng(0).normal(size=(48, 48, 48))  # > 65536 distinct levels: no level table
     vm = np.full(cont.shape, 3); vm[2, 2, 2] = 0
-    with pytest.raises(ValueError):
-        mod.variationalRegionGrowing(cont, vm)
+    keep = mod.CONTINUOUS_MAX_VOXELS
+    mod.CONTINUOUS_MAX_VOXELS = 0  # without the brute-force fallback this is an error
+    try:
+        with pytest.raises(ValueError):
+            mod.variationalRegionGrowing(cont, vm)
+    finally:
+        mod.CONTINUOUS_MAX_VOXELS = keep
+
+
+def test_dropin_falls_back_to_continuous_mode():
+    """More than 65536 distinct intensities: the drop-in takes the brute-force Parzen path and matches the reference."""
+    from arterynetwork_b200 import variationalRegionGrowing as mod
+    rng = np.random.default_rng(7)
+    data = np.zeros((40, 41, 41)); data[17:23, 17:23, 8:34] = 1.0
+    data = data + rng.normal(0, 0.1, data.shape)  # 67240 distinct values
+    vm = np.full(data.shape, 3); vm[19:21, 19:21, 20:22] = 0
+    from oracle.vrg_oracle import vrg_oracle_exact
+    ref = vrg_oracle_exact(data, vm, max_segment_size=10 ** 9)
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        segmented, seg_map, vm_out = mod.variationalRegionGrowing(data, vm, maxSegmentSize=10 ** 9)
+    assert "Finished at iteration %d\n" % ref["iterations"] in buf.getvalue()
+    assert np.array_equal(vm_out, ref["labels"]) and np.array_equal(seg_map == 1, ref["seg"])
 
 
 @pytest.mark.parametrize("mode", MODES)
