@@ -265,7 +265,7 @@ def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
     torch.cuda.set_device(local)
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    shape = workloads[args.workload]
+    shape = bench.workload_shape(args, world)
     nvox = shape[0] * shape[1] * shape[2]
     b = slab_bounds(shape[0], world)
     z0, z1 = b[rank], b[rank + 1]
@@ -348,7 +348,7 @@ def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
         achieved = algo_bytes * local_vox / (per_launch_ms * 1e-3) / 1e9
         line = {
             "metric": metric, "value": value, "unit": "Gvoxel-updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s %dx%dx%d vessel-forest phantom, seed %d" % (args.workload, shape[2], shape[1], shape[0], args.seed),
                        "intensity_mode": args.intensity, "partition": "z-slabs, %d planes per rank, halo %d" % (z1 - z0, HALO),

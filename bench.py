@@ -116,7 +116,7 @@ def device_phantom(shape, seed, z0, nz, device):
 def cpu_sample(shape, seed):
     """Bounded CPU sample of the workload: its first CPU_SAMPLE_PLANES planes, as its own volume."""
     from arterynetwork_b200.phantom import make_phantom
-    nz = min(CPU_SAMPLE_PLANES, shape[0])
+    nz = min(CPU_SAMPLE_PLANES, shape[0], max(8, int(1.0e8 // (shape[1] * shape[2]))))  # bounded: about 1e8 voxels
     data, vm, _ = make_phantom(shape, seed=seed, z0=0, nz=nz)
     return data, vm, "planes [0,%d) of the %dx%dx%d phantom as a %dx%dx%d volume, run to convergence" % (
         nz, shape[2], shape[1], shape[0], shape[2], shape[1], nz)
@@ -208,12 +208,20 @@ def roofline_of(r, nvox, peak, peak_kind, traffic=None):
             "cancel_ms_per_launch": prof["cancel_ms"] / max(1, prof["cancel_launches"])}
 
 
+def workload_shape(args, n_gpus):
+    """(Z, Y, X) of the run: the named config, or under --scaling weak its planes / 8 per GPU."""
+    Z, Y, X = WORKLOADS[args.workload]
+    if args.scaling == "weak":
+        Z = (Z // 8) * n_gpus
+    return (Z, Y, X)
+
+
 def run_single(args):
     import torch
     from arterynetwork_b200.engine import VRGEngine
     dev = 0
     torch.cuda.set_device(dev)
-    shape = WORKLOADS[args.workload]
+    shape = workload_shape(args, 1)
     nvox = shape[0] * shape[1] * shape[2]
     peak, peak_kind = measured_peak()
     d_data, d_vm = device_phantom(shape, args.seed, 0, shape[0], dev)
@@ -287,7 +295,7 @@ def run_single(args):
             traffic = None
     line = {
         "metric": METRIC, "value": prim["value"], "unit": "Gvoxel-updates/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": prim["ms"] / args.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": prim["ms"] / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s %dx%dx%d vessel-forest phantom, seed %d" % (args.workload, shape[2], shape[1], shape[0], args.seed),
                    "intensity_mode": args.intensity, "sweeps_per_step": prim["sweeps"] // args.steps,
@@ -318,6 +326,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--intensity", default="f64_dense", choices=["f64_dense", "f64_band", "index"])
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the named volume over N slabs (the BASELINE metric); weak: every GPU gets 1/8 of the "
+                         "named volume's planes, i.e. the volume grows with N (c5: 2048x2048x128 per GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
