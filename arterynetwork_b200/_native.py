@@ -70,6 +70,13 @@ _SIGS = {
     "vrg_get_table": [vp, vp, vp, i64],
     "vrg_get_table_levels": [vp, vp, i64],
     "vrg_get_band_sums": [vp, vp, vp, vp, i64, ctypes.POINTER(i64)],
+    "vrg_edt": [ctypes.c_int, vp, vp, vp],
+    "vrg_edt_device": [ctypes.c_int, vp, vp, vp, vp],
+    "vrg_release_scratch": [ctypes.c_int],
+    "vrg_label_components": [ctypes.c_int, vp, vp, vp, ctypes.POINTER(i64), vp, i64],
+    "vrg_label_components_device": [ctypes.c_int, vp, vp, vp, ctypes.POINTER(i64), vp, i64, vp],
+    "vrg_vessel_mask": [ctypes.c_int, vp, vp, vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, i64, vp, vp, vp],
+    "vrg_vessel_mask_device": [ctypes.c_int, vp, vp, vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, i64, vp, vp, vp, vp],
     "vrg_phantom_device": [ctypes.c_int, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, ctypes.c_int, vp, vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["vrg_last_error", "vrg_version"])

@@ -78,6 +78,10 @@ struct vrg_handle {
     long long *d_slots = nullptr;
     std::vector<void *> ipc_opened;
     long long epoch = 0;
+    // second stream of a slab run: the halo exchange runs beside the statistics exchange + decision table
+    cudaStream_t halo_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool halo_pending = false, p2p_overlap = true;
     // continuous-intensity mode (vrg_parzen.cuh)
     Cont cq;
     bool cont_alloc = false;
@@ -128,6 +132,7 @@ static void prof_collect(vrg_handle *h, int64_t sweeps_now) {
 }
 
 const char *vrg_last_error(void) { return g_err.c_str(); }
+void vrg_set_error_internal(const char *msg) { g_err = msg ? msg : ""; }  // for the other translation units of the library
 int vrg_version(void) { return 101; }
 
 static void free_levels(vrg_handle *h) {
@@ -225,6 +230,9 @@ int vrg_destroy(vrg_handle *h) {
         cudaFree(h->cq.rowlist); cudaFree(h->cq.count); cudaFree(h->cq.partial);
     }
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    if (h->halo_stream) { cudaStreamSynchronize(h->halo_stream); cudaStreamDestroy(h->halo_stream); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (void *o : h->ipc_opened) cudaIpcCloseMemHandle(o);
     cudaFree(h->d_recv); cudaFree(h->d_flags); cudaFree(h->d_slots);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -441,17 +449,33 @@ int vrg_use_separate_global_stats(vrg_handle *h) {
 // ---- init -------------------------------------------------------------------------------------
 static int launch_init_hist(vrg_handle *h) {
     const Params &p = h->p;
-    // lane-private shared histograms when at least 4 warps' worth fit (64 B per level per warp)
+    // lane-private shared histograms (64 B per level per warp)
     const size_t per_warp = (size_t)((p.L + 1) & ~1) * 32 * sizeof(uint16_t);
+    if (!h->hist_attr_set) {
+        CK(cudaFuncSetAttribute(k_init_hist_private<MODE_INDEX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_private<MODE_INDEX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_private<MODE_F64_BAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_private<MODE_F64_BAND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_tma<MODE_INDEX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_tma<MODE_INDEX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_tma<MODE_F64_BAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_tma<MODE_F64_BAND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        h->hist_attr_set = true;
+    }
+    // TMA-staged variant: the level source streams through a per-warp ring (16-byte aligned row segments only)
+    const size_t elem = h->cfg.intensity_mode == VRG_INTENSITY_INDEX ? sizeof(uint16_t) : sizeof(double);
+    if (((size_t)p.X * elem) % 16 == 0 && !h->force_ldg) {
+        const size_t stage_bytes = ((size_t)p.segw * 32 * elem + 127) & ~(size_t)127;
+        const size_t per = per_warp + HIST_STAGES * stage_bytes + HIST_STAGES * 8;
+        const int hw = (int)std::min<size_t>(16, (227 * 1024 - 256) / per);
+        if (hw >= 3) {
+            const size_t smem = (((size_t)hw * HIST_STAGES * 8 + 127) & ~(size_t)127) + (size_t)hw * HIST_STAGES * stage_bytes + hw * per_warp;
+            LAUNCH_ML(k_init_hist_tma, h->sms, hw * 32, smem, p, hw, (int)stage_bytes);
+            return VRG_OK;
+        }
+    }
     const int hw = (int)std::min<size_t>(16, (220 * 1024) / per_warp);
     if (hw >= 4) {
-        if (!h->hist_attr_set) {
-            CK(cudaFuncSetAttribute(k_init_hist_private<MODE_INDEX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CK(cudaFuncSetAttribute(k_init_hist_private<MODE_INDEX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CK(cudaFuncSetAttribute(k_init_hist_private<MODE_F64_BAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            CK(cudaFuncSetAttribute(k_init_hist_private<MODE_F64_BAND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            h->hist_attr_set = true;
-        }
         LAUNCH_ML(k_init_hist_private, h->sms, hw * 32, hw * per_warp, p, hw);
         return VRG_OK;
     }
@@ -639,10 +663,8 @@ int vrg_init(vrg_handle *h) {
     if (!h || !h->inited) return fail(VRG_ERR_ARG, "init first"); \
     CK(cudaSetDevice(h->cfg.device))
 
-int vrg_enqueue_decide(vrg_handle *h) {
-    NEED_INIT();
+static int enqueue_sweep(vrg_handle *h) {
     const Params &p = h->p;
-    k_table<<<p.LW, TABLE_BLOCK, 0, h->stream>>>(p);
     const size_t smem = (size_t)p.LW * sizeof(uint32_t);
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     if (h->cfg.intensity_mode == VRG_INTENSITY_F64_DENSE) {
@@ -661,9 +683,15 @@ int vrg_enqueue_decide(vrg_handle *h) {
         LAUNCH_ML(k_sweep_band, h->grid, BLOCK, smem, p);
     }
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
-    h->launches += 2;
+    h->launches++;
     CK(cudaGetLastError());
     return VRG_OK;
+}
+int vrg_enqueue_decide(vrg_handle *h) {
+    NEED_INIT();
+    k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p);
+    h->launches++;
+    return enqueue_sweep(h);
 }
 int vrg_enqueue_cancel(vrg_handle *h) {
     NEED_INIT();
@@ -701,16 +729,19 @@ int vrg_enqueue_advance(vrg_handle *h) {
 
 // ---- peer-memory transport ---------------------------------------------------------------------------
 // phase 0: executed flips (and cancelled flips when label 4 is present) after cancel; phase 1: excluded plane after flip
-int vrg_enqueue_p2p_halo(vrg_handle *h, int phase) {
-    NEED_INIT();
-    if (!h->p2p_on) return fail(VRG_ERR_ARG, "p2p transport not connected");
+static int enqueue_p2p_halo_on(vrg_handle *h, int phase, cudaStream_t st) {
     const int kinds = phase == 0 ? ((1 << PK_F) | (h->p.E ? (1 << PK_C) : 0)) : (h->p.E ? (1 << PK_E) : 0);
     if (!kinds) return VRG_OK;
-    k_p2p_push_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p, h->q, kinds, 0);
-    k_p2p_wait_unpack_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p, h->q, kinds, 0, phase == 0);
+    k_p2p_push_halo<<<h->sms, BLOCK, 0, st>>>(h->p, h->q, kinds, 0);
+    k_p2p_wait_unpack_halo<<<h->sms, BLOCK, 0, st>>>(h->p, h->q, kinds, 0, phase == 0);
     h->launches += 2;
     CK(cudaGetLastError());
     return VRG_OK;
+}
+int vrg_enqueue_p2p_halo(vrg_handle *h, int phase) {
+    NEED_INIT();
+    if (!h->p2p_on) return fail(VRG_ERR_ARG, "p2p transport not connected");
+    return enqueue_p2p_halo_on(h, phase, h->stream);
 }
 int vrg_enqueue_p2p_stats(vrg_handle *h) {
     NEED_INIT();
@@ -729,7 +760,7 @@ int vrg_p2p_export(vrg_handle *h, int world, void *handles_out) {
     const Params &p = h->p;
     const int slot_words = 2 * VRG_MAX_LEVELS + ST_EXTRA;
     if (!h->d_recv) {
-        const size_t rb = (size_t)P2P_KINDS * 2 * HALO * p.plane_words * sizeof(uint32_t);
+        const size_t rb = (size_t)2 * P2P_KINDS * 2 * HALO * p.plane_words * sizeof(uint32_t);  // two sequence parities
         const size_t sb = (size_t)2 * world * slot_words * sizeof(long long);
         CK(cudaMalloc((void **)&h->d_recv, rb));
         CK(cudaMalloc((void **)&h->d_flags, FLAG_WORDS * sizeof(unsigned long long)));
@@ -770,6 +801,12 @@ int vrg_p2p_connect(vrg_handle *h, int rank, int world, const void *all_handles)
             q.peer_recv[r == rank - 1 ? 0 : 1] = (uint32_t *)pr;
         }
     }
+    if (!h->halo_stream) {
+        CK(cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    h->p2p_overlap = getenv("VRG_P2P_SERIAL") == nullptr;  // A/B switch: everything on one stream, in program order
     h->p2p_on = true;
     h->inited = false;
     return VRG_OK;
@@ -793,11 +830,42 @@ int vrg_poll(vrg_handle *h, vrg_result *res) {
     return VRG_OK;
 }
 
+// Slab run without label 4: after cancel the iteration forks -- the halo exchange (push, wait, unpack) goes to a
+// second stream while the statistics exchange, the loop bookkeeping and the next decision table stay on the main one;
+// the next sweep is the join.  (With label 4 the absorb step sits between two halo exchanges: everything stays serial.)
+static int join_halo(vrg_handle *h) {
+    if (h->halo_pending) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        h->halo_pending = false;
+    }
+    return VRG_OK;
+}
+
+static int enqueue_table(vrg_handle *h) {
+    k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p);
+    h->launches++;
+    return VRG_OK;
+}
+
 static int enqueue_batch(vrg_handle *h, int n) {
     for (int k = 0; k < n; ++k) {
         int rc;
         if (h->cfg.intensity_mode == VRG_INTENSITY_CONTINUOUS) {
             if ((rc = cont_enqueue_iteration(h)) != VRG_OK) return rc;
+            continue;
+        }
+        const bool overlap = h->p2p_on && h->p2p_overlap && h->p.E == nullptr && h->halo_stream != nullptr;
+        if (overlap) {
+            if ((rc = enqueue_table(h)) != VRG_OK) return rc;
+            if ((rc = join_halo(h)) != VRG_OK) return rc;          // the sweep reads the halo planes of S
+            if ((rc = enqueue_sweep(h)) != VRG_OK) return rc;
+            if ((rc = vrg_enqueue_cancel(h)) != VRG_OK) return rc;
+            CK(cudaEventRecord(h->ev_fork, h->stream));
+            CK(cudaStreamWaitEvent(h->halo_stream, h->ev_fork, 0));
+            if ((rc = enqueue_p2p_halo_on(h, 0, h->halo_stream)) != VRG_OK) return rc;
+            CK(cudaEventRecord(h->ev_join, h->halo_stream));
+            h->halo_pending = true;
+            if ((rc = vrg_enqueue_p2p_stats(h)) != VRG_OK) return rc;
             continue;
         }
         if ((rc = vrg_enqueue_decide(h)) != VRG_OK) return rc;
@@ -812,7 +880,7 @@ static int enqueue_batch(vrg_handle *h, int n) {
             if ((rc = vrg_enqueue_advance(h)) != VRG_OK) return rc;
         }
     }
-    return VRG_OK;
+    return join_halo(h);  // a batch ends joined: it may be a captured graph, and the host polls the main stream
 }
 
 static uint64_t run_signature(const vrg_handle *h) {

@@ -2,104 +2,229 @@
 // Reference call sites: Code/manualCorrectionGUI.py:248 (vessel radii from the VRG output mask) and
 // Code/generateVesselVolume.py:183 (distance to the brain-mask boundary), both
 // scipy.ndimage.distance_transform_edt(mask) with default arguments: every non-zero voxel gets its Euclidean distance
-// to the nearest zero voxel, float64.
+// to the nearest zero voxel, float64, unit spacing.
 //
-// Separable and exact in integers: three passes  out(p) = min_k in(p + k*stride) + k^2  along x, y, z over int32
-// squared distances, then one sqrt.  Each pass is a windowed search: the candidate at offset k costs at least k^2,
-// so a voxel stops as soon as k^2 >= its current best -- the work per voxel is its own distance, which is small for
-// vessel masks.  Threads map to x in every pass, so all loads and stores are coalesced whatever the axis.
+// Separable and exact in integers (Meijster, Roerdink, Hesselink 2000):
+//   pass x   g(x)  = (distance to the nearest zero voxel of the same row)^2: a prefix-max / suffix-min scan, one warp per row
+//   pass y,z out(u) = min_i (u - i)^2 + in(i) along the axis: lower envelope of parabolas, one thread per line, O(n) per
+//            line whatever the distances are; neighbouring threads own neighbouring x, so every access of the scan
+//            (input, envelope stacks, output) is a coalesced row of the volume
+//   sqrt     fp64 square root of the integer squared distance (correctly rounded, as NumPy's)
+// Squared distances are int32 (axes <= 32768 would overflow: axes are limited to 16384, 3 * 16384^2 < 2^30).
 #include "../../include/vrg_b200.h"
+
+#include "vrg_scratch.cuh"
 
 #include <cuda_runtime.h>
 
+void vrg_set_error_internal(const char *msg);  // vrg_b200.cu: text behind vrg_last_error()
+
 namespace {
 
-constexpr int EDT_INF = 1 << 29;  // + k^2 (k <= 2^15) stays below 2^31
+using vrg_scratch::Buf;
 
-template <bool FIRST>
-__global__ void __launch_bounds__(256) k_edt_pass(const uint8_t *__restrict__ mask, const int *__restrict__ in, int *__restrict__ out,
-                                                  long long n, int len, long long stride) {
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
-        const int pos = (int)((p / stride) % len);
-        int best = FIRST ? (mask[p] ? EDT_INF : 0) : in[p];
-        for (int k = 1; (long long)k * k < best; ++k) {
-            const bool lo = pos - k >= 0, hi = pos + k < len;
-            if (!lo && !hi) break;
-            const int kk = k * k;
-            if (lo) {
-                const long long q = p - (long long)k * stride;
-                const int v = FIRST ? (mask[q] ? EDT_INF : 0) : in[q];
-                best = min(best, v + kk);
+constexpr int EDT_INF = 1 << 30;  // "no zero voxel seen yet"; sums with k^2 are formed in 64 bits
+constexpr unsigned FULLMASK = 0xFFFFFFFFu;
+
+// pass x: one warp per row, 32 voxels per step; the nearest zero to the left is a running maximum of positions,
+// the nearest to the right a running minimum, each a 5-step warp scan plus a carry
+__global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ mask, int *__restrict__ out, long long nrows, int X) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int NONE_L = -(1 << 20), NONE_R = 1 << 20;  // farther than any axis: the squared distance saturates to EDT_INF
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+        const uint8_t *row = mask + r * X;
+        int *orow = out + r * X;
+        int carry = NONE_L;
+        for (int x0 = 0; x0 < X; x0 += 32) {  // left to right: store the distance to the left zero
+            const int x = x0 + lane;
+            int v = (x < X && row[x] == 0) ? x : NONE_L;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULLMASK, v, o);
+                if (lane >= o) v = max(v, t);
             }
-            if (hi) {
-                const long long q = p + (long long)k * stride;
-                const int v = FIRST ? (mask[q] ? EDT_INF : 0) : in[q];
-                best = min(best, v + kk);
+            v = max(v, carry);
+            carry = __shfl_sync(FULLMASK, v, 31);
+            if (x < X) orow[x] = x - v;  // >= 2^20 - X when there is no zero to the left
+        }
+        carry = NONE_R;
+        for (int x0 = ((X - 1) / 32) * 32; x0 >= 0; x0 -= 32) {  // right to left
+            const int x = x0 + lane;
+            int v = (x < X && row[x] == 0) ? x : NONE_R;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(FULLMASK, v, o);
+                if (lane + o < 32) v = min(v, t);
+            }
+            v = min(v, carry);
+            carry = __shfl_sync(FULLMASK, v, 0);
+            if (x < X) {
+                const int d = min(orow[x], v - x);
+                orow[x] = d >= 32768 ? EDT_INF : d * d;
             }
         }
-        out[p] = best;
+    }
+}
+
+// pass y / z: lower envelope of the parabolas (u - i)^2 + f(i) along one axis.  Thread = one line; `line` enumerates
+// (outer, x) so that threads of a warp sit on neighbouring x.  s / t: the envelope's stack (parabola apex, start of its
+// reign), stored like the volume (element q of a line at q * stride) so that they coalesce as well.
+__global__ void __launch_bounds__(128) k_edt_lines(const int *__restrict__ in, int *__restrict__ out, short *__restrict__ s,
+                                                   int *__restrict__ t, long long nlines, int len, long long stride,
+                                                   int X, long long outer_stride) {
+    for (long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x; line < nlines; line += (long long)gridDim.x * blockDim.x) {
+        const long long base = (line / X) * outer_stride + (line % X);
+        const int *f = in + base;
+        short *ss = s + base;
+        int *tt = t + base;
+        int *o = out + base;
+        // forward scan.  Registers hold the top of the stack (sq, tq, fq = f(sq)).
+        int q = 0, sq = 0, tq = 0;
+        long long fq = f[0];
+        ss[0] = 0; tt[0] = 0;
+        for (int u = 1; u < len; ++u) {
+            const long long fu = f[(long long)u * stride];
+            if (fu >= EDT_INF) continue;  // an infinite parabola never reaches the envelope
+            bool pushed = false;
+            while (true) {
+                // F(tq, sq) > F(tq, u) ?  the new parabola is already lower where the top one starts: pop
+                const long long a = (long long)(tq - sq) * (tq - sq) + fq, b = (long long)(tq - u) * (tq - u) + fu;
+                if (a <= b) break;
+                if (q == 0) { sq = u; fq = fu; tq = 0; ss[0] = (short)u; pushed = true; break; }
+                --q;
+                sq = ss[(long long)q * stride]; tq = tt[(long long)q * stride];
+                fq = f[(long long)sq * stride];
+            }
+            if (pushed) continue;
+            // first position where parabola u is lower than the top one
+            const long long w = 1 + ((long long)u * u - (long long)sq * sq + fu - fq) / (2LL * (u - sq));
+            if (w < len) {
+                ++q; sq = u; tq = (int)w; fq = fu;
+                ss[(long long)q * stride] = (short)u; tt[(long long)q * stride] = (int)w;
+            }
+        }
+        // backward scan
+        for (int u = len - 1; u >= 0; --u) {
+            const long long d = (long long)(u - sq) * (u - sq) + fq;
+            o[(long long)u * stride] = d >= EDT_INF ? EDT_INF : (int)d;
+            if (u == tq && q > 0) {
+                --q;
+                sq = ss[(long long)q * stride]; tq = tt[(long long)q * stride];
+                fq = f[(long long)sq * stride];
+            }
+        }
     }
 }
 
 __global__ void __launch_bounds__(256) k_edt_sqrt(const int *__restrict__ sq, double *__restrict__ out, long long n, int *no_background) {
+    bool inf = false;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
         const int v = sq[p];
-        if (v >= EDT_INF) *no_background = 1;
+        inf |= v >= EDT_INF;
         out[p] = sqrt((double)v);
     }
+    if (inf) *no_background = 1;
+}
+
+int edt_check(const int64_t *shape) {
+    if (!shape || shape[0] <= 0 || shape[1] <= 0 || shape[2] <= 0) return VRG_ERR_ARG;
+    if (shape[0] > 16384 || shape[1] > 16384 || shape[2] > 16384) return VRG_ERR_ARG;
+    return VRG_OK;
+}
+
+// squared distances (int32) of a device mask; scratch = 2 int32 + 1 int16 volume.  sq_out must hold n ints.
+// Asynchronous on `stream`.
+int edt_squared_device(const uint8_t *d_mask, const int64_t *shape, int *sq_out, cudaStream_t stream) {
+    const long long Z = shape[0], Y = shape[1], X = shape[2], n = Z * Y * X;
+    Buf a, t, s;
+    cudaError_t e = a.alloc(n * sizeof(int), stream);
+    if (e == cudaSuccess) e = t.alloc(n * sizeof(int), stream);
+    if (e == cudaSuccess) e = s.alloc(n * sizeof(short), stream);
+    if (e == cudaSuccess) {
+        const int grid = 148 * 8;
+        k_edt_rows<<<grid, 256, 0, stream>>>(d_mask, sq_out, Z * Y, (int)X);                                             // mask -> sq_out
+        k_edt_lines<<<grid, 128, 0, stream>>>(sq_out, a.as<int>(), s.as<short>(), t.as<int>(), Z * X, (int)Y, X, (int)X, X * Y);   // y: sq_out -> a
+        k_edt_lines<<<grid, 128, 0, stream>>>(a.as<int>(), sq_out, s.as<short>(), t.as<int>(), Y * X, (int)Z, X * Y, (int)(X * Y), 0);  // z: a -> sq_out
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA;
+    return VRG_OK;
 }
 
 int edt_device(const uint8_t *d_mask, const int64_t *shape, double *d_out, cudaStream_t stream) {
-    const long long Z = shape[0], Y = shape[1], X = shape[2], n = Z * Y * X;
-    int *a = nullptr, *b = nullptr, *flag = nullptr;
-    cudaError_t e = cudaMalloc((void **)&a, n * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&b, n * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&flag, sizeof(int));
+    const long long n = (long long)shape[0] * shape[1] * shape[2];
+    Buf sq, flag;
+    cudaError_t e = sq.alloc(n * sizeof(int), stream);
+    if (e == cudaSuccess) e = flag.alloc(sizeof(int), stream);
     int rc = VRG_OK;
     if (e == cudaSuccess) {
-        cudaMemsetAsync(flag, 0, sizeof(int), stream);
-        const int grid = 148 * 16;
-        k_edt_pass<true><<<grid, 256, 0, stream>>>(d_mask, nullptr, a, n, (int)X, 1);
-        k_edt_pass<false><<<grid, 256, 0, stream>>>(nullptr, a, b, n, (int)Y, X);
-        k_edt_pass<false><<<grid, 256, 0, stream>>>(nullptr, b, a, n, (int)Z, X * Y);
-        k_edt_sqrt<<<grid, 256, 0, stream>>>(a, d_out, n, flag);
-        int h_flag = 0;
-        e = cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        if (e == cudaSuccess && h_flag) rc = VRG_ERR_ARG;  // no zero voxel anywhere: the transform is undefined
+        rc = edt_squared_device(d_mask, shape, sq.as<int>(), stream);
+        if (rc == VRG_OK) {
+            cudaMemsetAsync(flag.p, 0, sizeof(int), stream);
+            k_edt_sqrt<<<148 * 8, 256, 0, stream>>>(sq.as<int>(), d_out, n, flag.as<int>());
+            int h_flag = 0;
+            e = cudaMemcpyAsync(&h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e == cudaSuccess && h_flag) {  // no zero voxel anywhere: the transform is undefined
+                vrg_set_error_internal("distance transform: the mask has no zero voxel");
+                rc = VRG_ERR_ARG;
+            }
+        }
     }
-    if (e != cudaSuccess) rc = e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA;
-    cudaFree(a); cudaFree(b); cudaFree(flag);
+    if (e != cudaSuccess) {
+        vrg_set_error_internal(cudaGetErrorString(e));
+        rc = e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA;
+    }
     return rc;
+}
+
+int bad_args(const char *what) {
+    vrg_set_error_internal(what);
+    return VRG_ERR_ARG;
 }
 
 }  // namespace
 
+// shared with vrg_mask.cu: squared EDT of a device mask into a device int32 volume
+int vrg_edt_squared_device_internal(const uint8_t *d_mask, const int64_t *shape, int *sq_out, cudaStream_t stream) {
+    return edt_squared_device(d_mask, shape, sq_out, stream);
+}
+
 // mask / dist live on the device
 extern "C" int vrg_edt_device(int device, const uint8_t *mask_dev, const int64_t *shape, double *dist_dev, void *cuda_stream) {
-    if (!mask_dev || !shape || !dist_dev || shape[0] <= 0 || shape[1] <= 0 || shape[2] <= 0) return VRG_ERR_ARG;
-    if (shape[0] > 32768 || shape[1] > 32768 || shape[2] > 32768) return VRG_ERR_ARG;
+    if (!mask_dev || !dist_dev || edt_check(shape) != VRG_OK) return bad_args("distance transform: null buffer or bad shape (axes 1..16384)");
     if (cudaSetDevice(device) != cudaSuccess) return VRG_ERR_CUDA;
+    vrg_scratch::pool_setup(device);
     return edt_device(mask_dev, shape, dist_dev, (cudaStream_t)cuda_stream);
 }
 
 // host buffers: mask uint8 (non-zero = foreground), dist float64, both (Z, Y, X) C order
 extern "C" int vrg_edt(int device, const uint8_t *mask_host, const int64_t *shape, double *dist_host) {
-    if (!mask_host || !shape || !dist_host || shape[0] <= 0 || shape[1] <= 0 || shape[2] <= 0) return VRG_ERR_ARG;
-    if (shape[0] > 32768 || shape[1] > 32768 || shape[2] > 32768) return VRG_ERR_ARG;
+    if (!mask_host || !dist_host || edt_check(shape) != VRG_OK) return bad_args("distance transform: null buffer or bad shape (axes 1..16384)");
     if (cudaSetDevice(device) != cudaSuccess) return VRG_ERR_CUDA;
+    vrg_scratch::pool_setup(device);
     const size_t n = (size_t)shape[0] * shape[1] * shape[2];
-    uint8_t *d_mask = nullptr;
-    double *d_out = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_mask, n);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, n * sizeof(double));
+    Buf d_mask, d_out;
+    cudaError_t e = d_mask.alloc(n, nullptr);
+    if (e == cudaSuccess) e = d_out.alloc(n * sizeof(double), nullptr);
     int rc = VRG_OK;
-    if (e == cudaSuccess) e = cudaMemcpy(d_mask, mask_host, n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_mask.p, mask_host, n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        rc = edt_device(d_mask, shape, d_out, 0);
-        if (rc == VRG_OK) e = cudaMemcpy(dist_host, d_out, n * sizeof(double), cudaMemcpyDeviceToHost);
+        rc = edt_device(d_mask.as<uint8_t>(), shape, d_out.as<double>(), nullptr);
+        if (rc == VRG_OK) e = cudaMemcpy(dist_host, d_out.p, n * sizeof(double), cudaMemcpyDeviceToHost);
     }
-    if (e != cudaSuccess) rc = e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA;
-    cudaFree(d_mask); cudaFree(d_out);
+    if (e != cudaSuccess) {
+        vrg_set_error_internal(cudaGetErrorString(e));
+        rc = e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA;
+    }
     return rc;
+}
+
+// hands the cached scratch blocks of the handle-less entry points (EDT, labelling, vessel mask) back to the driver
+extern "C" int vrg_release_scratch(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) return VRG_ERR_CUDA;
+    cudaDeviceSynchronize();
+    vrg_scratch::pool_trim(device);
+    return VRG_OK;
 }

@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace vrg {
 
 constexpr int HALO = 2;
@@ -33,7 +35,8 @@ constexpr int DENSE_STAGES = 2;
 constexpr int STAGE_BYTES = WORDS_PER_WARP * 32 * 8;
 
 enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, ST_BAD_LABEL = 5, ST_NONFINITE = 6, ST_EXTRA = 8 };
-enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_TABLE_CHANGED = 8, C_WORDS = 16 };
+enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_TABLE_CHANGED = 8,
+       C_EPOCH = 9, C_PEER_TIMEOUT = 10, C_HALO_SEQ = 11, C_HALO_GO = 12, C_WORDS = 16 };  // 9..12: slab runs (vrg_p2p.cuh)
 constexpr long long RUNNING = -1;
 
 enum { MODE_F64_DENSE = 0, MODE_F64_BAND = 1, MODE_INDEX = 2, MODE_CONT = 3 };  // MODE_CONT: no level table (vrg_parzen.cuh)
@@ -527,22 +530,24 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         // lane's voxel in word j;  phase 2: 32x32 bit transpose across the warp, lane j+1 ends up with word j.
         uint32_t mine = 0;
         // batches of 10 words: loads first, then the level arithmetic, then the table look-ups, so that ten
-        // dependency chains are in flight at once whatever the register allocator would prefer
-        const int nbatch = p.segw > 20 ? 3 : (p.segw > 10 ? 2 : 1);
+        // dependency chains are in flight at once whatever the register allocator would prefer.  (Narrower batches
+        // that overshoot segw less -- 4 x 7 for 28 words, 3 x 8 for 22 -- measured the same or slower: profiles/README.md.)
+        constexpr int BW = 10;
+        const int nbatch = (p.segw + BW - 1) / BW;
 #pragma unroll
-        for (int jb = 0; jb < WORDS_PER_WARP; jb += 10) {
-            if (jb / 10 >= nbatch) break;  // warp-uniform (words past segw hold valid stale data, masked by the band)
-            double v[10];
-            int l[10];
-            uint32_t w[10];
+        for (int jb = 0; jb < WORDS_PER_WARP; jb += BW) {
+            if (jb / BW >= nbatch) break;  // warp-uniform (words past segw hold valid stale data, masked by the band)
+            double v[BW];
+            int l[BW];
+            uint32_t w[BW];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) v[k] = sv[(jb + k) * 32];
+            for (int k = 0; k < BW; ++k) v[k] = sv[(jb + k) * 32];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) l[k] = level_of<LATTICE>(p, v[k]);
+            for (int k = 0; k < BW; ++k) l[k] = level_of<LATTICE>(p, v[k]);
 #pragma unroll
-            for (int k = 0; k < 10; ++k) w[k] = s_dbits[l[k] >> 5];
+            for (int k = 0; k < BW; ++k) w[k] = s_dbits[l[k] >> 5];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) mine |= ((w[k] >> (l[k] & 31)) & 1u) << (jb + k + 1);
+            for (int k = 0; k < BW; ++k) mine |= ((w[k] >> (l[k] & 31)) & 1u) << (jb + k + 1);
         }
         const uint32_t D = transpose32(mine, lane);
         __syncwarp();
@@ -656,7 +661,14 @@ __device__ __forceinline__ void claim_dirty_rows(const Params &p, int zl, int y,
 // histogram deltas that replace the reference's incremental float sums (VRG:232-247).
 template <int MODE, bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
-    if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
+    const bool go = p.ctrl[C_STATUS] == RUNNING && p.ctrl[C_APPLY];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // snapshot for the slab halo exchange that follows (vrg_p2p.cuh): it may run beside the statistics exchange,
+        // whose bookkeeping advances C_SWEEPS / C_STATUS.  Sequence number = (run epoch << 32) | (sweep + 1).
+        p.ctrl[C_HALO_GO] = go;
+        p.ctrl[C_HALO_SEQ] = (long long)(((unsigned long long)p.ctrl[C_EPOCH] << 32) | (unsigned long long)(p.ctrl[C_SWEEPS] + 1));
+    }
+    if (!go) return;
     const int lane = threadIdx.x & 31;
     long long d_in = 0;
     unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
@@ -851,15 +863,14 @@ __global__ void __launch_bounds__(BLOCK) k_init_planes(Params p, const uint8_t *
                 const uint4 v = q[h];
                 const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const uint32_t byte = (ws[k] >> (8 * b)) & 0xFFu;
-                        const int bit = h * 16 + k * 4 + b;
-                        s |= (uint32_t)(byte == 0u) << bit;
-                        e |= (uint32_t)(byte == 4u) << bit;
-                        bad |= !(byte == 0u || byte == 3u || byte == 4u);
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    // per-byte compares (0xFF where equal), then the four byte flags gathered into four adjacent bits
+                    const uint32_t z = __vcmpeq4(ws[k], 0u), f = __vcmpeq4(ws[k], 0x04040404u), t = __vcmpeq4(ws[k], 0x03030303u);
+                    const int sh = h * 16 + k * 4;
+                    s |= (((z & 0x01010101u) * 0x10204080u) >> 28) << sh;  // bytes 0..3 -> bits 0..3
+                    e |= (((f & 0x01010101u) * 0x10204080u) >> 28) << sh;
+                    bad |= (z | f | t) != 0xFFFFFFFFu;
+                }
             }
         } else {
             for (int b = 0; b < n; ++b) {
@@ -982,34 +993,161 @@ __global__ void k_init_hist_private(Params p, int hw) {
         }
         pending = 0;
     };
+    constexpr int U = 14;  // independent level loads in flight per lane: unconditional (clamped) so that they all issue first
     for (int r = blockIdx.x * hw + warp; r < nrows; r += nwarps) {
         const int y = r % p.Y, zl = p.own_lo + r / p.Y;
         const long long wbase = (long long)zl * p.plane_words + (long long)y * p.WP;
         const long long vbase = (long long)zl * p.plane_vox + (long long)y * p.X;
-        for (int cb = 0; cb < p.XW; cb += 8) {  // eight independent level loads in flight per lane
-            int lv[8];
-            uint32_t sw[8], ew[8];
+        for (int c32 = 0; c32 < p.XW; c32 += 32) {
+            const int nw = min(32, p.XW - c32);
+            const uint32_t srow = lane < nw ? p.S[wbase + c32 + lane] : 0u;
+            const uint32_t erow = (p.E && lane < nw) ? p.E[wbase + c32 + lane] : 0u;
+            for (int cb = 0; cb < nw; cb += U) {
+                int lv[U];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int c = cb + k, x = c * 32 + lane;
-                lv[k] = -1; sw[k] = 0u; ew[k] = 0u;
-                if (c < p.XW) {
-                    sw[k] = p.S[wbase + c];
-                    ew[k] = p.E ? p.E[wbase + c] : 0u;
-                    if (x < p.X) lv[k] = level_at<MODE, LATTICE>(p, vbase + x);
+                for (int k = 0; k < U; ++k) {
+                    const int x = min((c32 + cb + k) * 32 + lane, p.X - 1);
+                    lv[k] = level_at<MODE, LATTICE>(p, vbase + x);
                 }
-            }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int l = lv[k];
-                if (l < 0) continue;
-                const uint32_t bit = 1u << lane;
-                if (sw[k] & bit) { n_in++; atomicAdd(&hin[l], 1ull); }
-                else if (ew[k] & bit) n_ex++;
-                else { n_out++; mine[(l >> 1) * 64 + (l & 1)] += 1; }
+                for (int k = 0; k < U; ++k) {
+                    const int c = c32 + cb + k;
+                    const uint32_t sw = __shfl_sync(FULL, srow, (cb + k) & 31), ew = __shfl_sync(FULL, erow, (cb + k) & 31);
+                    if (cb + k >= nw || c * 32 + lane >= p.X) continue;
+                    const int l = lv[k];
+                    const uint32_t bit = 1u << lane;
+                    if (sw & bit) { n_in++; atomicAdd(&hin[l], 1ull); }
+                    else if (ew & bit) n_ex++;
+                    else { n_out++; mine[(l >> 1) * 64 + (l & 1)] += 1; }
+                }
             }
         }
         pending += p.XW;
+        if (pending > 60000) flush();
+    }
+    flush();
+    n_in = warp_sum(n_in); n_out = warp_sum(n_out); n_ex = warp_sum(n_ex);
+    if (lane == 0) {
+        if (n_in) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_IN], (unsigned long long)n_in);
+        if (n_out) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_OUT], (unsigned long long)n_out);
+        if (n_ex) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_EXCL], (unsigned long long)n_ex);
+    }
+}
+
+// k_init_hist_tma: k_init_hist_private with the level source (fp64 intensities, or the uint16 index volume) streamed
+// through a per-warp ring of TMA bulk-copy stages, exactly like the dense sweep: one stage = one row segment.  With the
+// loads off the warps' dependency chains, the few warps that fit beside their private histograms (5 at 468 levels)
+// keep enough bytes in flight to run at HBM speed.  Needs 16-byte aligned row segments (host checks).
+constexpr int HIST_STAGES = 2;
+template <int MODE, bool LATTICE>
+__global__ void k_init_hist_tma(Params p, int hw, int stage_bytes) {
+    using T = typename std::conditional<MODE == MODE_INDEX, uint16_t, double>::type;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int LP = (p.L + 1) & ~1;
+    uint64_t *bars = (uint64_t *)smem_raw;                                                  // [hw][HIST_STAGES]
+    unsigned char *stages = smem_raw + ((hw * HIST_STAGES * 8 + 127) & ~127);                // [hw][HIST_STAGES][stage_bytes]
+    uint16_t *s_hp = (uint16_t *)(stages + (size_t)hw * HIST_STAGES * stage_bytes);         // [hw][LP][32]
+    for (int i = threadIdx.x; i < hw * LP * 32; i += blockDim.x) s_hp[i] = 0;
+    uint64_t *mybar = bars + warp * HIST_STAGES;
+    unsigned char *mystage = stages + (size_t)warp * HIST_STAGES * stage_bytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < HIST_STAGES; ++s) mbar_init(mybar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint16_t *mine = s_hp + (size_t)warp * LP * 32 + lane * 2;
+    unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
+    const long long nrows = (long long)(p.own_hi - p.own_lo) * p.Y * p.nseg;
+    const long long stride = (long long)gridDim.x * hw;
+    auto decode = [&](long long r, int &zl, int &y, int &sg) {
+        sg = (int)(r % p.nseg);
+        const long long t = r / p.nseg;
+        y = (int)(t % p.Y);
+        zl = p.own_lo + (int)(t / p.Y);
+    };
+    auto issue = [&](long long r, int s) {  // lane 0 only
+        int zl, y, sg;
+        decode(r, zl, y, sg);
+        const int x0 = sg * p.segw * 32;
+        const uint32_t bytes = (uint32_t)min(p.segw * 32, p.X - x0) * (uint32_t)sizeof(T);
+        const long long vox = (long long)zl * p.plane_vox + (long long)y * p.X + x0;
+        const void *src = MODE == MODE_INDEX ? (const void *)(p.index + vox) : (const void *)(p.data + vox);
+        mbar_expect_tx(mybar + s, bytes);
+        tma_bulk_load(mystage + (size_t)s * stage_bytes, src, bytes, mybar + s);
+    };
+    long long pre = (long long)blockIdx.x * hw + warp, cur = pre;
+#pragma unroll
+    for (int s = 0; s < HIST_STAGES; ++s) {
+        if (pre < nrows) {
+            if (lane == 0) issue(pre, s);
+            pre += stride;
+        }
+    }
+    long long n_in = 0, n_out = 0, n_ex = 0;
+    int pending = 0, stage = 0;
+    uint32_t parity = 0;
+    auto flush = [&]() {
+        __syncwarp();
+        for (int l = 0; l < p.L; ++l) {
+            unsigned int v = mine[(l >> 1) * 64 + (l & 1)];
+            mine[(l >> 1) * 64 + (l & 1)] = 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+            if (lane == 0 && v) atomicAdd(&hout[l], (unsigned long long)v);
+        }
+        pending = 0;
+    };
+    for (; cur < nrows; cur += stride) {
+        int zl, y, sg;
+        decode(cur, zl, y, sg);
+        const int cfirst = sg * p.segw, nw = min(p.segw, p.XW - cfirst);
+        const long long wbase = (long long)zl * p.plane_words + (long long)y * p.WP + cfirst;
+        // lane j holds word j of the segment: region sizes by popcount, per-voxel work below only for the histogram
+        const uint32_t vrow = lane < nw ? valid_mask(p, cfirst + lane) : 0u;
+        const uint32_t srow = lane < nw ? p.S[wbase + lane] & vrow : 0u;
+        const uint32_t erow = (p.E && lane < nw) ? p.E[wbase + lane] & vrow & ~srow : 0u;
+        const uint32_t orow = vrow & ~srow & ~erow;  // outside region: the histogram this kernel keeps in shared memory
+        n_in += __popc(srow); n_ex += __popc(erow); n_out += __popc(orow);
+        const T *sv = (const T *)(mystage + (size_t)stage * stage_bytes) + lane;
+        mbar_wait(mybar + stage, parity);
+        constexpr int BW = 10;
+#pragma unroll
+        for (int jb = 0; jb < WORDS_PER_WARP; jb += BW) {
+            if (jb >= nw) break;  // warp-uniform
+            int lv[BW];
+#pragma unroll
+            for (int k = 0; k < BW; ++k) {
+                if (MODE == MODE_INDEX) lv[k] = (int)sv[(jb + k) * 32];
+                else lv[k] = level_of<LATTICE>(p, (double)sv[(jb + k) * 32]);
+            }
+            // branch-free: every lane does its load / add / store, adding 0 where the voxel is not an outside voxel
+            // (words past the row end hold stale bytes: their level is forced to 0, their increment is 0)
+            uint32_t segbits = 0;
+#pragma unroll
+            for (int k = 0; k < BW; ++k) {
+                const uint32_t ow = __shfl_sync(FULL, orow, (jb + k) & 31), sw = __shfl_sync(FULL, srow, (jb + k) & 31);
+                const uint32_t inc = (ow >> lane) & 1u, seg = (sw >> lane) & 1u;
+                const int l = (inc | seg) ? lv[k] : 0;
+                lv[k] = l;
+                segbits |= seg << k;
+                uint16_t *slot = mine + (l >> 1) * 64 + (l & 1);
+                *slot = (uint16_t)(*slot + inc);
+            }
+            if (__any_sync(FULL, segbits != 0u)) {  // the (tiny) inside region goes through global atomics
+#pragma unroll
+                for (int k = 0; k < BW; ++k)
+                    if (segbits & (1u << k)) atomicAdd(&hin[lv[k]], 1ull);
+            }
+        }
+        __syncwarp();
+        if (pre < nrows) {  // the stage is drained: re-arm it for a later row
+            if (lane == 0) issue(pre, stage);
+            pre += stride;
+        }
+        if (++stage == HIST_STAGES) { stage = 0; parity ^= 1u; }
+        pending += nw;
         if (pending > 60000) flush();
     }
     flush();
@@ -1032,23 +1170,31 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 __global__ void __launch_bounds__(BLOCK) k_scan_levels(const double *__restrict__ data, long long n, unsigned long long *table,
                                                        int cap_mask, int *count, int max_count, int *flags) {
     unsigned long long last = HEMPTY;
-    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) {
-        const double v = data[i] + 0.0;
-        if (!isfinite(v)) { flags[0] = 1; continue; }
-        const unsigned long long key = (unsigned long long)__double_as_longlong(v);
-        if (key == last) continue;
-        last = key;
-        unsigned int h = (unsigned int)mix64(key) & cap_mask;
-        while (true) {
-            const unsigned long long cur = table[h];
-            if (cur == key) break;
-            if (cur == HEMPTY) {
-                if (*(volatile int *)count >= max_count) { flags[1] = 1; break; }
-                const unsigned long long old = atomicCAS(&table[h], HEMPTY, key);
-                if (old == HEMPTY) { atomicAdd(count, 1); break; }
-                if (old == key) break;
+    constexpr int U = 8;  // loads in flight per thread (the hash probe below is a dependent chain)
+    const long long nth = (long long)gridDim.x * BLOCK;
+    for (long long i0 = (long long)blockIdx.x * BLOCK + threadIdx.x; i0 < n; i0 += nth * U) {
+        double vs[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) vs[k] = data[min(i0 + k * nth, n - 1)];  // clamped: a repeat of the last voxel is harmless
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const double v = vs[k] + 0.0;
+            if (!isfinite(v)) { flags[0] = 1; continue; }
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+            if (key == last) continue;
+            last = key;
+            unsigned int h = (unsigned int)mix64(key) & cap_mask;
+            while (true) {
+                const unsigned long long cur = table[h];
+                if (cur == key) break;
+                if (cur == HEMPTY) {
+                    if (*(volatile int *)count >= max_count) { flags[1] = 1; break; }
+                    const unsigned long long old = atomicCAS(&table[h], HEMPTY, key);
+                    if (old == HEMPTY) { atomicAdd(count, 1); break; }
+                    if (old == key) break;
+                }
+                h = (h + 1) & cap_mask;
             }
-            h = (h + 1) & cap_mask;
         }
     }
 }

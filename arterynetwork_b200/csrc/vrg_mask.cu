@@ -1,0 +1,433 @@
+// Vessel-mask construction on the device: the step before the VRG path.
+// Reference: Code/generateVesselVolume.py (GVV:line)
+//   GVV:188-192  two cut-offs relative to the range of the vesselness volume, the first one applied only to voxels within
+//                `edge_distance` (10) of the brain-mask boundary (EDT of the brain mask, GVV:183)
+//   GVV:195-200  binarise, label the 26-connected components (skimage.measure.label, connectivity=3, GVV:126),
+//                drop components of at most `min_size` (150) voxels
+//   GVV:216      the result is saved as a uint8 mask
+// and labelVolume (GVV:108-136): labelled volume + (label, size) list, components numbered in raster order.
+//
+// Connected components: lock-free union-find over voxel indices (roots = smallest index of the component, so the
+// raster-order numbering of skimage / SciPy falls out of a prefix sum over the roots).  Voxels of one x-run start out
+// pointing at the run's first voxel (a warp scan per row), so only links between rows and planes need unions.
+#include "../../include/vrg_b200.h"
+
+#include "vrg_scratch.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+int vrg_edt_squared_device_internal(const uint8_t *d_mask, const int64_t *shape, int *sq_out, cudaStream_t stream);
+void vrg_set_error_internal(const char *msg);  // vrg_b200.cu: text behind vrg_last_error()
+
+namespace {
+
+constexpr unsigned FULLMASK = 0xFFFFFFFFu;
+constexpr int GRID = 148 * 8;
+
+// ---- range of the vesselness volume (GVV:187): per-block partial minima / maxima, folded on the host ---------------
+__global__ void __launch_bounds__(256) k_minmax(const double *__restrict__ v, long long n, double *partial) {
+    double lo = INFINITY, hi = -INFINITY;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n; p += (long long)gridDim.x * 256) {
+        const double x = v[p];
+        lo = fmin(lo, x); hi = fmax(hi, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(FULLMASK, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(FULLMASK, hi, o));
+    }
+    __shared__ double s_lo[8], s_hi[8];
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { lo = fmin(lo, s_lo[i]); hi = fmax(hi, s_hi[i]); }
+        partial[2 * blockIdx.x] = lo; partial[2 * blockIdx.x + 1] = hi;
+    }
+}
+
+// ---- GVV:189-195: the two cut-offs and the binarisation, one pass ----------------------------------------------------
+// A voxel survives iff it is not (near the brain boundary and <= t_edge), is > t_all, and is non-zero.
+__global__ void __launch_bounds__(256) k_rule(const double *__restrict__ v, const int *__restrict__ edt_sq, long long n,
+                                              double edge_distance, double t_edge, double t_all, uint8_t *__restrict__ out) {
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n; p += (long long)gridDim.x * 256) {
+        const double x = v[p];
+        const bool near_edge = sqrt((double)edt_sq[p]) <= edge_distance;
+        const bool zeroed = (near_edge && x <= t_edge) || x <= t_all;
+        out[p] = (!zeroed && x != 0.0) ? 1 : 0;
+    }
+}
+
+// ---- connected components ------------------------------------------------------------------------------------------------
+// parent[p] = first voxel of p's x-run (foreground) or -1 (background): one warp per row, running maximum of the
+// positions of background voxels
+__global__ void __launch_bounds__(256) k_cc_init(const uint8_t *__restrict__ fg, int *__restrict__ parent, long long nrows, int X) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * 8;
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+        const uint8_t *row = fg + r * X;
+        int carry = -1;
+        for (int x0 = 0; x0 < X; x0 += 32) {
+            const int x = x0 + lane;
+            const bool f = x < X && row[x] != 0;
+            int v = (x < X && !f) ? x : -1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULLMASK, v, o);
+                if (lane >= o) v = max(v, t);
+            }
+            v = max(v, carry);
+            carry = __shfl_sync(FULLMASK, v, 31);
+            if (x < X) parent[r * X + x] = f ? (int)(r * X + v + 1) : -1;
+        }
+    }
+}
+
+__device__ __forceinline__ int cc_find(int *parent, int a) {
+    while (true) {
+        const int pa = parent[a];
+        if (pa == a) return a;
+        const int ga = parent[pa];
+        if (ga != pa) parent[a] = ga;  // path halving (a benign race: any ancestor is a valid parent)
+        a = ga;
+    }
+}
+__device__ __forceinline__ void cc_union(int *parent, int a, int b) {
+    while (true) {
+        a = cc_find(parent, a); b = cc_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }  // the larger root is hung under the smaller one
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// links to the previous row / plane: for each of the 4 earlier neighbour rows (dz,dy) in {(0,-1),(-1,-1),(-1,0),(-1,+1)},
+// x-1, x, x+1; when the voxel straight across is foreground it already joins its own neighbours, so the diagonals are
+// skipped.  Two x-runs that touch need one union, not one per touching voxel pair: a pair is linked only if p is the
+// first voxel of its run or the neighbour is the first voxel of its run (every touching pair of runs has such a pair).
+// Four voxels per thread and load: background words (almost all of a vessel mask) cost one 32-bit load.
+__device__ __forceinline__ void cc_merge_voxel(const uint8_t *__restrict__ fg, int *parent, long long p, int Y, int X) {
+    const int x = (int)(p % X), y = (int)((p / X) % Y), z = (int)(p / ((long long)X * Y));
+    const bool pstart = x == 0 || !fg[p - 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dz = k == 0 ? 0 : -1, dy = k == 0 ? -1 : k - 2;
+        const int zz = z + dz, yy = y + dy;
+        if (zz < 0 || yy < 0 || yy >= Y) continue;
+        const long long q = ((long long)zz * Y + yy) * X + x;
+        const bool ql = x > 0 && fg[q - 1];
+        if (fg[q]) {
+            if (pstart || !ql) cc_union(parent, (int)p, (int)q);
+        } else {
+            if (ql && (pstart || x < 2 || !fg[q - 2])) cc_union(parent, (int)p, (int)(q - 1));
+            if (x + 1 < X && fg[q + 1]) cc_union(parent, (int)p, (int)(q + 1));  // q + 1 starts its run (q is background)
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_cc_merge(const uint8_t *__restrict__ fg, int *parent, int Z, int Y, int X) {
+    const long long n = (long long)Z * Y * X, ngroups = (n + 3) / 4;
+    const bool aligned = (((uintptr_t)fg) & 3) == 0;
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (long long)gridDim.x * 256) {
+        const long long p0 = g * 4;
+        uint32_t w;
+        if (aligned && p0 + 3 < n) w = *(const uint32_t *)(fg + p0);
+        else {
+            w = 0;
+            for (int b = 0; b < 4; ++b)
+                if (p0 + b < n) w |= (uint32_t)fg[p0 + b] << (8 * b);
+        }
+        if (w == 0u) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if ((w >> (8 * b)) & 0xFFu) cc_merge_voxel(fg, parent, p0 + b, Y, X);
+    }
+}
+
+// parent[p] = root; component sizes at the roots (one atomic per group of equal roots in a warp).
+// The walk to the root is read-only here: with path halving, another thread's late write of a stale grandparent
+// could land on parent[p] after p's own thread stored the root, and the consumers below index by parent[p].
+__global__ void __launch_bounds__(256) k_cc_flatten_count(int *parent, int *__restrict__ size, long long n) {
+    const int lane = threadIdx.x & 31;
+    const long long nround = (n + 255) / 256 * 256;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < nround; p += (long long)gridDim.x * 256) {
+        int root = -1;
+        if (p < n && parent[p] >= 0) {
+            root = (int)p;
+            for (int up = parent[root]; up != root; up = parent[root]) root = up;
+            parent[p] = root;
+        }
+        const unsigned peers = __match_any_sync(FULLMASK, root);
+        if (root >= 0 && lane == __ffs(peers) - 1) atomicAdd(&size[root], __popc(peers));
+    }
+}
+
+// keep[p] = foreground and component size > min_size (GVV:198-200); counts the kept voxels and components
+__global__ void __launch_bounds__(256) k_cc_filter(const int *__restrict__ parent, const int *__restrict__ size, long long n,
+                                                   long long min_size, uint8_t *__restrict__ out, unsigned long long *counts) {
+    unsigned long long kept = 0, comps = 0;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n; p += (long long)gridDim.x * 256) {
+        const int root = parent[p];
+        const bool keep = root >= 0 && size[root] > min_size;
+        out[p] = keep ? 1 : 0;
+        kept += keep;
+        comps += keep && root == p;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kept += __shfl_xor_sync(FULLMASK, kept, o);
+        comps += __shfl_xor_sync(FULLMASK, comps, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (kept) atomicAdd(&counts[0], kept);
+        if (comps) atomicAdd(&counts[1], comps);
+    }
+}
+
+// raster-order numbering: roots per chunk of 1024 voxels -> exclusive scan over chunks -> labels
+constexpr int CHUNK = 1024;
+__global__ void __launch_bounds__(256) k_cc_chunk_roots(const int *__restrict__ parent, long long n, int *__restrict__ chunk_count) {
+    const long long c0 = (long long)blockIdx.x;
+    for (long long c = c0; c * CHUNK < n; c += gridDim.x) {
+        int cnt = 0;
+        for (int i = threadIdx.x; i < CHUNK; i += 256) {
+            const long long p = c * CHUNK + i;
+            cnt += p < n && parent[p] == p;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, o);
+        __shared__ int s[8];
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) chunk_count[c] = s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7];
+        __syncthreads();
+    }
+}
+// one block: chunk_count -> exclusive prefix sums in place; total -> *total
+__global__ void __launch_bounds__(1024) k_cc_scan_chunks(int *chunk_count, long long nchunks, int *total) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < nchunks; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const int v = i < nchunks ? chunk_count[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULLMASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULLMASK, w, o);
+                if (lane >= o) w += t;
+            }
+            s_warp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int before = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
+        if (i < nchunks) chunk_count[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+// number[root] = 1 + rank of the root in raster order (written into `size`, which is no longer needed at the roots'
+// slots once `sizes_by_label` has been filled), then labels[p] = number[root(p)]
+__global__ void __launch_bounds__(256) k_cc_number_roots(const int *__restrict__ parent, long long n, const int *__restrict__ chunk_base,
+                                                         int *__restrict__ size, int *__restrict__ sizes_by_label) {
+    const long long c0 = (long long)blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int s_w[8];
+    for (long long c = c0; c * CHUNK < n; c += gridDim.x) {
+        int running = chunk_base[c];
+        for (int i0 = 0; i0 < CHUNK; i0 += 256) {  // 256 voxels at a time, in order
+            const long long p = c * CHUNK + i0 + threadIdx.x;
+            const bool is_root = p < n && parent[p] == p;
+            const unsigned b = __ballot_sync(FULLMASK, is_root);
+            if (lane == 0) s_w[warp] = __popc(b);
+            __syncthreads();
+            int before = running;
+            for (int w = 0; w < warp; ++w) before += s_w[w];
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += s_w[w];
+            if (is_root) {
+                const int number = before + __popc(b & ((1u << lane) - 1u)) + 1;
+                sizes_by_label[number - 1] = size[p];
+                size[p] = number;
+            }
+            running += tot;
+            __syncthreads();
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_cc_labels(const int *__restrict__ parent, const int *__restrict__ number, long long n,
+                                                   int *__restrict__ labels) {
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n; p += (long long)gridDim.x * 256) {
+        const int root = parent[p];
+        labels[p] = root >= 0 ? number[root] : 0;
+    }
+}
+
+using DevBuf = vrg_scratch::Buf;
+
+int status_of(cudaError_t e) {
+    if (e == cudaSuccess) return VRG_OK;
+    vrg_set_error_internal(cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA;
+}
+int bad_args(const char *what) {
+    vrg_set_error_internal(what);
+    return VRG_ERR_ARG;
+}
+const char *const SHAPE_MSG = "null buffer or bad shape (3 axes of 1..16384, fewer than 2^31 voxels)";
+
+bool shape_ok(const int64_t *shape) {
+    if (!shape || shape[0] <= 0 || shape[1] <= 0 || shape[2] <= 0) return false;
+    if (shape[0] > 16384 || shape[1] > 16384 || shape[2] > 16384) return false;
+    return (double)shape[0] * (double)shape[1] * (double)shape[2] < 2147483647.0;  // voxel indices are int32
+}
+
+// parent / size of the 26-connected components of a device uint8 volume (non-zero = foreground)
+int components_device(const uint8_t *d_fg, const int64_t *shape, int *d_parent, int *d_size, cudaStream_t st) {
+    const long long Z = shape[0], Y = shape[1], X = shape[2], n = Z * Y * X;
+    cudaMemsetAsync(d_size, 0, n * sizeof(int), st);
+    k_cc_init<<<GRID, 256, 0, st>>>(d_fg, d_parent, Z * Y, (int)X);
+    k_cc_merge<<<GRID, 256, 0, st>>>(d_fg, d_parent, (int)Z, (int)Y, (int)X);
+    k_cc_flatten_count<<<GRID, 256, 0, st>>>(d_parent, d_size, n);
+    return status_of(cudaGetLastError());
+}
+
+}  // namespace
+
+// labelVolume, GVV:108-136.  binary: device uint8 (non-zero = foreground); labels_out: device int32 (0 = background,
+// components 1..K in raster order of their first voxel); sizes_out (host, optional): voxel count of component k at [k-1].
+extern "C" int vrg_label_components_device(int device, const uint8_t *binary_dev, const int64_t *shape, int32_t *labels_dev,
+                                           int64_t *n_components, int64_t *sizes_out, int64_t sizes_cap, void *cuda_stream) {
+    if (!binary_dev || !labels_dev || !shape_ok(shape)) return bad_args(SHAPE_MSG);
+    if (cudaSetDevice(device) != cudaSuccess) return VRG_ERR_CUDA;
+    vrg_scratch::pool_setup(device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const long long n = (long long)shape[0] * shape[1] * shape[2], nchunks = (n + CHUNK - 1) / CHUNK;
+    DevBuf parent, size, chunks, total, bylabel;
+    cudaError_t e = parent.alloc(n * sizeof(int), st);
+    if (e == cudaSuccess) e = size.alloc(n * sizeof(int), st);
+    if (e == cudaSuccess) e = chunks.alloc(nchunks * sizeof(int), st);
+    if (e == cudaSuccess) e = total.alloc(sizeof(int), st);
+    if (e != cudaSuccess) return status_of(e);
+    int rc = components_device(binary_dev, shape, parent.as<int>(), size.as<int>(), st);
+    if (rc != VRG_OK) return rc;
+    k_cc_chunk_roots<<<GRID, 256, 0, st>>>(parent.as<int>(), n, chunks.as<int>());
+    k_cc_scan_chunks<<<1, 1024, 0, st>>>(chunks.as<int>(), nchunks, total.as<int>());
+    int K = 0;
+    e = cudaMemcpyAsync(&K, total.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = bylabel.alloc((size_t)K * sizeof(int), st);
+    if (e != cudaSuccess) return status_of(e);
+    k_cc_number_roots<<<GRID, 256, 0, st>>>(parent.as<int>(), n, chunks.as<int>(), size.as<int>(), bylabel.as<int>());
+    k_cc_labels<<<GRID, 256, 0, st>>>(parent.as<int>(), size.as<int>(), n, labels_dev);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && sizes_out && sizes_cap > 0 && K > 0) {
+        std::vector<int> tmp((size_t)std::min<int64_t>(K, sizes_cap));
+        e = cudaMemcpyAsync(tmp.data(), bylabel.p, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        for (size_t i = 0; i < tmp.size(); ++i) sizes_out[i] = tmp[i];
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (n_components) *n_components = K;
+    return status_of(e);
+}
+
+extern "C" int vrg_label_components(int device, const uint8_t *binary_host, const int64_t *shape, int32_t *labels_host,
+                                    int64_t *n_components, int64_t *sizes_out, int64_t sizes_cap) {
+    if (!binary_host || !labels_host || !shape_ok(shape)) return bad_args(SHAPE_MSG);
+    if (cudaSetDevice(device) != cudaSuccess) return VRG_ERR_CUDA;
+    vrg_scratch::pool_setup(device);
+    const size_t n = (size_t)shape[0] * shape[1] * shape[2];
+    DevBuf b, l;
+    cudaError_t e = b.alloc(n, nullptr);
+    if (e == cudaSuccess) e = l.alloc(n * sizeof(int32_t), nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(b.p, binary_host, n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return status_of(e);
+    const int rc = vrg_label_components_device(device, b.as<uint8_t>(), shape, l.as<int32_t>(), n_components, sizes_out, sizes_cap, nullptr);
+    if (rc != VRG_OK) return rc;
+    return status_of(cudaMemcpy(labels_host, l.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+}
+
+// GVV:187-200 on device buffers.  vesselness: float64; brain_mask: uint8 (non-zero = brain); mask_out: uint8 0/1.
+// info_out (optional, host): [0] kept voxels, [1] kept components, then the two cut-offs as doubles via thresholds_out.
+extern "C" int vrg_vessel_mask_device(int device, const double *vesselness_dev, const uint8_t *brain_mask_dev, const int64_t *shape,
+                                      double edge_distance, double edge_fraction, double fraction, int64_t min_size,
+                                      uint8_t *mask_out_dev, int64_t *info_out, double *thresholds_out, void *cuda_stream) {
+    if (!vesselness_dev || !brain_mask_dev || !mask_out_dev || !shape_ok(shape)) return bad_args(SHAPE_MSG);
+    if (cudaSetDevice(device) != cudaSuccess) return VRG_ERR_CUDA;
+    vrg_scratch::pool_setup(device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const long long n = (long long)shape[0] * shape[1] * shape[2];
+    DevBuf sq, partial, parent, size, counts, binary;
+    cudaError_t e = sq.alloc(n * sizeof(int), st);
+    if (e == cudaSuccess) e = partial.alloc(2 * GRID * sizeof(double), st);
+    if (e == cudaSuccess) e = counts.alloc(2 * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = binary.alloc(n, st);
+    if (e != cudaSuccess) return status_of(e);
+    // range of the vesselness volume, GVV:187
+    k_minmax<<<GRID, 256, 0, st>>>(vesselness_dev, n, partial.as<double>());
+    std::vector<double> hp(2 * GRID);
+    e = cudaMemcpyAsync(hp.data(), partial.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return status_of(e);
+    double lo = hp[0], hi = hp[1];
+    for (int i = 1; i < GRID; ++i) { lo = std::fmin(lo, hp[2 * i]); hi = std::fmax(hi, hp[2 * i + 1]); }
+    if (!std::isfinite(lo) || !std::isfinite(hi)) { vrg_set_error_internal("vesselness volume holds NaN or Inf"); return VRG_ERR_NONFINITE; }
+    const double t_edge = lo + edge_fraction * (hi - lo), t_all = lo + fraction * (hi - lo);  // GVV:189,191, same expression
+    if (thresholds_out) { thresholds_out[0] = t_edge; thresholds_out[1] = t_all; }
+    // distance to the brain-mask boundary, GVV:183 (squared, exact)
+    int rc = vrg_edt_squared_device_internal(brain_mask_dev, shape, sq.as<int>(), st);
+    if (rc != VRG_OK) return rc;
+    k_rule<<<GRID, 256, 0, st>>>(vesselness_dev, sq.as<int>(), n, edge_distance, t_edge, t_all, binary.as<uint8_t>());
+    sq.release();  // stream-ordered: the block is reusable once k_rule has run
+    e = parent.alloc(n * sizeof(int), st);
+    if (e == cudaSuccess) e = size.alloc(n * sizeof(int), st);
+    if (e != cudaSuccess) return status_of(e);
+    rc = components_device(binary.as<uint8_t>(), shape, parent.as<int>(), size.as<int>(), st);
+    if (rc != VRG_OK) return rc;
+    cudaMemsetAsync(counts.p, 0, 2 * sizeof(unsigned long long), st);
+    k_cc_filter<<<GRID, 256, 0, st>>>(parent.as<int>(), size.as<int>(), n, min_size, mask_out_dev, counts.as<unsigned long long>());
+    unsigned long long hc[2] = {0, 0};
+    e = cudaMemcpyAsync(hc, counts.p, sizeof hc, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (info_out) { info_out[0] = (int64_t)hc[0]; info_out[1] = (int64_t)hc[1]; }
+    return status_of(e);
+}
+
+extern "C" int vrg_vessel_mask(int device, const double *vesselness_host, const uint8_t *brain_mask_host, const int64_t *shape,
+                               double edge_distance, double edge_fraction, double fraction, int64_t min_size,
+                               uint8_t *mask_out_host, int64_t *info_out, double *thresholds_out) {
+    if (!vesselness_host || !brain_mask_host || !mask_out_host || !shape_ok(shape)) return bad_args(SHAPE_MSG);
+    if (cudaSetDevice(device) != cudaSuccess) return VRG_ERR_CUDA;
+    vrg_scratch::pool_setup(device);
+    const size_t n = (size_t)shape[0] * shape[1] * shape[2];
+    DevBuf v, b, o;
+    cudaError_t e = v.alloc(n * sizeof(double), nullptr);
+    if (e == cudaSuccess) e = b.alloc(n, nullptr);
+    if (e == cudaSuccess) e = o.alloc(n, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(v.p, vesselness_host, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(b.p, brain_mask_host, n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return status_of(e);
+    const int rc = vrg_vessel_mask_device(device, v.as<double>(), b.as<uint8_t>(), shape, edge_distance, edge_fraction, fraction,
+                                          min_size, o.as<uint8_t>(), info_out, thresholds_out, nullptr);
+    if (rc != VRG_OK) return rc;
+    return status_of(cudaMemcpy(mask_out_host, o.p, n, cudaMemcpyDeviceToHost));
+}

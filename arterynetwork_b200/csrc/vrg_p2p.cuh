@@ -21,7 +21,6 @@ namespace vrg {
 constexpr int P2P_MAX_WORLD = 8;
 constexpr int P2P_KINDS = 3;  // F, C, E
 enum { PK_F = 0, PK_C = 1, PK_E = 2 };
-enum { C_EPOCH = 9, C_PEER_TIMEOUT = 10 };                  // extra ctrl words
 constexpr long long EXIT_PEER_TIMEOUT = 99;
 constexpr long long P2P_SPIN_LIMIT = 40000000000ll;          // ~20 s of SM clocks: a dead peer must not hang the box
 
@@ -39,7 +38,7 @@ struct P2P {
     int slot_words;                                  // int64 words per statistics slot (capacity, >= 2L + ST_EXTRA)
     unsigned long long *flags;                       // my flag words
     long long *slots;                                // my mailbox: [2 parities][world][slot_words]
-    uint32_t *recv;                                  // my halo receive buffer: [P2P_KINDS][2 sides][HALO][plane_words]
+    uint32_t *recv;                                  // my halo receive buffer: [2 parities][P2P_KINDS][2 sides][HALO][plane_words]
     unsigned long long *peer_flags[P2P_MAX_WORLD];   // every rank's flag words (mine included)
     long long *peer_slots[P2P_MAX_WORLD];
     uint32_t *peer_recv[2];                          // lower / upper neighbour's receive buffer (nullptr at the ends)
@@ -81,10 +80,21 @@ __device__ __forceinline__ bool p2p_last_block(unsigned long long *counter) {
 
 // ---- halo --------------------------------------------------------------------------------------------------------
 // kinds: bit mask over PK_*.  `running_only`: loop exchanges obey the run status; the one after init does not.
+// Loop exchanges take their sequence number and their go / no-go from the snapshot k_cancel left in the control block
+// (C_HALO_SEQ, C_HALO_GO): the halo exchange may run on a second stream beside the statistics exchange, whose
+// bookkeeping moves C_SWEEPS / C_STATUS on.  The receive buffer is double-buffered by sequence parity, because a
+// neighbour that is one iteration ahead may push its next planes while this rank still unpacks the current ones.
+__device__ __forceinline__ bool p2p_halo_seq(const Params &p, int seq_zero, unsigned long long &seq) {
+    if (seq_zero) { seq = (unsigned long long)p.ctrl[C_EPOCH] << 32; return true; }
+    seq = (unsigned long long)p.ctrl[C_HALO_SEQ];
+    return p.ctrl[C_HALO_GO] != 0;
+}
+
 __global__ void __launch_bounds__(BLOCK) k_p2p_push_halo(Params p, P2P q, int kinds, int seq_zero) {
-    if (!seq_zero && (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY])) return;
-    const unsigned long long seq = seq_zero ? ((unsigned long long)p.ctrl[C_EPOCH] << 32) : p2p_seq(p);
+    unsigned long long seq;
+    if (!p2p_halo_seq(p, seq_zero, seq)) return;
     const long long n = (long long)HALO * p.plane_words;
+    const long long par_off = (long long)(seq & 1ull) * P2P_KINDS * 2 * n;
     const long long tid = (long long)blockIdx.x * BLOCK + threadIdx.x, nth = (long long)gridDim.x * BLOCK;
     for (int kind = 0; kind < P2P_KINDS; ++kind) {
         if (!(kinds & (1 << kind))) continue;
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_push_halo(Params p, P2P q, int ki
             uint32_t *dst = q.peer_recv[side];
             if (dst == nullptr) continue;
             // my first own planes land in the lower neighbour's "from above" region (its side 1) and vice versa
-            dst += ((long long)kind * 2 + (side ^ 1)) * n;
+            dst += par_off + ((long long)kind * 2 + (side ^ 1)) * n;
             const uint32_t *src = plane + (long long)(side == 0 ? p.own_lo : p.own_hi - HALO) * p.plane_words;
             for (long long i = tid; i < n; i += nth) dst[i] = src[i];
         }
@@ -111,8 +121,8 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_push_halo(Params p, P2P q, int ki
 // `flip`: the unpacked executed-flip words are applied to the halo copy of the segmented plane in the same pass
 // (what k_flip_halo does on the collective path).
 __global__ void __launch_bounds__(BLOCK) k_p2p_wait_unpack_halo(Params p, P2P q, int kinds, int seq_zero, int flip) {
-    if (!seq_zero && (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY])) return;
-    const unsigned long long seq = seq_zero ? ((unsigned long long)p.ctrl[C_EPOCH] << 32) : p2p_seq(p);
+    unsigned long long seq;
+    if (!p2p_halo_seq(p, seq_zero, seq)) return;
     __shared__ int ok;
     if (threadIdx.x == 0) {
         ok = 1;
@@ -127,6 +137,7 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_wait_unpack_halo(Params p, P2P q,
     __syncthreads();
     if (!ok) return;
     const long long n = (long long)HALO * p.plane_words;
+    const long long par_off = (long long)(seq & 1ull) * P2P_KINDS * 2 * n;
     const long long tid = (long long)blockIdx.x * BLOCK + threadIdx.x, nth = (long long)gridDim.x * BLOCK;
     for (int kind = 0; kind < P2P_KINDS; ++kind) {
         if (!(kinds & (1 << kind))) continue;
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_wait_unpack_halo(Params p, P2P q,
         if (plane == nullptr) continue;
         for (int side = 0; side < 2; ++side) {  // side 0: data from the lower neighbour -> my lower halo planes
             if (q.peer_recv[side] == nullptr) continue;
-            const uint32_t *src = q.recv + ((long long)kind * 2 + side) * n;
+            const uint32_t *src = q.recv + par_off + ((long long)kind * 2 + side) * n;
             uint32_t *dst = plane + (long long)(side == 0 ? p.own_lo - HALO : p.own_hi) * p.plane_words;
             if (kind == PK_F && flip) {
                 uint32_t *sdst = p.S + (long long)(side == 0 ? p.own_lo - HALO : p.own_hi) * p.plane_words;

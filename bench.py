@@ -114,12 +114,16 @@ def device_phantom(shape, seed, z0, nz, device):
 
 
 def cpu_sample(shape, seed):
-    """Bounded CPU sample of the workload: its first CPU_SAMPLE_PLANES planes, as its own volume."""
-    from arterynetwork_b200.phantom import make_phantom
-    nz = min(CPU_SAMPLE_PLANES, shape[0], max(8, int(1.0e8 // (shape[1] * shape[2]))))  # bounded: about 1e8 voxels
-    data, vm, _ = make_phantom(shape, seed=seed, z0=0, nz=nz)
-    return data, vm, "planes [0,%d) of the %dx%dx%d phantom as a %dx%dx%d volume, run to convergence" % (
-        nz, shape[2], shape[1], shape[0], shape[2], shape[1], nz)
+    """Bounded CPU sample of the workload: a window of its planes (about 1e8 voxels at most) that holds seeds, as its
+    own volume.  Returns (data, value_map, description, z0)."""
+    from arterynetwork_b200.phantom import forest_segments, make_phantom
+    nz = min(CPU_SAMPLE_PLANES, shape[0], max(8, int(1.0e8 // (shape[1] * shape[2]))))
+    _, roots = forest_segments(shape, seed=seed)
+    rz = int(roots[:, 0].min())
+    z0 = 0 if rz + 2 <= nz else max(0, min(shape[0] - nz, rz - nz // 2))  # planes [0, nz) unless they hold no seed
+    data, vm, _ = make_phantom(shape, seed=seed, z0=z0, nz=nz)
+    return data, vm, "planes [%d,%d) of the %dx%dx%d phantom as a %dx%dx%d volume, run to convergence" % (
+        z0, z0 + nz, shape[2], shape[1], shape[0], shape[2], shape[1], nz), z0
 
 
 def time_cpu_port(data, vm, threads):
@@ -136,7 +140,7 @@ def run_reference_arm(args):
         return
     shape = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    data, vm, sample = cpu_sample(shape, args.seed)
+    data, vm, sample, _ = cpu_sample(shape, args.seed)
     for _ in range(args.warmup):
         time_cpu_port(data, vm, threads)
     t0 = time.perf_counter()
@@ -281,11 +285,11 @@ def run_single(args):
                 del out
     prim = results[args.intensity]
     # CPU baseline (rank 0, N=1): the oracle port on a bounded sample of the same phantom
-    data_s, vm_s, sample = cpu_sample(shape, args.seed)
+    data_s, vm_s, sample, z0_s = cpu_sample(shape, args.seed)
     threads = os.cpu_count() or 1
     cpu_val, cpu_dt, cpu_it = time_cpu_port(data_s, vm_s, threads)
     # the device generator and the NumPy generator must agree bit for bit on the sample
-    gen_equal = bool(np.array_equal(d_data[: data_s.shape[0]].cpu().numpy(), data_s))
+    gen_equal = bool(np.array_equal(d_data[z0_s: z0_s + data_s.shape[0]].cpu().numpy(), data_s))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_%s_%s.json" % (args.workload, args.intensity))
     if os.path.exists(tpath):

@@ -171,6 +171,41 @@ int vrg_phantom_device(int device, const int64_t *shape, int64_t z0, int64_t nz,
                        int64_t sigma_k, int64_t exclude_below_k, int use_exclude, double *data_dev,
                        uint8_t *value_map_dev);
 
+/* ---- the array operations on either side of the path -------------------------
+ * Volumes are (Z, Y, X) C order; each axis <= 16384.  The *_device variants take device pointers and a cudaStream_t
+ * (as void*, may be NULL) and synchronise that stream before returning. */
+
+/* scipy.ndimage.distance_transform_edt(mask), default arguments -- Code/manualCorrectionGUI.py:248 (vessel radii from the
+ * VRG output mask), Code/generateVesselVolume.py:183 (distance to the brain-mask boundary).  mask: uint8, non-zero =
+ * foreground; dist: float64 Euclidean distance of every foreground voxel to the nearest zero voxel (0 on the background).
+ * VRG_ERR_ARG when the mask has no zero voxel. */
+int vrg_edt(int device, const uint8_t *mask_host, const int64_t *shape, double *dist_host);
+int vrg_edt_device(int device, const uint8_t *mask_dev, const int64_t *shape, double *dist_dev, void *cuda_stream);
+/* these entry points take their scratch memory from the device's stream-ordered pool and keep it cached between calls;
+ * this hands it back to the driver */
+int vrg_release_scratch(int device);
+
+/* labelVolume, Code/generateVesselVolume.py:108-136 = skimage.measure.label(volume, return_num=True, connectivity=3):
+ * 26-connected components of the non-zero voxels, numbered 1..K in raster order of each component's first voxel,
+ * int32 labels (0 = background); sizes_out (optional, host) receives the voxel counts of components 1..min(K, cap).
+ * The volume must hold fewer than 2^31 voxels. */
+int vrg_label_components(int device, const uint8_t *binary_host, const int64_t *shape, int32_t *labels_host,
+                         int64_t *n_components, int64_t *sizes_out, int64_t sizes_cap);
+int vrg_label_components_device(int device, const uint8_t *binary_dev, const int64_t *shape, int32_t *labels_dev,
+                                int64_t *n_components, int64_t *sizes_out, int64_t sizes_cap, void *cuda_stream);
+
+/* vesselness volume -> vessel mask, Code/generateVesselVolume.py:183-200,216: with lo/hi the range of the vesselness
+ * volume, voxels within edge_distance (10) of the brain-mask boundary and <= lo + edge_fraction (0.8) * (hi - lo) are
+ * zeroed, then voxels <= lo + fraction (0.7) * (hi - lo); the non-zero rest is binarised and its 26-connected components
+ * of at most min_size (150) voxels are removed.  vesselness: float64; brain_mask: uint8; mask_out: uint8 0/1.
+ * info_out (optional): [0] voxels kept, [1] components kept.  thresholds_out (optional): the two cut-offs. */
+int vrg_vessel_mask(int device, const double *vesselness_host, const uint8_t *brain_mask_host, const int64_t *shape,
+                    double edge_distance, double edge_fraction, double fraction, int64_t min_size,
+                    uint8_t *mask_out_host, int64_t *info_out, double *thresholds_out);
+int vrg_vessel_mask_device(int device, const double *vesselness_dev, const uint8_t *brain_mask_dev, const int64_t *shape,
+                           double edge_distance, double edge_fraction, double fraction, int64_t min_size,
+                           uint8_t *mask_out_dev, int64_t *info_out, double *thresholds_out, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
