@@ -17,6 +17,8 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 void vrg_set_error_internal(const char *msg);  // vrg_b200.cu: text behind vrg_last_error()
 
 namespace {
@@ -68,50 +70,71 @@ __global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ ma
 }
 
 // pass y / z: lower envelope of the parabolas (u - i)^2 + f(i) along one axis.  Thread = one line; `line` enumerates
-// (outer, x) so that threads of a warp sit on neighbouring x.  s / t: the envelope's stack (parabola apex, start of its
-// reign), stored like the volume (element q of a line at q * stride) so that they coalesce as well.
+// (outer, x) so that threads of a warp sit on neighbouring x.  s / t / g: the envelope's stack (parabola apex, start of its
+// reign, its height f(apex)), stored like the volume (element q of a line at q * stride) so that they coalesce as well.
+// A line is one dependent chain, so both scans keep memory latency off it: the forward scan fetches its inputs eight
+// steps ahead, the backward scan (pure pops: entries below the top no longer change) fetches four stack entries at once.
 __global__ void __launch_bounds__(128) k_edt_lines(const int *__restrict__ in, int *__restrict__ out, short *__restrict__ s,
-                                                   int *__restrict__ t, long long nlines, int len, long long stride,
-                                                   int X, long long outer_stride) {
+                                                   int *__restrict__ t, int *__restrict__ g, long long nlines, int len,
+                                                   long long stride, int X, long long outer_stride) {
     for (long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x; line < nlines; line += (long long)gridDim.x * blockDim.x) {
         const long long base = (line / X) * outer_stride + (line % X);
         const int *f = in + base;
         short *ss = s + base;
-        int *tt = t + base;
+        int *tt = t + base, *gg = g + base;
         int *o = out + base;
         // forward scan.  Registers hold the top of the stack (sq, tq, fq = f(sq)).
         int q = 0, sq = 0, tq = 0;
         long long fq = f[0];
-        ss[0] = 0; tt[0] = 0;
-        for (int u = 1; u < len; ++u) {
-            const long long fu = f[(long long)u * stride];
-            if (fu >= EDT_INF) continue;  // an infinite parabola never reaches the envelope
-            bool pushed = false;
-            while (true) {
-                // F(tq, sq) > F(tq, u) ?  the new parabola is already lower where the top one starts: pop
-                const long long a = (long long)(tq - sq) * (tq - sq) + fq, b = (long long)(tq - u) * (tq - u) + fu;
-                if (a <= b) break;
-                if (q == 0) { sq = u; fq = fu; tq = 0; ss[0] = (short)u; pushed = true; break; }
-                --q;
-                sq = ss[(long long)q * stride]; tq = tt[(long long)q * stride];
-                fq = f[(long long)sq * stride];
-            }
-            if (pushed) continue;
-            // first position where parabola u is lower than the top one
-            const long long w = 1 + ((long long)u * u - (long long)sq * sq + fu - fq) / (2LL * (u - sq));
-            if (w < len) {
-                ++q; sq = u; tq = (int)w; fq = fu;
-                ss[(long long)q * stride] = (short)u; tt[(long long)q * stride] = (int)w;
+        ss[0] = 0; tt[0] = 0; gg[0] = (int)fq;
+        constexpr int PF = 8;
+        for (int u0 = 1; u0 < len; u0 += PF) {
+            int fpre[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) fpre[k] = f[(long long)min(u0 + k, len - 1) * stride];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int u = u0 + k;
+                if (u >= len) break;
+                const long long fu = fpre[k];
+                if (fu >= EDT_INF) continue;  // an infinite parabola never reaches the envelope
+                bool replaced = false;
+                while (true) {
+                    // F(tq, sq) > F(tq, u) ?  the new parabola is already lower where the top one starts: pop
+                    const long long a = (long long)(tq - sq) * (tq - sq) + fq, b = (long long)(tq - u) * (tq - u) + fu;
+                    if (a <= b) break;
+                    if (q == 0) { sq = u; fq = fu; tq = 0; ss[0] = (short)u; gg[0] = (int)fu; replaced = true; break; }
+                    --q;
+                    sq = ss[(long long)q * stride]; tq = tt[(long long)q * stride]; fq = gg[(long long)q * stride];
+                }
+                if (replaced) continue;
+                // first position where parabola u is lower than the top one
+                const long long w = 1 + ((long long)u * u - (long long)sq * sq + fu - fq) / (2LL * (u - sq));
+                if (w < len) {
+                    ++q; sq = u; tq = (int)w; fq = fu;
+                    ss[(long long)q * stride] = (short)u; tt[(long long)q * stride] = (int)w; gg[(long long)q * stride] = (int)fu;
+                }
             }
         }
         // backward scan
+        constexpr int PB = 4;
+        int ps[PB], pt[PB], pg[PB], have = 0;  // entries q-1 .. q-have, fetched ahead (ps[0] is the next one to pop)
         for (int u = len - 1; u >= 0; --u) {
             const long long d = (long long)(u - sq) * (u - sq) + fq;
             o[(long long)u * stride] = d >= EDT_INF ? EDT_INF : (int)d;
             if (u == tq && q > 0) {
-                --q;
-                sq = ss[(long long)q * stride]; tq = tt[(long long)q * stride];
-                fq = f[(long long)sq * stride];
+                if (have == 0) {
+#pragma unroll
+                    for (int k = 0; k < PB; ++k) {
+                        const long long e = (long long)max(q - 1 - k, 0) * stride;
+                        ps[k] = ss[e]; pt[k] = tt[e]; pg[k] = gg[e];
+                    }
+                    have = min(PB, q);
+                }
+                --q; --have;
+                sq = ps[0]; tq = pt[0]; fq = pg[0];
+#pragma unroll
+                for (int k = 0; k + 1 < PB; ++k) { ps[k] = ps[k + 1]; pt[k] = pt[k + 1]; pg[k] = pg[k + 1]; }
             }
         }
     }
@@ -133,19 +156,21 @@ int edt_check(const int64_t *shape) {
     return VRG_OK;
 }
 
-// squared distances (int32) of a device mask; scratch = 2 int32 + 1 int16 volume.  sq_out must hold n ints.
+// squared distances (int32) of a device mask; scratch = 3 int32 + 1 int16 volume.  sq_out must hold n ints.
 // Asynchronous on `stream`.
 int edt_squared_device(const uint8_t *d_mask, const int64_t *shape, int *sq_out, cudaStream_t stream) {
     const long long Z = shape[0], Y = shape[1], X = shape[2], n = Z * Y * X;
-    Buf a, t, s;
+    Buf a, t, s, g;
     cudaError_t e = a.alloc(n * sizeof(int), stream);
     if (e == cudaSuccess) e = t.alloc(n * sizeof(int), stream);
+    if (e == cudaSuccess) e = g.alloc(n * sizeof(int), stream);
     if (e == cudaSuccess) e = s.alloc(n * sizeof(short), stream);
     if (e == cudaSuccess) {
         const int grid = 148 * 8;
+        const int gy = (int)std::min<long long>((Z * X + 127) / 128, 148 * 16), gz = (int)std::min<long long>((Y * X + 127) / 128, 148 * 16);
         k_edt_rows<<<grid, 256, 0, stream>>>(d_mask, sq_out, Z * Y, (int)X);                                             // mask -> sq_out
-        k_edt_lines<<<grid, 128, 0, stream>>>(sq_out, a.as<int>(), s.as<short>(), t.as<int>(), Z * X, (int)Y, X, (int)X, X * Y);   // y: sq_out -> a
-        k_edt_lines<<<grid, 128, 0, stream>>>(a.as<int>(), sq_out, s.as<short>(), t.as<int>(), Y * X, (int)Z, X * Y, (int)(X * Y), 0);  // z: a -> sq_out
+        k_edt_lines<<<gy, 128, 0, stream>>>(sq_out, a.as<int>(), s.as<short>(), t.as<int>(), g.as<int>(), Z * X, (int)Y, X, (int)X, X * Y);   // y: sq_out -> a
+        k_edt_lines<<<gz, 128, 0, stream>>>(a.as<int>(), sq_out, s.as<short>(), t.as<int>(), g.as<int>(), Y * X, (int)Z, X * Y, (int)(X * Y), 0);  // z: a -> sq_out
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA;
