@@ -69,11 +69,17 @@ __global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ ma
     }
 }
 
-// pass y / z: lower envelope of the parabolas (u - i)^2 + f(i) along one axis.  Thread = one line; `line` enumerates
-// (outer, x) so that threads of a warp sit on neighbouring x.  s / t / g: the envelope's stack (parabola apex, start of its
-// reign, its height f(apex)), stored like the volume (element q of a line at q * stride) so that they coalesce as well.
-// A line is one dependent chain, so both scans keep memory latency off it: the forward scan fetches its inputs eight
-// steps ahead, the backward scan (pure pops: entries below the top no longer change) fetches four stack entries at once.
+// pass y / z: out(u) = min_i (u - i)^2 + f(i) along one axis: lower envelope of parabolas (Meijster).  Thread = one
+// line; `line` enumerates (outer, x) so that threads of a warp sit on neighbouring x, walk u in lockstep, and every
+// access is a coalesced row of the volume.
+// Where f(u) = 0 the answer is 0, and a zero shields everything behind it ((u - i)^2 + f(i) > (u - z)^2 for i beyond a
+// zero at z): only the zeros next to a positive voxel can matter to the envelope, so the zeros inside a stretch of
+// background are neither pushed nor popped.  For a vessel mask almost every voxel is background: the pass is two reads
+// and one write per voxel, and the envelope stack (s / t / g: parabola apex, start of its reign, height) holds a few
+// entries per vessel crossing, at the front of the line's slots, which stay in cache.  For a solid mask (the brain) the
+// runs are long and the scan is still O(n) per line whatever the distances.  A line is one dependent chain: inputs are
+// fetched eight steps ahead in both directions, and the pops of the backward scan (entries below the top no longer
+// change) fetch four stack entries at once.
 __global__ void __launch_bounds__(128) k_edt_lines(const int *__restrict__ in, int *__restrict__ out, short *__restrict__ s,
                                                    int *__restrict__ t, int *__restrict__ g, long long nlines, int len,
                                                    long long stride, int X, long long outer_stride) {
@@ -83,33 +89,31 @@ __global__ void __launch_bounds__(128) k_edt_lines(const int *__restrict__ in, i
         short *ss = s + base;
         int *tt = t + base, *gg = g + base;
         int *o = out + base;
-        // forward scan.  Registers hold the top of the stack (sq, tq, fq = f(sq)).
-        int q = 0, sq = 0, tq = 0;
-        long long fq = f[0];
-        ss[0] = 0; tt[0] = 0; gg[0] = (int)fq;
+        // forward scan.  Registers hold the top of the stack (sq, tq, fq = f(sq)); q = depth - 1, -1 = empty.
+        int q = -1, sq = 0, tq = 0, prev = 0;
+        long long fq = 0;
         constexpr int PF = 8;
-        for (int u0 = 1; u0 < len; u0 += PF) {
-            int fpre[PF];
+        for (int u0 = 0; u0 < len; u0 += PF) {
+            int fpre[PF + 1];
 #pragma unroll
-            for (int k = 0; k < PF; ++k) fpre[k] = f[(long long)min(u0 + k, len - 1) * stride];
+            for (int k = 0; k <= PF; ++k) fpre[k] = f[(long long)min(u0 + k, len - 1) * stride];
 #pragma unroll
             for (int k = 0; k < PF; ++k) {
                 const int u = u0 + k;
                 if (u >= len) break;
                 const long long fu = fpre[k];
-                if (fu >= EDT_INF) continue;  // an infinite parabola never reaches the envelope
-                bool replaced = false;
-                while (true) {
-                    // F(tq, sq) > F(tq, u) ?  the new parabola is already lower where the top one starts: pop
+                const bool wanted = fu == 0 ? (prev > 0 || (u + 1 < len && fpre[k + 1] > 0)) : fu < EDT_INF;
+                prev = (int)fu;
+                if (!wanted) continue;  // background away from any foreground, or an infinite parabola
+                while (q >= 0) {
+                    // F(tq, sq) > F(tq, u): the new parabola is already lower where the top one starts to reign: pop
                     const long long a = (long long)(tq - sq) * (tq - sq) + fq, b = (long long)(tq - u) * (tq - u) + fu;
                     if (a <= b) break;
-                    if (q == 0) { sq = u; fq = fu; tq = 0; ss[0] = (short)u; gg[0] = (int)fu; replaced = true; break; }
                     --q;
-                    sq = ss[(long long)q * stride]; tq = tt[(long long)q * stride]; fq = gg[(long long)q * stride];
+                    if (q >= 0) { sq = ss[(long long)q * stride]; tq = tt[(long long)q * stride]; fq = gg[(long long)q * stride]; }
                 }
-                if (replaced) continue;
-                // first position where parabola u is lower than the top one
-                const long long w = 1 + ((long long)u * u - (long long)sq * sq + fu - fq) / (2LL * (u - sq));
+                long long w = 0;  // first position where parabola u is the lowest
+                if (q >= 0) w = 1 + ((long long)u * u - (long long)sq * sq + fu - fq) / (2LL * (u - sq));
                 if (w < len) {
                     ++q; sq = u; tq = (int)w; fq = fu;
                     ss[(long long)q * stride] = (short)u; tt[(long long)q * stride] = (int)w; gg[(long long)q * stride] = (int)fu;
@@ -119,22 +123,32 @@ __global__ void __launch_bounds__(128) k_edt_lines(const int *__restrict__ in, i
         // backward scan
         constexpr int PB = 4;
         int ps[PB], pt[PB], pg[PB], have = 0;  // entries q-1 .. q-have, fetched ahead (ps[0] is the next one to pop)
-        for (int u = len - 1; u >= 0; --u) {
-            const long long d = (long long)(u - sq) * (u - sq) + fq;
-            o[(long long)u * stride] = d >= EDT_INF ? EDT_INF : (int)d;
-            if (u == tq && q > 0) {
-                if (have == 0) {
+        for (int u0 = len - 1; u0 >= 0; u0 -= PF) {
+            int fpre[PF];
 #pragma unroll
-                    for (int k = 0; k < PB; ++k) {
-                        const long long e = (long long)max(q - 1 - k, 0) * stride;
-                        ps[k] = ss[e]; pt[k] = tt[e]; pg[k] = gg[e];
+            for (int k = 0; k < PF; ++k) fpre[k] = f[(long long)max(u0 - k, 0) * stride];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int u = u0 - k;
+                if (u < 0) break;
+                while (q > 0 && u < tq) {  // the top parabola reigns from tq on: below it the previous one does
+                    if (have == 0) {
+#pragma unroll
+                        for (int j = 0; j < PB; ++j) {
+                            const long long e = (long long)max(q - 1 - j, 0) * stride;
+                            ps[j] = ss[e]; pt[j] = tt[e]; pg[j] = gg[e];
+                        }
+                        have = min(PB, q);
                     }
-                    have = min(PB, q);
-                }
-                --q; --have;
-                sq = ps[0]; tq = pt[0]; fq = pg[0];
+                    --q; --have;
+                    sq = ps[0]; tq = pt[0]; fq = pg[0];
 #pragma unroll
-                for (int k = 0; k + 1 < PB; ++k) { ps[k] = ps[k + 1]; pt[k] = pt[k + 1]; pg[k] = pg[k + 1]; }
+                    for (int j = 0; j + 1 < PB; ++j) { ps[j] = ps[j + 1]; pt[j] = pt[j + 1]; pg[j] = pg[j + 1]; }
+                }
+                long long d = EDT_INF;
+                if (fpre[k] == 0) d = 0;
+                else if (q >= 0) d = (long long)(u - sq) * (u - sq) + fq;
+                o[(long long)u * stride] = d >= EDT_INF ? EDT_INF : (int)d;
             }
         }
     }

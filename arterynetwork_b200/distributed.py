@@ -353,7 +353,7 @@ def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
             "config": {"workload": "%s %dx%dx%d vessel-forest phantom, seed %d" % (args.workload, shape[2], shape[1], shape[0], args.seed),
                        "intensity_mode": args.intensity, "partition": "z-slabs, %d planes per rank, halo %d" % (z1 - z0, HALO),
                        "sweeps_per_step": sweeps // args.steps, "segmented_voxels": res["n_in"],
-                       "label_histogram": [int(x) for x in cs.tolist()], "transport": transport, "cuda_graph": use_graph,
+                       "label_histogram": [int(x) for x in cs.tolist()], "transport": transport, "cuda_graph": bool(use_graph or transport == "p2p"),
                        "l2": "inputs larger than L2; no flush",
                        "step": "attach resident slab (zero-copy) + level scan/all-gather + init + all iterations"},
             "clocks": clocks,

@@ -284,3 +284,55 @@ def test_device_phantom_equals_numpy_phantom():
                                      len(roots), 2, 256, 31, 20, 1, d.data_ptr(), v.data_ptr()))
     assert np.array_equal(d.cpu().numpy(), data[z0:z0 + nz])
     assert np.array_equal(v.cpu().numpy(), vm[z0:z0 + nz])
+
+
+def test_config_c3_full_size_properties():
+    """BASELINE.json configs[2], 880x880x640 (the headline shape): no CPU reference finishes here inside a test budget,
+    so check what the domain offers -- the three sweep modes agree bit for bit (labels and trace), the region sizes are
+    conserved in every iteration (n_in + n_out = N without label 4), the last trace row is the label histogram, the run
+    converged, the tubes are recovered exactly, and the distance transform of
+    the result (the next step of the pipeline) is 0 off the mask and >= 1 on it."""
+    import torch
+    import bench
+    from arterynetwork_b200.engine import VRGEngine
+    from arterynetwork_b200.phantom import forest_segments
+    shape = bench.WORKLOADS["c3"]
+    nvox = shape[0] * shape[1] * shape[2]
+    d, v = bench.device_phantom(shape, 0, 0, shape[0], 0)
+    torch.cuda.synchronize()
+    out = torch.empty(shape, dtype=torch.uint8, device="cuda")
+    first = None
+    for mode in MODES:
+        with VRGEngine(shape, max_segment_size=10 ** 15, intensity=mode) as eng:
+            eng.attach_device(d.data_ptr(), v.data_ptr())
+            eng.init()
+            res = eng.run()
+            trace = eng.trace()
+            eng.labels_device(out.data_ptr())
+            torch.cuda.synchronize()
+            assert res["exit_reason"] == 0 and 20 <= res["iterations"] <= 200
+            assert np.all(trace[:, 1] + trace[:, 2] == nvox)
+            hist = torch.bincount(out.flatten().to(torch.int64), minlength=5).cpu().numpy()
+            assert hist[0] + hist[1] == trace[-1, 1] == res["n_in"] and hist[2] + hist[3] == trace[-1, 2] and hist[4] == 0
+            if first is None:
+                first = (out.clone(), trace)
+            else:
+                assert torch.equal(out, first[0]) and np.array_equal(trace, first[1])
+    seg = (first[0] <= 1)
+    # exact recovery of the phantom's tubes (integer geometry, NumPy rasteriser): 4,294,594 voxels
+    from arterynetwork_b200.phantom import rasterize
+    segs, _ = forest_segments(shape, seed=0)
+    tubes = rasterize(shape, segs)
+    assert int(tubes.sum()) == int(first[1][-1, 1])
+    assert np.array_equal(seg.cpu().numpy(), tubes)
+    del tubes
+    # the step after the path on the full-size result (device resident)
+    import ctypes
+    from arterynetwork_b200 import _native as nat
+    dist = torch.empty(shape, dtype=torch.float64, device="cuda")
+    shp = (nat.i64 * 3)(*shape)
+    m8 = seg.to(torch.uint8).contiguous()
+    nat.check(nat.load().vrg_edt_device(0, m8.data_ptr(), ctypes.addressof(shp), dist.data_ptr(), None))
+    assert float(dist[~seg].max()) == 0.0 and float(dist[seg].min()) >= 1.0
+    sq = torch.round(dist * dist)
+    assert torch.equal(torch.sqrt(sq), dist) and float(dist.max()) <= 8.0
