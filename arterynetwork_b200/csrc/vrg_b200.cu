@@ -227,7 +227,7 @@ int vrg_destroy(vrg_handle *h) {
     free_levels(h);
     if (h->cont_alloc) {
         cudaFree(h->cq.pin); cudaFree(h->cq.pout); cudaFree(h->cq.B); cudaFree(h->cq.newlist); cudaFree(h->cq.oldlist);
-        cudaFree(h->cq.rowlist); cudaFree(h->cq.count); cudaFree(h->cq.partial);
+        cudaFree(h->cq.rowlist); cudaFree(h->cq.count); cudaFree(h->cq.partial); cudaFree(h->cq.abrowlist); cudaFree(h->cq.AB);
     }
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->halo_stream) { cudaStreamSynchronize(h->halo_stream); cudaStreamDestroy(h->halo_stream); }
@@ -500,6 +500,8 @@ static int cont_alloc(vrg_handle *h) {
     CK(cudaMalloc((void **)&q.newlist, (size_t)q.cap * sizeof(int)));
     CK(cudaMalloc((void **)&q.oldlist, (size_t)q.cap * sizeof(int)));
     CK(cudaMalloc((void **)&q.rowlist, h->rowflag_bytes * sizeof(int)));
+    CK(cudaMalloc((void **)&q.abrowlist, h->rowflag_bytes * sizeof(int)));
+    CK(cudaMalloc((void **)&q.AB, h->plane_bytes));
     CK(cudaMalloc((void **)&q.count, CC_WORDS * sizeof(int)));
     CK(cudaMalloc((void **)&q.partial, ntiles * CONT_SPLIT * CONT_TILE * 2 * sizeof(double)));
     h->cont_alloc = true;
@@ -541,11 +543,12 @@ static int cont_init(vrg_handle *h) {
     c[C_TRACE_N] = 1; c[C_TABLE_CHANGED] = 1; c[C_EPOCH] = ++h->epoch;
     memcpy(h->h_ctrl, c, sizeof c);
     CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof c, cudaMemcpyHostToDevice, h->stream));
-    p.E = h->d_E; p.C = nullptr;
+    CK(cudaMemsetAsync(h->d_C, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(q.AB, 0, h->plane_bytes, h->stream));
+    p.E = h->d_E; p.C = h->d_C;
     k_init_planes<<<h->grid, BLOCK, 0, h->stream>>>(p, h->vm_base, h->d_E);
-    k_init_bands<<<h->grid, BLOCK, 0, h->stream>>>(p);
+    k_init_bands<<<h->grid, BLOCK, 0, h->stream>>>(p);  // E = Eraw & ~dil26(S), VRG:137
     k_cont_count<<<h->grid, BLOCK, 0, h->stream>>>(p);
-    p.E = nullptr;
     k_cont_band<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
     k_cont_full1<<<dim3(h->sms, CONT_SPLIT), BLOCK, 0, h->stream>>>(p, q);
     k_cont_full2<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
@@ -553,14 +556,11 @@ static int cont_init(vrg_handle *h) {
     CK(cudaGetLastError());
     long long ex[ST_EXTRA];
     int cc[CC_WORDS];
-    std::vector<uint32_t> eplane(h->plane_bytes / sizeof(uint32_t));
     CK(cudaMemcpyAsync(ex, h->d_lstats, sizeof ex, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(cc, q.count, sizeof cc, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(eplane.data(), h->d_E, h->plane_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (ex[ST_BAD_LABEL]) return fail(VRG_ERR_LABEL, "initial valueMap may only hold labels 0 (seed), 3 (outside) and 4 (excluded)");
-    for (uint32_t w : eplane)
-        if (w) return fail(VRG_ERR_ARG, "continuous mode does not support excluded voxels (label 4) yet");
+    if (ex[ST_N_EXCL] == 0) { p.E = nullptr; p.C = nullptr; }  // no label 4: skip the absorb path
     if (ex[ST_N_IN] == 0) return fail(VRG_ERR_EMPTY_SEED, "no seed voxel (label 0) in valueMap");
     if (ex[ST_N_BAND] == 0) return fail(VRG_ERR_NO_BAND, "seed has no boundary: every voxel is inside");
     if (cc[CC_OVERFLOW]) return fail(VRG_ERR_ARG, "continuous mode: more than %d band voxels entered at once", q.cap);
@@ -579,8 +579,14 @@ static int cont_enqueue_iteration(vrg_handle *h) {
     k_cont_begin<<<1, 32, 0, h->stream>>>(p, q);
     k_cont_decide<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
     k_cancel<MODE_CONT, false><<<h->grid, BLOCK, 0, h->stream>>>(p);
+    if (p.E != nullptr) {  // label 4: absorb around the flips, and remember which voxels joined the outside region
+        CK(cudaMemsetAsync(q.AB, 0, h->plane_bytes, h->stream));
+        k_absorb<MODE_CONT, false><<<h->grid, BLOCK, 0, h->stream>>>(p, q.AB);
+        k_cont_rows<<<1, 1024, 0, h->stream>>>(p, q, 1);
+        h->launches += 2;
+    }
     k_advance<<<1, 32, 0, h->stream>>>(p);
-    k_cont_rows<<<1, 1024, 0, h->stream>>>(p, q);
+    k_cont_rows<<<1, 1024, 0, h->stream>>>(p, q, 0);
     k_cont_band<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
     k_cont_incr<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
     k_cont_full1<<<dim3(h->sms, CONT_SPLIT), BLOCK, 0, h->stream>>>(p, q);
@@ -705,7 +711,7 @@ int vrg_enqueue_cancel(vrg_handle *h) {
 int vrg_enqueue_absorb(vrg_handle *h) {
     NEED_INIT();
     if (!h->p.E) return VRG_OK;
-    LAUNCH_ML(k_absorb, h->grid, BLOCK, 0, h->p);
+    LAUNCH_ML(k_absorb, h->grid, BLOCK, 0, h->p, nullptr);
     h->launches++;
     CK(cudaGetLastError());
     return VRG_OK;

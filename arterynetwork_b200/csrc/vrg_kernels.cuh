@@ -760,8 +760,10 @@ __global__ void __launch_bounds__(BLOCK) k_flip_halo(Params p) {
 // ---------------------------------------------------------------------------------------------
 // k_absorb: excluded voxels within 1 of any listed flip (executed or cancelled), or within 2 of an executed flip,
 // become outside (VRG:167-168, 177-179, 207-208).  Runs after k_cancel (and the F/C halo exchange).
+// ab_out (continuous mode only, else nullptr): bit-plane that receives the absorbed voxels of this iteration -- that mode
+// has no histograms, its band voxels get the absorbed voxels' kernel terms one by one (VRG:235,247, k_cont_incr).
 template <int MODE, bool LATTICE>
-__global__ void __launch_bounds__(BLOCK) k_absorb(Params p) {
+__global__ void __launch_bounds__(BLOCK) k_absorb(Params p, uint32_t *ab_out) {
     if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_APPLY]) return;
     const int lane = threadIdx.x & 31;
     const long long nrows = (long long)(p.own_hi - p.own_lo) * p.Y * p.nseg;
@@ -808,10 +810,13 @@ __global__ void __launch_bounds__(BLOCK) k_absorb(Params p) {
         if (!active || ab == 0u) continue;
         p.E[widx] = e & ~ab;
         n_abs += __popc(ab);
-        const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
-        while (ab) {
-            const int b = __ffs(ab) - 1; ab &= ab - 1;
-            atomicAdd(&hout[level_at<MODE, LATTICE>(p, rowvox + b)], 1ull);  // addedPoints, VRG:235,247
+        if (ab_out != nullptr) ab_out[widx] = ab;
+        if (MODE != MODE_CONT) {
+            const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
+            while (ab) {
+                const int b = __ffs(ab) - 1; ab &= ab - 1;
+                atomicAdd(&hout[level_at<MODE, LATTICE>(p, rowvox + b)], 1ull);  // addedPoints, VRG:235,247
+            }
         }
     }
     n_abs = warp_sum(n_abs);

@@ -10,13 +10,15 @@
 //   k_cont_incr    staying voxels: pin += sum_A K - sum_R K, pout -= the same  (A entered, R left)          VRG:232-247
 //   k_cont_full    entering voxels: both sums over the whole volume, O(n_new * N) fp64 exp                   VRG:249-255
 // Fixed traversal orders everywhere (canonical row order for the corrections, a fixed volume partition and a fixed
-// reduction tree for the full sums), so results do not depend on scheduling.  Single slab, no label 4 (yet).
+// reduction tree for the full sums), so results do not depend on scheduling.  Single slab.
+// Label 4: excluded voxels belong to neither region; those absorbed in an iteration (k_absorb<CONT> records them in the
+// plane AB) join the outside region, i.e. every staying band voxel's pout gains their kernel terms (VRG:235,247).
 #pragma once
 #include "vrg_kernels.cuh"
 
 namespace vrg {
 
-enum { CC_NEW = 0, CC_OLD = 1, CC_ROWS = 2, CC_OVERFLOW = 3, CC_WORDS = 8 };
+enum { CC_NEW = 0, CC_OLD = 1, CC_ROWS = 2, CC_OVERFLOW = 3, CC_ABROWS = 4, CC_WORDS = 8 };
 constexpr int CONT_TILE = 16;    // new voxels whose sums one block accumulates while streaming the volume
 constexpr int CONT_SPLIT = 8;    // volume partitions per tile (second-stage sum in partition order)
 constexpr long long EXIT_CONT_OVERFLOW = 98;
@@ -26,6 +28,8 @@ struct Cont {
     uint32_t *B;             // band plane the sums are valid for
     int *newlist, *oldlist;  // local voxel ids of band voxels that entered / stayed
     int *rowlist;            // row-segment ids whose flip word is non-zero, ascending
+    uint32_t *AB;            // voxels absorbed (label 4 -> 3) in this iteration (only with label 4 in the input)
+    int *abrowlist;          // row-segment ids that hold an absorbed voxel, ascending
     int *count;              // [CC_WORDS]
     int cap;                 // capacity of the voxel lists
     double *partial;         // [tiles][CONT_SPLIT][CONT_TILE][2]
@@ -43,48 +47,62 @@ __global__ void k_cont_begin(Params p, Cont q) {
     dirty_list(p, (int)((p.ctrl[C_SWEEPS] + 1) & 1))[0] = 0;
 }
 
-// region sizes at init (VRG:49-52)
+// region sizes at init (VRG:49-52); excluded voxels (label 4) belong to neither region
 __global__ void __launch_bounds__(BLOCK) k_cont_count(Params p) {
     const int lane = threadIdx.x & 31;
     const int nrows = (p.own_hi - p.own_lo) * p.Y, nwarps = gridDim.x * WARPS;
-    long long n_in = 0, n_all = 0;
+    long long n_in = 0, n_all = 0, n_ex = 0;
     for (int r = blockIdx.x * WARPS + (threadIdx.x >> 5); r < nrows; r += nwarps) {
         const long long wbase = (long long)(p.own_lo + r / p.Y) * p.plane_words + (long long)(r % p.Y) * p.WP;
         for (int c = lane; c < p.XW; c += 32) {
-            n_in += __popc(p.S[wbase + c]);
+            const uint32_t s = p.S[wbase + c];
+            n_in += __popc(s);
             n_all += __popc(valid_mask(p, c));
+            if (p.E) n_ex += __popc(p.E[wbase + c] & ~s & valid_mask(p, c));
         }
     }
-    n_in = warp_sum(n_in); n_all = warp_sum(n_all);
+    n_in = warp_sum(n_in); n_all = warp_sum(n_all); n_ex = warp_sum(n_ex);
     if (lane == 0) {
         atomicAdd((unsigned long long *)&p.lstats[ST_N_IN], (unsigned long long)n_in);
-        atomicAdd((unsigned long long *)&p.lstats[ST_N_OUT], (unsigned long long)(n_all - n_in));
+        atomicAdd((unsigned long long *)&p.lstats[ST_N_OUT], (unsigned long long)(n_all - n_in - n_ex));
+        if (n_ex) atomicAdd((unsigned long long *)&p.lstats[ST_N_EXCL], (unsigned long long)n_ex);
     }
 }
 
-// rows whose flip word is non-zero, ascending (one block; the row space of this mode is small)
-__global__ void __launch_bounds__(1024) k_cont_rows(Params p, Cont q) {
+// ascending list of the row segments that satisfy a predicate (one block; the row space of this mode is small):
+// which = 0: the flip word is non-zero (row flag)  -> rowlist / CC_ROWS
+// which = 1: the row holds an absorbed voxel (AB)   -> abrowlist / CC_ABROWS
+__global__ void __launch_bounds__(1024) k_cont_rows(Params p, Cont q, int which) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
     __shared__ int s_warp[32];
     __shared__ int s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nrows = (p.own_hi - p.own_lo) * p.Y * p.nseg, base = p.own_lo * p.Y * p.nseg;
+    int *list = which ? q.abrowlist : q.rowlist;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     for (int i0 = 0; i0 < nrows; i0 += 1024) {
         const int i = i0 + threadIdx.x;
-        const bool flag = i < nrows && p.rowflag[base + i] != 0;
+        bool flag = false;
+        if (i < nrows) {
+            if (!which) flag = p.rowflag[base + i] != 0;
+            else {
+                const int rr = base + i, sg = rr % p.nseg, t = rr / p.nseg;
+                const uint32_t *row = q.AB + (long long)(t / p.Y) * p.plane_words + (long long)(t % p.Y) * p.WP;
+                for (int c = sg * p.segw; c < min((sg + 1) * p.segw, p.XW); ++c) flag |= row[c] != 0u;
+            }
+        }
         const unsigned m = __ballot_sync(FULL, flag);
         if (lane == 0) s_warp[warp] = __popc(m);
         __syncthreads();
         int before = 0;
         for (int w = 0; w < warp; ++w) before += s_warp[w];
-        if (flag) q.rowlist[s_base + before + __popc(m & ((1u << lane) - 1u))] = base + i;
+        if (flag) list[s_base + before + __popc(m & ((1u << lane) - 1u))] = base + i;
         __syncthreads();
         if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += s_warp[w]; s_base += t; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) q.count[CC_ROWS] = s_base;
+    if (threadIdx.x == 0) q.count[which ? CC_ABROWS : CC_ROWS] = s_base;
 }
 
 // appends the voxel ids of the set bits of `bits` (one word per lane) to a list, warp-aggregated
@@ -127,6 +145,7 @@ __global__ void __launch_bounds__(BLOCK) k_cont_band(Params p, Cont q) {
             uint32_t s, inner, outer;
             st.step(y, s, inner, outer);
             const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
+            if (p.E != nullptr && outer) outer &= ~p.E[widx];  // outer is non-zero on active lanes only
             const uint32_t band = inner | outer;
             const uint32_t bold = st.active ? q.B[widx] : 0u;
             if (__ballot_sync(FULL, (band | bold) != 0u) == 0u) continue;
@@ -169,8 +188,24 @@ __global__ void __launch_bounds__(BLOCK) k_cont_incr(Params p, Cont q) {
                 }
             }
         }
-        q.pin[vox] = q.pin[vox] + sum_a - sum_r;   // innerProb += innerCorrection; innerProb -= outerCorrection
-        q.pout[vox] = q.pout[vox] - sum_a + sum_r; // outerProb -= innerCorrection; outerProb += outerCorrection
+        double sum_ab = 0.0;  // voxels absorbed into the outside region (label 4 -> 3), same canonical order
+        const int nab = p.E != nullptr ? q.count[CC_ABROWS] : 0;
+        for (int k = 0; k < nab; ++k) {
+            const int rr = q.abrowlist[k];
+            const int sg = rr % p.nseg, t = rr / p.nseg, y = t % p.Y, zl = t / p.Y;
+            const long long wrow = (long long)zl * p.plane_words + (long long)y * p.WP;
+            const long long vrow = (long long)zl * p.plane_vox + (long long)y * p.X;
+            for (int c = sg * p.segw; c < min((sg + 1) * p.segw, p.XW); ++c) {
+                uint32_t ab = q.AB[wrow + c];
+                while (ab) {
+                    const int b = __ffs(ab) - 1;
+                    ab &= ab - 1;
+                    sum_ab += parzen(p, p.data[vrow + (long long)c * 32 + b], v);
+                }
+            }
+        }
+        q.pin[vox] = q.pin[vox] + sum_a - sum_r;            // innerProb += innerCorrection; innerProb -= outerCorrection
+        q.pout[vox] = q.pout[vox] - sum_a + sum_r + sum_ab;  // outerProb -= inner...; += outer...; += addedCorrection
     }
 }
 
@@ -199,9 +234,11 @@ __global__ void __launch_bounds__(BLOCK) k_cont_full1(Params p, Cont q) {
             const int y = (int)(t % p.Y), zl = p.own_lo + (int)(t / p.Y);
             const int x = c * 32 + lane;
             if (x >= p.X) continue;
-            const uint32_t s = p.S[(long long)zl * p.plane_words + (long long)y * p.WP + c];
+            const long long wi = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+            const uint32_t s = p.S[wi], e = p.E ? p.E[wi] : 0u;
             const double val = p.data[(long long)zl * p.plane_vox + (long long)y * p.X + x];
             const bool in = (s >> lane) & 1u;
+            if (!in && ((e >> lane) & 1u)) continue;  // excluded: in neither region
 #pragma unroll
             for (int k = 0; k < CONT_TILE; ++k) {
                 const double kv = parzen(p, val, vt[k]);

@@ -52,7 +52,7 @@ typedef enum {
     VRG_INTENSITY_F64_BAND = 1,  /* fp64 volume, but only 32-voxel words that hold a band voxel */
     VRG_INTENSITY_INDEX = 2,     /* uint16 level-index volume built once; band words only */
     VRG_INTENSITY_CONTINUOUS = 3 /* no level table: brute-force Parzen sums per band voxel (VRG:151-155,232-255), for data
-                                    with more than VRG_MAX_LEVELS distinct intensities; single GPU, small volumes, no label 4 */
+                                    with more than VRG_MAX_LEVELS distinct intensities; single GPU, small volumes */
 } vrg_intensity_mode;
 
 #define VRG_MAX_LEVELS 65536

@@ -133,6 +133,16 @@ def case_forest_cont():
     return data, 0, vm.astype(np.int64), dict(H=2.25, max_segment_size=None)
 
 
+def case_excl_cont():  # continuous intensities AND label 4: absorbed voxels join the outside sums (VRG:235,247)
+    data = np.zeros((16, 16, 28))
+    data[6:10, 6:10, 4:24] = 1.0
+    data = data + np.random.default_rng(3).normal(0, 0.12, data.shape)
+    vm = np.full(data.shape, 3)
+    vm[data <= 0.05] = 4  # the darker two thirds of the background (cf. the commented-out initialisation at VRG:41-43)
+    vm[7:9, 7:9, 13:15] = 0
+    return data, 0, vm, dict(H=2.25, max_segment_size=None)
+
+
 C1_KW = dict(cell=(128, 128, 128), margin=8, depth=4, root_r2=16, min_len=16, max_len=34)
 
 
@@ -155,6 +165,7 @@ CASES = {
     "c1_128": case_c1_128,
     "tube_cont": case_tube_cont,
     "forest_cont": case_forest_cont,
+    "excl_cont": case_excl_cont,
 }
 SMALL = [c for c in CASES if c != "c1_128"]
 

@@ -236,11 +236,14 @@ def test_continuous_mode_matches_reference_and_exact_oracle(name):
     np.testing.assert_allclose(pout, rpout, rtol=TABLE_RTOL, atol=0)
 
 
-def test_continuous_data_in_table_modes_is_rejected_or_exact():
-    """13824 distinct values still fit the level table (non-lattice binary-search path): same result as the reference."""
-    g = load_golden("forest_cont")
+@pytest.mark.parametrize("name", ["forest_cont", "excl_cont"])
+def test_continuous_data_in_table_modes_is_rejected_or_exact(name):
+    """13824 (7168) distinct values still fit the level table (non-lattice binary-search path, with and without label 4):
+    same result as the reference."""
+    g = load_golden(name)
     o = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], "f64_band")
     assert o["iterations"] == g["iterations"] and np.array_equal(o["labels"], g["labels"])
+    assert np.array_equal(o["trace"], g["trace"])
 
 
 def test_attach_device_runs_in_place_and_can_rerun():
