@@ -121,3 +121,23 @@ def test_oracle_errors():
         vrg_oracle_c(data, np.full(data.shape, 3))
     with pytest.raises(ValueError):
         vrg_oracle_c(data, np.zeros(data.shape, dtype=int))
+
+
+@pytest.mark.parametrize("i", range(12))
+def test_c_oracle_equals_numpy_oracle_on_random_cases(i):
+    """The two restatements agree on seeded random inputs (odd shapes, label 4, several seeds, caps)."""
+    from random_cases import random_case
+    from oracle.c_oracle import vrg_oracle_c
+    from oracle.vrg_oracle import vrg_oracle
+    data, vm, H, max_seg = random_case(i)
+    try:
+        a = vrg_oracle(data, vm, H=H, max_segment_size=max_seg)
+    except ValueError:
+        with pytest.raises(ValueError):
+            vrg_oracle_c(data, vm, H=H, max_segment_size=max_seg)
+        return
+    b = vrg_oracle_c(data, vm, H=H, max_segment_size=max_seg)
+    if a["min_margin"] < 1e-9:
+        pytest.skip("a band voxel sits on a numerical tie: summation order decides")
+    assert a["iterations"] == b["iterations"] and a["exit"] == b["exit"]
+    assert np.array_equal(a["trace"], b["trace"]) and np.array_equal(a["labels"], b["labels"])
