@@ -16,6 +16,7 @@ EXIT_RUNNING, EXIT_CONVERGED, EXIT_MAX_TIME, EXIT_MAX_SEGMENT, EXIT_MAX_ITER = -
 INTENSITY_F64_DENSE, INTENSITY_F64_BAND, INTENSITY_INDEX = 0, 1, 2
 INTENSITY_MODES = {"f64_dense": 0, "f64_band": 1, "index": 2, "continuous": 3}
 HALO = 2
+MAX_LEVELS = 65536
 P2P_HANDLE_BYTES = 192
 BUF_SEG, BUF_EXCL, BUF_FLIPS, BUF_CANCELLED, BUF_LOCAL_STATS, BUF_GLOBAL_STATS, BUF_CTRL = range(7)
 ST_N_IN, ST_N_OUT, ST_N_EXCL, ST_N_FLIPS, ST_N_BAND, ST_BAD_LABEL, ST_NONFINITE, ST_EXTRA = 0, 1, 2, 3, 4, 5, 6, 8

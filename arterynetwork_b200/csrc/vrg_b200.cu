@@ -54,7 +54,7 @@ struct vrg_handle {
     uint32_t *d_dbits = nullptr;
     long long *d_lstats = nullptr, *d_gstats = nullptr, *d_ctrl = nullptr, *d_trace = nullptr;
     long long *h_ctrl = nullptr;  // pinned
-    unsigned long long *d_hash = nullptr;
+    unsigned long long *d_hash = nullptr, *d_hkeys = nullptr;
     int *d_hcount = nullptr;
     std::vector<double> levels;  // distinct levels seen (sorted)
     int64_t n_distinct = 0;
@@ -202,6 +202,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     alloc((void **)&h->d_ctrl, C_WORDS * sizeof(long long));
     alloc((void **)&h->d_trace, 3 * (cfg->iter_max + 2) * sizeof(long long));
     alloc((void **)&h->d_hash, (size_t)HASH_CAP * sizeof(unsigned long long));
+    alloc((void **)&h->d_hkeys, (size_t)VRG_MAX_LEVELS * sizeof(unsigned long long));
     alloc((void **)&h->d_hcount, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_ctrl, C_WORDS * sizeof(long long));
     if (e != cudaSuccess) {
@@ -223,7 +224,7 @@ int vrg_destroy(vrg_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_data); cudaFree(h->d_vm); cudaFree(h->d_index); cudaFree(h->d_labels);
     cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_dirty); cudaFree(h->d_stamp);
-    cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hcount);
+    cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hkeys); cudaFree(h->d_hcount);
     free_levels(h);
     if (h->cont_alloc) {
         cudaFree(h->cq.pin); cudaFree(h->cq.pout); cudaFree(h->cq.B); cudaFree(h->cq.newlist); cudaFree(h->cq.oldlist);
@@ -327,17 +328,18 @@ int vrg_scan_levels(vrg_handle *h, int64_t *n_levels) {
                                                      h->d_hcount, VRG_MAX_LEVELS, h->d_hcount + 1);
     h->launches++;
     CK(cudaGetLastError());
+    k_compact_levels<<<h->sms, BLOCK, 0, h->stream>>>(h->d_hash, HASH_CAP, h->d_hkeys, h->d_hcount + 3, VRG_MAX_LEVELS);
+    h->launches++;
     int hc[4];
     CK(cudaMemcpyAsync(hc, h->d_hcount, sizeof hc, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (hc[1]) return fail(VRG_ERR_NONFINITE, "intensity volume holds NaN or Inf");
-    if (hc[2] || hc[0] > VRG_MAX_LEVELS)
+    if (hc[2] || hc[0] > VRG_MAX_LEVELS || hc[3] > VRG_MAX_LEVELS)
         return fail(VRG_ERR_LEVELS, "more than %d distinct intensity levels: continuous data needs the brute-force Parzen path", VRG_MAX_LEVELS);
-    std::vector<unsigned long long> tab(HASH_CAP);
-    CK(cudaMemcpy(tab.data(), h->d_hash, tab.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> keys((size_t)hc[3]);
+    if (hc[3]) CK(cudaMemcpy(keys.data(), h->d_hkeys, keys.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     h->levels.clear();
-    for (unsigned long long k : tab)
-        if (k != HEMPTY) { double v; memcpy(&v, &k, 8); h->levels.push_back(v); }
+    for (unsigned long long k : keys) { double v; memcpy(&v, &k, 8); h->levels.push_back(v); }
     std::sort(h->levels.begin(), h->levels.end());
     h->n_distinct = (int64_t)h->levels.size();
     if (n_levels) *n_levels = h->n_distinct;

@@ -1204,6 +1204,18 @@ __global__ void __launch_bounds__(BLOCK) k_scan_levels(const double *__restrict_
     }
 }
 
+// the keys of the hash set, densely packed (unordered; the host sorts the few hundred values)
+__global__ void __launch_bounds__(BLOCK) k_compact_levels(const unsigned long long *__restrict__ table, int cap,
+                                                          unsigned long long *__restrict__ out, int *n_out, int max_out) {
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < cap; i += gridDim.x * BLOCK) {
+        const unsigned long long k = table[i];
+        if (k != HEMPTY) {
+            const int j = atomicAdd(n_out, 1);
+            if (j < max_out) out[j] = k;
+        }
+    }
+}
+
 template <bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_build_index(Params p, const double *__restrict__ data, uint16_t *index, long long n) {
     for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK)

@@ -170,18 +170,36 @@ class DistributedVRG:
 
     # -- phases ---------------------------------------------------------------------------------
     def prepare_levels(self):
-        """Union of the slabs' intensity levels: every rank builds the same table domain."""
+        """Union of the slabs' intensity levels: every rank builds the same table domain.
+
+        One fixed-size all-gather of float64 tensors ([count, levels..., padding]; 4096 slots, or 65537 when some slab
+        holds more levels) instead of a pickled object gather, which costs milliseconds per call on NCCL."""
+        torch, dist = self.torch, self.dist
         mine = np.asarray(self.e.local_levels(), dtype=np.float64)
-        gathered = [None] * self.world
-        self.dist.all_gather_object(gathered, mine)
-        levels = np.unique(np.concatenate(gathered))
+        dev = getattr(self.e, "device", "cpu") if dist.get_backend() == "nccl" else "cpu"
+        cap = 4096
+        while True:
+            buf = torch.zeros(cap, dtype=torch.float64)
+            n = min(len(mine), cap - 1)
+            buf[0] = float(len(mine))
+            buf[1:1 + n] = torch.from_numpy(np.ascontiguousarray(mine[:n]))
+            buf = buf.to(dev)
+            parts = [torch.empty(cap, dtype=torch.float64, device=dev) for _ in range(self.world)]
+            dist.all_gather(parts, buf)
+            g = torch.stack(parts).cpu().numpy()
+            counts = g[:, 0].astype(np.int64)
+            if int(counts.max()) <= cap - 1:
+                break
+            cap = nat.MAX_LEVELS + 1  # some slab has more than 4095 levels: once more with room for the maximum
+        levels = np.unique(np.concatenate([g[r, 1:1 + counts[r]] for r in range(self.world)]))
         self.e.set_levels(levels)
         return levels
 
     def init(self):
         if self.transport == "p2p":
             self._connect_p2p()
-            self.dist.barrier()  # the init exchange spins on the peers: start together
+            # no barrier: the ranks left prepare_levels (a collective) together, and the init exchange below waits for
+            # its peers on the device (sequence-numbered flags, 20 s timeout)
             self.e.eng.init()    # seeds, bands, histograms + device-side halo / statistics exchange and the error checks
             self.init_row = tuple(int(x) for x in self.e.eng.trace()[0])
             return
