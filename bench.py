@@ -168,6 +168,19 @@ def cpu_sample(shape, seed):
         z0, z0 + nz, shape[2], shape[1], shape[0], shape[2], shape[1], nz), z0
 
 
+def reference_python_c1():
+    """The unmodified reference's own time on config C1 (128^3), measured in the build container when the golden
+    fixture was made (tests/golden/make_golden.py c1_128): the reference is pure Python and cannot travel to the GPU
+    box, so this is a recorded number, not one measured in this run."""
+    try:
+        f = np.load(os.path.join(ROOT, "tests", "golden", "c1_128.npz"))
+        sec, it = float(f["reference_wall_s"]), int(f["iterations"])
+        return {"seconds": sec, "iterations": it, "Gvoxel_updates_per_s": 128 ** 3 * it / sec / 1e9, "cores": 1,
+                "where": "build container, recorded in tests/golden/c1_128.npz (unmodified reference, NumPy %s)" % str(f["numpy_version"])}
+    except Exception:
+        return None
+
+
 def time_cpu_port(data, vm, threads):
     from oracle.c_oracle import vrg_oracle_c
     t0 = time.perf_counter()
@@ -354,7 +367,7 @@ def run_single(args):
         "roofline": roofline_of(prim, nvox, peak, peak_kind, traffic),
         "cpu_baseline": {"value": cpu_val, "unit": "Gvoxel-updates/s", "cores": threads, "kind": "port",
                          "sample": sample, "seconds": cpu_dt, "iterations": cpu_it,
-                         "device_phantom_equals_numpy_phantom": gen_equal},
+                         "device_phantom_equals_numpy_phantom": gen_equal, "reference_python_c1": reference_python_c1()},
         "modes": {m: {"value": r["value"], "ms_per_step": r["ms"] / max(1, (args.steps if m == args.intensity else min(args.steps, 3))),
                       "roofline_frac_10B": roofline_of(r, nvox, peak, peak_kind)["frac"],
                       "decide_ms_per_launch": r["prof"]["decide_ms"] / max(1, r["prof"]["decide_launches"]),
