@@ -472,8 +472,14 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     for (int i = threadIdx.x; i < p.LW; i += DENSE_WARPS * 32) s_dbits[i] = p.dbits[i];
     uint64_t *mybar = bars + warp * DENSE_STAGES;
     double *mystage = stages + (size_t)warp * DENSE_STAGES * (STAGE_BYTES / 8);
-    // stages start out holding a valid intensity everywhere: a row shorter than 960 voxels leaves the rest untouched
-    for (int i = lane; i < DENSE_STAGES * (STAGE_BYTES / 8); i += 32) mystage[i] = p.lev0;
+    // the part of a stage that no row segment ever overwrites (beyond the shortest segment: the row's tail, and the
+    // words up to the batch width) must hold a valid intensity, since the evaluation below is branch-free
+    {
+        const int shortest = min(p.segw * 32, p.X - (p.nseg - 1) * p.segw * 32);
+#pragma unroll
+        for (int s = 0; s < DENSE_STAGES; ++s)
+            for (int i = shortest + lane; i < STAGE_BYTES / 8; i += 32) mystage[s * (STAGE_BYTES / 8) + i] = p.lev0;
+    }
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < DENSE_STAGES; ++s) mbar_init(mybar + s, 1);
@@ -712,19 +718,25 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
         if (active) {
             d_in += __popc(a) - __popc(r);
             const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
-            uint32_t m = MODE == MODE_CONT ? 0u : r;  // the continuous mode has no histograms: see k_cont_incr
+            // histogram deltas of the flipped voxels (the continuous mode has none: see k_cont_incr).  Their levels are
+            // gathered four at a time: the loads of one batch are independent, a plain bit loop would wait for each.
+            uint32_t m = MODE == MODE_CONT ? 0u : (r | a);
             while (m) {
-                const int b = __ffs(m) - 1; m &= m - 1;
-                const int l = level_at<MODE, LATTICE>(p, rowvox + b);
-                atomicAdd(&hin[l], ~0ull);
-                atomicAdd(&hout[l], 1ull);
-            }
-            m = MODE == MODE_CONT ? 0u : a;
-            while (m) {
-                const int b = __ffs(m) - 1; m &= m - 1;
-                const int l = level_at<MODE, LATTICE>(p, rowvox + b);
-                atomicAdd(&hin[l], 1ull);
-                atomicAdd(&hout[l], ~0ull);
+                int bs[4], ls[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    bs[k] = m ? __ffs(m) - 1 : -1;
+                    m &= m - 1;  // 0 stays 0
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ls[k] = level_at<MODE, LATTICE>(p, rowvox + max(bs[k], 0));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (bs[k] < 0) continue;
+                    const unsigned long long d = (a >> bs[k]) & 1u ? 1ull : ~0ull;  // entered: +1 inside, -1 outside; left: the reverse
+                    atomicAdd(&hin[ls[k]], d);
+                    atomicAdd(&hout[ls[k]], 0ull - d);
+                }
             }
         }
     });
