@@ -161,8 +161,8 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     h->sms = prop.multiProcessorCount;
     h->grid = h->sms * 8;
-    h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;
-    h->graph_ok = getenv("VRG_NO_GRAPH") == nullptr;  // A/B switch: dense sweep with plain loads instead of the TMA ring
+    h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;  // A/B switch: plain loads instead of the TMA rings (sweep, init histogram)
+    h->graph_ok = getenv("VRG_NO_GRAPH") == nullptr;    // A/B switch: vrg_run stays on plain stream launches
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     Params &p = h->p;
