@@ -466,7 +466,8 @@ static int launch_init_hist(vrg_handle *h) {
     }
     // TMA-staged variant: the level source streams through a per-warp ring (16-byte aligned row segments only)
     const size_t elem = h->cfg.intensity_mode == VRG_INTENSITY_INDEX ? sizeof(uint16_t) : sizeof(double);
-    if (((size_t)p.X * elem) % 16 == 0 && !h->force_ldg) {
+    const uintptr_t src_base = h->cfg.intensity_mode == VRG_INTENSITY_INDEX ? (uintptr_t)p.index : (uintptr_t)p.data;
+    if (((size_t)p.X * elem) % 16 == 0 && (src_base & 15) == 0 && !h->force_ldg) {
         const size_t stage_bytes = ((size_t)p.segw * 32 * elem + 127) & ~(size_t)127;
         const size_t per = per_warp + HIST_STAGES * stage_bytes + HIST_STAGES * 8;
         const int hw = (int)std::min<size_t>(16, (227 * 1024 - 256) / per);
@@ -677,7 +678,7 @@ static int enqueue_sweep(vrg_handle *h) {
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     if (h->cfg.intensity_mode == VRG_INTENSITY_F64_DENSE) {
         const size_t dsm = dense_smem_bytes(p);
-        if ((p.X & 1) == 0 && dsm <= 227 * 1024 && !h->force_ldg) {  // TMA ring: 16-byte aligned row segments
+        if ((p.X & 1) == 0 && (((uintptr_t)p.data) & 15) == 0 && dsm <= 227 * 1024 && !h->force_ldg) {  // TMA ring: 16-byte aligned row segments
             if (!h->dense_attr_set) {
                 CK(cudaFuncSetAttribute(k_sweep_dense<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 CK(cudaFuncSetAttribute(k_sweep_dense<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

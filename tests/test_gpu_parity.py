@@ -361,3 +361,24 @@ def test_random_cases_match_oracle(i):
         assert o["iterations"] == ref["iterations"] and o["exit_reason"] == ref["exit"], mode
         assert np.array_equal(o["trace"], ref["trace"]), mode
         assert np.array_equal(o["labels"], ref["labels"]), mode
+
+
+def test_attach_device_with_an_8_byte_aligned_buffer():
+    """A resident intensity buffer that is only 8-byte aligned cannot feed the TMA bulk copies (16-byte source alignment):
+    the sweep and the init histogram fall back to plain loads and the result is the same."""
+    import torch
+    from arterynetwork_b200.engine import VRGEngine
+    g = load_golden("forest40")
+    n = g["data"].size
+    raw = torch.empty(n + 1, dtype=torch.float64, device="cuda")
+    d = raw[1:]
+    assert d.data_ptr() % 16 == 8
+    d.copy_(torch.from_numpy(np.ascontiguousarray(g["data"], dtype=np.float64).ravel()))
+    v = torch.from_numpy(g["value_map_in"].astype(np.uint8)).cuda()
+    for mode in ("f64_dense", "f64_band"):
+        with VRGEngine(g["data"].shape, max_segment_size=g["max_segment_size"], intensity=mode) as eng:
+            eng.attach_device(d.data_ptr(), v.data_ptr())
+            eng.init()
+            res = eng.run()
+            assert res["iterations"] == g["iterations"]
+            assert np.array_equal(eng.labels(), g["labels"]) and np.array_equal(eng.trace(), g["trace"])
