@@ -36,6 +36,11 @@ def _case(name):
         data, vm, _ = make_phantom((24, 28, 32), seed=2, cell=(24, 28, 32), margin=3, depth=3, root_r2=9,
                                    min_len=6, max_len=10)
         return data, vm, 60
+    if name == "manylevels":  # more than 4095 distinct levels per slab: the level gather grows to its large form
+        data, vm, _ = make_phantom((20, 20, 24), seed=2, cell=(20, 20, 24), margin=3, depth=2, root_r2=4, min_len=5,
+                                   max_len=8)
+        data = data + np.random.default_rng(9).normal(0, 1e-3, data.shape)  # 9600 distinct values
+        return data, vm, 10 ** 12
     raise KeyError(name)
 
 
@@ -60,7 +65,7 @@ def _worker(rank, world, port, name, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("forest", 2), ("excl", 2), ("forest", 3), ("maxseg", 2)])
+@pytest.mark.parametrize("name,world", [("forest", 2), ("excl", 2), ("forest", 3), ("maxseg", 2), ("manylevels", 2)])
 def test_slab_driver_equals_whole_volume_oracle(name, world, tmp_path):
     from oracle.vrg_oracle import vrg_oracle
     data, vm, max_seg = _case(name)
