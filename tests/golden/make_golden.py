@@ -143,6 +143,57 @@ def case_excl_cont():  # continuous intensities AND label 4: absorbed voxels joi
     return data, 0, vm, dict(H=2.25, max_segment_size=None)
 
 
+def _tube_k(seed, q=128, sigma=0.12, shape=(16, 16, 28)):
+    data = np.zeros(shape)
+    data[6:10, 6:10, 4:24] = 1.0
+    return np.round((data + np.random.default_rng(seed).normal(0, sigma, shape)) * q).astype(np.int64)
+
+
+def case_forest48_s1():  # a second forest, other seed and size
+    k, q, vm = _phantom_k((48, 48, 48), 1, cell=(48, 48, 48), margin=4, depth=3, root_r2=9, min_len=9, max_len=18)
+    return k, q, vm.astype(np.int64), dict(H=2.25, max_segment_size=None)
+
+
+def case_forest_two_trees():  # two trees (two seeds), anisotropic volume, rows longer than 64 voxels
+    k, q, vm = _phantom_k((40, 56, 72), 2, cell=(40, 56, 36), margin=4, depth=3, root_r2=9, min_len=8, max_len=14)
+    return k, q, vm.astype(np.int64), dict(H=2.25, max_segment_size=None)
+
+
+def case_tube_h4():  # narrow Parzen kernel
+    k = _tube_k(5)
+    vm = np.full(k.shape, 3)
+    vm[7:9, 7:9, 13:15] = 0
+    return k, 128, vm, dict(H=4.0, max_segment_size=None)
+
+
+def case_tube_two_seeds():  # two seeds in one tube: the fronts meet and merge
+    k = _tube_k(6)
+    vm = np.full(k.shape, 3)
+    vm[7:9, 7:9, 6:8] = 0
+    vm[7:9, 7:9, 20:22] = 0
+    return k, 128, vm, dict(H=2.25, max_segment_size=None)
+
+
+def case_int_levels():  # integer data, a handful of levels (the self-tests' dtype, VRG:285,302)
+    k = _tube_k(7, q=1, sigma=0.0) * 3 + np.random.default_rng(7).integers(0, 2, (16, 16, 28))
+    vm = np.full(k.shape, 3)
+    vm[7:9, 7:9, 13:15] = 0
+    return k, 1, vm, dict(H=2.25, max_segment_size=None)
+
+
+def case_excl32_b():  # label 4 on the darkest third only, other tree
+    data, vm, info = make_phantom((32, 32, 32), seed=3, cell=(32, 32, 32), margin=3, depth=3, root_r2=9, min_len=8,
+                                  max_len=12, exclude_below_k=-10)
+    return np.rint(data * 256).astype(np.int64), 256, vm.astype(np.int64), dict(H=2.25, max_segment_size=None)
+
+
+def case_tube_fat_seed():  # seed cube wider than the tube: removals at its sides while it grows along the tube
+    k = _tube_k(8)
+    vm = np.full(k.shape, 3)
+    vm[5:11, 5:11, 10:16] = 0
+    return k, 128, vm, dict(H=2.25, max_segment_size=None)
+
+
 C1_KW = dict(cell=(128, 128, 128), margin=8, depth=4, root_r2=16, min_len=16, max_len=34)
 
 
@@ -166,6 +217,13 @@ CASES = {
     "tube_cont": case_tube_cont,
     "forest_cont": case_forest_cont,
     "excl_cont": case_excl_cont,
+    "forest48_s1": case_forest48_s1,
+    "forest_two_trees": case_forest_two_trees,
+    "tube_h4": case_tube_h4,
+    "tube_two_seeds": case_tube_two_seeds,
+    "int_levels": case_int_levels,
+    "excl32_b": case_excl32_b,
+    "tube_fat_seed": case_tube_fat_seed,
 }
 SMALL = [c for c in CASES if c != "c1_128"]
 
