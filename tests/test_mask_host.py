@@ -33,3 +33,46 @@ def test_argument_errors_raise_before_any_gpu_call():
         gvv.labelVolume(np.ones((4, 4, 4)), maxHop=2)
     with pytest.raises(ValueError):
         gvv.vesselnessToVesselMask(np.zeros((2, 3, 4)), np.ones((2, 3, 5)))
+
+
+def test_run_pair_pruning_rule_of_the_component_merge():
+    """The rule k_cc_merge (csrc/vrg_mask.cu) uses to link a voxel to the previous row -- straight across only if the voxel
+    or its neighbour starts an x-run, the left diagonal only across a background voxel and under the same condition, the
+    right diagonal across a background voxel always -- transcribed to Python and checked exhaustively on all pairs of rows
+    of 7 voxels: it links exactly the pairs of runs that touch (26-connectivity within two rows), each at least once."""
+    import itertools
+    W = 7
+
+    def runs(row):
+        out, start = [], None
+        for x, v in enumerate(list(row) + [0]):
+            if v and start is None:
+                start = x
+            if not v and start is not None:
+                out.append((start, x - 1))
+                start = None
+        return out
+
+    def run_of(rs, x):
+        return next(i for i, (s, e) in enumerate(rs) if s <= x <= e)
+
+    for A in itertools.product([0, 1], repeat=W):
+        ra = runs(A)
+        for B in itertools.product([0, 1], repeat=W):
+            rb = runs(B)
+            touching = {(i, j) for i, (a0, a1) in enumerate(ra) for j, (b0, b1) in enumerate(rb) if a0 - 1 <= b1 and b0 <= a1 + 1}
+            linked = set()
+            for x in range(W):
+                if not A[x]:
+                    continue
+                pstart = x == 0 or not A[x - 1]
+                ql = x > 0 and B[x - 1]
+                if B[x]:
+                    if pstart or not ql:
+                        linked.add((run_of(ra, x), run_of(rb, x)))
+                else:
+                    if ql and (pstart or x < 2 or not B[x - 2]):
+                        linked.add((run_of(ra, x), run_of(rb, x - 1)))
+                    if x + 1 < W and B[x + 1]:
+                        linked.add((run_of(ra, x), run_of(rb, x + 1)))
+            assert linked == touching, (A, B)
