@@ -76,3 +76,60 @@ def test_run_pair_pruning_rule_of_the_component_merge():
                     if x + 1 < W and B[x + 1]:
                         linked.add((run_of(ra, x), run_of(rb, x + 1)))
             assert linked == touching, (A, B)
+
+
+def test_edt_line_pass_transcription_equals_brute_force():
+    """The line pass of the distance transform (k_edt_lines, csrc/vrg_edt.cu) -- lower envelope of parabolas in which the
+    zeros inside a stretch of background are neither pushed nor popped -- transcribed to Python and fuzzed against the plain
+    double loop, infinite inputs (rows without a zero voxel) included."""
+    INF = 1 << 30
+
+    def line_pass(f):
+        n = len(f)
+        ss, tt, gg = [0] * n, [0] * n, [0] * n
+        q, sq, tq, fq, prev = -1, 0, 0, 0, 0
+        for u in range(n):
+            fu = f[u]
+            wanted = (prev > 0 or (u + 1 < n and f[u + 1] > 0)) if fu == 0 else fu < INF
+            prev = fu
+            if not wanted:
+                continue
+            while q >= 0:
+                if (tq - sq) ** 2 + fq <= (tq - u) ** 2 + fu:
+                    break
+                q -= 1
+                if q >= 0:
+                    sq, tq, fq = ss[q], tt[q], gg[q]
+            w = 0
+            if q >= 0:
+                w = 1 + int((u * u - sq * sq + fu - fq) / (2 * (u - sq)))  # truncating division, as in C++
+            if w < n:
+                q += 1
+                sq, tq, fq = u, w, fu
+                ss[q], tt[q], gg[q] = u, w, fu
+        out = [0] * n
+        for u in range(n - 1, -1, -1):
+            while q > 0 and u < tq:
+                q -= 1
+                sq, tq, fq = ss[q], tt[q], gg[q]
+            d = 0 if f[u] == 0 else ((u - sq) ** 2 + fq if q >= 0 else INF)
+            out[u] = min(d, INF)
+        return out
+
+    def brute(f):
+        return [min([INF] + [(u - i) ** 2 + v for i, v in enumerate(f) if v < INF]) for u in range(len(f))]
+
+    rng = np.random.default_rng(0)
+    for _ in range(3000):
+        n = int(rng.integers(1, 40))
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            f = rng.integers(0, 3, n) * rng.integers(0, 30, n)
+        elif kind == 1:
+            f = np.where(rng.random(n) < 0.3, INF, rng.integers(0, 50, n))
+        elif kind == 2:
+            f = (np.minimum(np.arange(n), np.arange(n)[::-1]) ** 2) * int(rng.integers(0, 2))
+        else:
+            f = np.where(rng.random(n) < 0.5, 0, rng.integers(1, 400, n))
+        f = [int(v) for v in f]
+        assert line_pass(f) == brute(f), f
