@@ -21,21 +21,48 @@ def find_nvcc():
     return None
 
 
+FLAGS_STAMP = os.path.join(CSRC, ".build.flags")
+
+
 def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    if any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS):
+        return True
+    try:  # a library built with other flags is stale too (the stamp travels with the .so)
+        with open(FLAGS_STAMP) as f:
+            return f.read() != " ".join(NVCC_FLAGS)
+    except OSError:
+        return False  # prebuilt library without a stamp (e.g. built by hand): trust the time stamps
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libvrg_b200.so.  Several ranks (torchrun, mp.spawn) may get here at once: one of them compiles, under a file
+    lock, into a temporary file that is renamed into place, so nobody ever loads a half-written library."""
     if not force and not stale():
         return LIB
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build %s" % LIB)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
+    import fcntl
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():  # another process built it while this one waited
+                return LIB
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+            try:
+                subprocess.check_call(cmd, cwd=CSRC)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+            with open(FLAGS_STAMP, "w") as f:
+                f.write(" ".join(NVCC_FLAGS))
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

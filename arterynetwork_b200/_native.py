@@ -19,7 +19,9 @@ HALO = 2
 MAX_LEVELS = 65536
 P2P_HANDLE_BYTES = 192
 BUF_SEG, BUF_EXCL, BUF_FLIPS, BUF_CANCELLED, BUF_LOCAL_STATS, BUF_GLOBAL_STATS, BUF_CTRL = range(7)
-ST_N_IN, ST_N_OUT, ST_N_EXCL, ST_N_FLIPS, ST_N_BAND, ST_BAD_LABEL, ST_NONFINITE, ST_EXTRA = 0, 1, 2, 3, 4, 5, 6, 8
+ST_N_IN, ST_N_OUT, ST_N_EXCL, ST_N_FLIPS, ST_N_BAND, ST_BAD_LABEL, ST_NONFINITE, ST_TIME_UP = range(8)
+ST_Q_CANCELLED, ST_Q_ADD_INSIDE, ST_Q_REM_OUTSIDE, ST_Q_REPROMOTED = 8, 9, 10, 11
+ST_EXTRA = 16
 C_STATUS, C_ITER, C_ITER_MAX, C_MAX_SEG, C_APPLY, C_APPLIED, C_TRACE_N, C_SWEEPS = range(8)
 
 
@@ -31,7 +33,8 @@ class Config(ctypes.Structure):
 
 class Result(ctypes.Structure):
     _fields_ = [("iterations", i64), ("exit_reason", i64), ("n_in", i64), ("n_out", i64), ("n_excluded", i64),
-                ("n_levels", i64), ("sweeps", i64), ("kernel_launches", i64)]
+                ("n_levels", i64), ("sweeps", i64), ("kernel_launches", i64), ("q_cancelled", i64),
+                ("q_add_to_inside", i64), ("q_remove_to_outside", i64), ("q_cancel_repromoted", i64)]
 
 
 _SIGS = {
@@ -53,6 +56,11 @@ _SIGS = {
     "vrg_enqueue_absorb": [vp],
     "vrg_enqueue_advance": [vp],
     "vrg_poll": [vp, ctypes.POINTER(Result)],
+    "vrg_apply_flips": [vp, vp, i64, ctypes.POINTER(Result)],
+    "vrg_enqueue_table": [vp],
+    "vrg_p2p_connect_local": [ctypes.POINTER(vp), ctypes.c_int],
+    "vrg_labels_hash": [vp, ctypes.POINTER(ctypes.c_uint64)],
+    "vrg_download_segmented_map_i64": [vp, vp],
     "vrg_profile": [vp, ctypes.c_int],
     "vrg_get_profile": [vp, vp, vp],
     "vrg_buffer_info": [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(i64)],
@@ -95,7 +103,7 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     if build_if_missing and _build.find_nvcc() is not None:
-        _build.build()
+        _build.build()  # serialised across processes by a file lock, written through a temporary file
     if not os.path.exists(_build.LIB):
         raise RuntimeError("vrg_b200: CUDA library %s is missing and cannot be built here (no nvcc); "
                            "there is no CPU fallback" % _build.LIB)

@@ -211,7 +211,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
         return code;
     }
     (void)nvox;  // the input buffers are allocated on the first vrg_upload*; vrg_attach_device needs none
-    p.S = h->d_S; p.F = h->d_F; p.rowflag = h->d_rowflag; p.front = h->d_front; p.unitmap = h->d_unitmap; p.dirty = h->d_dirty; p.stamp = h->d_stamp;
+    p.S = h->d_S; p.F = h->d_F; p.Cq = h->d_C; p.rowflag = h->d_rowflag; p.front = h->d_front; p.unitmap = h->d_unitmap; p.dirty = h->d_dirty; p.stamp = h->d_stamp;
     p.data = h->d_data;
     p.ctrl = h->d_ctrl; p.trace = h->d_trace;
     *out = h;
@@ -582,6 +582,8 @@ static int cont_enqueue_iteration(vrg_handle *h) {
     k_cont_begin<<<1, 32, 0, h->stream>>>(p, q);
     k_cont_decide<<<h->grid, BLOCK, 0, h->stream>>>(p, q);
     k_cancel<MODE_CONT, false><<<h->grid, BLOCK, 0, h->stream>>>(p);
+    k_quirks<<<h->grid, BLOCK, 0, h->stream>>>(p);
+    h->launches++;
     if (p.E != nullptr) {  // label 4: absorb around the flips, and remember which voxels joined the outside region
         CK(cudaMemsetAsync(q.AB, 0, h->plane_bytes, h->stream));
         k_absorb<MODE_CONT, false><<<h->grid, BLOCK, 0, h->stream>>>(p, q.AB);
@@ -722,8 +724,19 @@ int vrg_enqueue_absorb(vrg_handle *h) {
 int vrg_enqueue_flip(vrg_handle *h) {
     NEED_INIT();
     // own planes were flipped inside k_cancel; only a slab with neighbours has halo planes to follow
-    if (h->p.valid_lo == h->p.own_lo && h->p.valid_hi == h->p.own_hi) return VRG_OK;
-    k_flip_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p);
+    if (!(h->p.valid_lo == h->p.own_lo && h->p.valid_hi == h->p.own_hi)) {
+        k_flip_halo<<<h->sms, BLOCK, 0, h->stream>>>(h->p);
+        h->launches++;
+    }
+    k_quirks<<<h->grid, BLOCK, 0, h->stream>>>(h->p);  // order-dependence counters: needs the flipped halo planes
+    h->launches++;
+    CK(cudaGetLastError());
+    return VRG_OK;
+}
+int vrg_enqueue_table(vrg_handle *h) {
+    NEED_INIT();
+    if (h->cfg.intensity_mode == VRG_INTENSITY_CONTINUOUS) return fail(VRG_ERR_ARG, "the continuous mode has no table");
+    k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p);
     h->launches++;
     CK(cudaGetLastError());
     return VRG_OK;
@@ -744,6 +757,10 @@ static int enqueue_p2p_halo_on(vrg_handle *h, int phase, cudaStream_t st) {
     k_p2p_push_halo<<<h->sms, BLOCK, 0, st>>>(h->p, h->q, kinds, 0);
     k_p2p_wait_unpack_halo<<<h->sms, BLOCK, 0, st>>>(h->p, h->q, kinds, 0, phase == 0);
     h->launches += 2;
+    if (phase == 0) {
+        k_quirks<<<h->grid, BLOCK, 0, st>>>(h->p);
+        h->launches++;
+    }
     CK(cudaGetLastError());
     return VRG_OK;
 }
@@ -821,6 +838,50 @@ int vrg_p2p_connect(vrg_handle *h, int rank, int world, const void *all_handles)
     return VRG_OK;
 }
 
+// The same transport for N handles of ONE process (one per device): peer access instead of CUDA IPC mappings.
+int vrg_p2p_connect_local(vrg_handle **hs, int world) {
+    if (!hs || world < 2 || world > P2P_MAX_WORLD) return fail(VRG_ERR_ARG, "world must be 2..%d", P2P_MAX_WORLD);
+    for (int r = 0; r < world; ++r) {
+        if (!hs[r]) return fail(VRG_ERR_ARG, "null handle");
+        if (r && (hs[r]->cfg.z_begin != hs[r - 1]->cfg.z_end || hs[r]->cfg.device == hs[r - 1]->cfg.device))
+            return fail(VRG_ERR_ARG, "handles must own consecutive z-slabs on distinct devices, in rank order");
+    }
+    for (int r = 0; r < world; ++r) {
+        unsigned char dummy[VRG_P2P_HANDLE_BYTES];
+        int rc = vrg_p2p_export(hs[r], world, dummy);  // allocates the receive buffer, flag words and mailbox
+        if (rc != VRG_OK) return rc;
+        CK(cudaSetDevice(hs[r]->cfg.device));
+        for (int o = 0; o < world; ++o) {
+            if (o == r) continue;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, hs[r]->cfg.device, hs[o]->cfg.device));
+            if (!can) return fail(VRG_ERR_ARG, "device %d cannot access device %d's memory", hs[r]->cfg.device, hs[o]->cfg.device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(hs[o]->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+        }
+    }
+    for (int r = 0; r < world; ++r) {
+        vrg_handle *h = hs[r];
+        CK(cudaSetDevice(h->cfg.device));
+        P2P &q = h->q;
+        q.rank = r; q.world = world;
+        q.flags = h->d_flags; q.slots = h->d_slots; q.recv = h->d_recv;
+        for (int o = 0; o < world; ++o) { q.peer_flags[o] = hs[o]->d_flags; q.peer_slots[o] = hs[o]->d_slots; }
+        q.peer_recv[0] = r > 0 ? hs[r - 1]->d_recv : nullptr;
+        q.peer_recv[1] = r + 1 < world ? hs[r + 1]->d_recv : nullptr;
+        if (!h->halo_stream) {
+            CK(cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+        h->p2p_overlap = getenv("VRG_P2P_SERIAL") == nullptr;
+        h->p2p_on = true;
+        h->inited = false;
+    }
+    return VRG_OK;
+}
+
 int vrg_poll(vrg_handle *h, vrg_result *res) {
     NEED_INIT();
     long long ex[ST_EXTRA];
@@ -835,6 +896,8 @@ int vrg_poll(vrg_handle *h, vrg_result *res) {
         res->n_levels = h->p.L;
         res->sweeps = h->h_ctrl[C_SWEEPS];
         res->kernel_launches = h->launches;
+        res->q_cancelled = ex[ST_Q_CANCELLED]; res->q_add_to_inside = ex[ST_Q_ADD_INSIDE];
+        res->q_remove_to_outside = ex[ST_Q_REM_OUTSIDE]; res->q_cancel_repromoted = ex[ST_Q_REPROMOTED];
     }
     return VRG_OK;
 }
@@ -914,7 +977,7 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
     const int check_every = 8;
     const auto t0 = std::chrono::steady_clock::now();
     bool use_graph = !h->prof && h->graph_ok;
-    bool first = true;
+    bool first = true, time_flagged = false;
     while (true) {
         bool launched = false;
         if (use_graph && !first) {
@@ -954,6 +1017,16 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
         if (h->cfg.max_seconds > 0 &&
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= h->cfg.max_seconds) {
             // VRG:97: stop before applying the next flips; the state is that of the last applied update
+            if (h->p2p_on) {
+                // slabs: the ranks' clocks differ, so the exit is taken collectively -- this rank raises a flag in its own
+                // statistics vector, the next exchange sums it, and every rank leaves at the same update (advance_state)
+                if (!time_flagged) {
+                    static const long long one = 1;
+                    CK(cudaMemcpyAsync(h->d_lstats + 2 * h->p.L + ST_TIME_UP, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
+                    time_flagged = true;
+                }
+                continue;
+            }
             h->h_ctrl[C_STATUS] = VRG_EXIT_MAX_TIME;
             CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
             CK(cudaStreamSynchronize(h->stream));
@@ -961,8 +1034,56 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
             break;
         }
     }
+    if (h->p2p_on) {
+        // every rank left the loop at the same update: one more statistics exchange folds in what trailed the last one
+        k_p2p_stats<<<1, STATS_BLOCK, 0, h->stream>>>(h->p, h->q, h->d_gstats, 2);
+        h->launches++;
+        CK(cudaGetLastError());
+        int rc = vrg_poll(h, &r);
+        if (rc != VRG_OK) return rc;
+        if (h->h_ctrl[C_PEER_TIMEOUT]) return fail(VRG_ERR_CUDA, "peer GPU did not answer (p2p timeout)");
+    }
     if (res) *res = r;
     return VRG_OK;
+}
+
+// ---- update() with caller-chosen flips (VRG:124, flipedPoints given) -----------------------------------------
+int vrg_apply_flips(vrg_handle *h, const int64_t *coords, int64_t n, vrg_result *res) {
+    NEED_INIT();
+    if (n < 0 || (n > 0 && !coords)) return fail(VRG_ERR_ARG, "bad flip list");
+    const Params &p = h->p;
+    if (h->cfg.intensity_mode == VRG_INTENSITY_CONTINUOUS) return fail(VRG_ERR_ARG, "vrg_apply_flips needs a level-table mode");
+    if (h->p2p_on || p.valid_lo != p.own_lo || p.valid_hi != p.own_hi) return fail(VRG_ERR_ARG, "vrg_apply_flips runs on a whole-volume handle");
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t z = coords[3 * i], y = coords[3 * i + 1], x = coords[3 * i + 2];
+        if (z < h->cfg.z_begin || z >= h->cfg.z_end || y < 0 || y >= p.Y || x < 0 || x >= p.X)
+            return fail(VRG_ERR_ARG, "flip %lld = (%lld, %lld, %lld) lies outside the volume", (long long)i, (long long)z, (long long)y, (long long)x);
+    }
+    long long *d_coords = nullptr;
+    if (n) {
+        CK(cudaMalloc((void **)&d_coords, (size_t)n * 3 * sizeof(long long)));
+        CK(cudaMemcpyAsync(d_coords, coords, (size_t)n * 3 * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemsetAsync(h->d_F, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_C, 0, h->plane_bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_rowflag, 0, h->rowflag_bytes, h->stream));
+    k_prepare_apply<<<1, 32, 0, h->stream>>>(p);
+    if (n) k_set_flips<<<h->grid, BLOCK, 0, h->stream>>>(p, d_coords, n, h->cfg.z_begin);
+    k_mask_flips<<<h->grid, BLOCK, 0, h->stream>>>(p);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    int rc = vrg_enqueue_cancel(h);
+    if (rc == VRG_OK) rc = vrg_enqueue_absorb(h);
+    if (rc == VRG_OK) rc = vrg_enqueue_flip(h);
+    if (rc == VRG_OK) rc = vrg_enqueue_advance(h);
+    if (rc == VRG_OK) rc = vrg_enqueue_table(h);  // the sums of the new state; its incremental hint does not hold for foreign flips:
+    if (rc == VRG_OK) {
+        static const long long one = 1;
+        CK(cudaMemcpyAsync(h->d_ctrl + C_TABLE_CHANGED, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
+        rc = vrg_poll(h, res);
+    }
+    if (d_coords) { cudaStreamSynchronize(h->stream); cudaFree(d_coords); }
+    return rc;
 }
 
 // FNV-1a over the kernel parameter block: a host that replays captured launches (CUDA graphs) re-captures when it moves
@@ -1034,6 +1155,52 @@ static int download_impl(vrg_handle *h, uint8_t *out, int seg_only) {
     if (rc != VRG_OK) return rc;
     CK(cudaMemcpyAsync(out, h->d_labels, n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return VRG_OK;
+}
+// position-sensitive hash of the own planes' labels (see k_hash_labels): slab hashes add up to the whole volume's
+int vrg_labels_hash(vrg_handle *h, uint64_t *hash_out) {
+    NEED_INIT();
+    if (!hash_out) return fail(VRG_ERR_ARG, "null argument");
+    const size_t n = (size_t)h->nz_own * h->p.plane_vox;
+    if (!h->d_labels) CK(cudaMalloc((void **)&h->d_labels, n));
+    int rc = labels_impl(h, h->d_labels, 0);
+    if (rc != VRG_OK) return rc;
+    unsigned long long *d_out = (unsigned long long *)(h->d_hcount);  // 16 bytes of scratch, 8-byte aligned (cudaMalloc)
+    CK(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), h->stream));
+    k_hash_labels<<<h->grid, BLOCK, 0, h->stream>>>(h->d_labels, (long long)n, (long long)h->cfg.z_begin * h->p.plane_vox, d_out);
+    h->launches++;
+    CK(cudaGetLastError());
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, d_out, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *hash_out = (uint64_t)v;
+    return VRG_OK;
+}
+
+// segmentedMap in the reference's dtype (VRG:45: np.full(shape, 0) is int64): expanded on the device, chunk by chunk
+int vrg_download_segmented_map_i64(vrg_handle *h, int64_t *out) {
+    NEED_INIT();
+    if (!out) return fail(VRG_ERR_ARG, "null buffer");
+    const size_t n = (size_t)h->nz_own * h->p.plane_vox;
+    if (!h->d_labels) CK(cudaMalloc((void **)&h->d_labels, n));
+    int rc = labels_impl(h, h->d_labels, 1);
+    if (rc != VRG_OK) return rc;
+    const size_t chunk = std::min<size_t>(n, (size_t)32 << 20);  // 32 Mi voxels = 256 MiB of int64 per buffer, two buffers
+    long long *stage[2] = {nullptr, nullptr};
+    CK(cudaMalloc((void **)&stage[0], chunk * sizeof(long long)));
+    cudaError_t e = cudaMalloc((void **)&stage[1], chunk * sizeof(long long));
+    if (e != cudaSuccess) { cudaFree(stage[0]); return fail(VRG_ERR_NOMEM, "staging buffer: %s", cudaGetErrorString(e)); }
+    int b = 0;
+    for (size_t off = 0; off < n && e == cudaSuccess; off += chunk, b ^= 1) {
+        const size_t m = std::min(chunk, n - off);
+        k_expand_i64<<<h->grid, BLOCK, 0, h->stream>>>(h->d_labels + off, stage[b], (long long)m);
+        h->launches++;
+        // pageable destination: the copy returns once the chunk is staged, while the next chunk is being expanded
+        e = cudaMemcpyAsync(out + off, stage[b], m * sizeof(long long), cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(stage[0]); cudaFree(stage[1]);
+    if (e != cudaSuccess) return fail(VRG_ERR_CUDA, "segmented map download: %s", cudaGetErrorString(e));
     return VRG_OK;
 }
 int vrg_download_labels(vrg_handle *h, uint8_t *out) { return download_impl(h, out, 0); }

@@ -34,7 +34,9 @@ constexpr int DENSE_WARPS = 14;
 constexpr int DENSE_STAGES = 2;
 constexpr int STAGE_BYTES = WORDS_PER_WARP * 32 * 8;
 
-enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, ST_BAD_LABEL = 5, ST_NONFINITE = 6, ST_EXTRA = 8 };
+enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, ST_BAD_LABEL = 5, ST_NONFINITE = 6, ST_TIME_UP = 7,
+       // cumulative counts of the flip patterns on which the reference's result depends on its list order (k_quirks)
+       ST_Q_CANCELLED = 8, ST_Q_ADD_INSIDE = 9, ST_Q_REM_OUTSIDE = 10, ST_Q_REPROMOTED = 11, ST_EXTRA = 16 };
 enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_TABLE_CHANGED = 8,
        C_EPOCH = 9, C_PEER_TIMEOUT = 10, C_HALO_SEQ = 11, C_HALO_GO = 12, C_WORDS = 16 };  // 9..12: slab runs (vrg_p2p.cuh)
 constexpr long long RUNNING = -1;
@@ -52,6 +54,7 @@ struct Params {
     long long plane_vox;              // Y * X
     // state
     uint32_t *S, *E, *F, *C;          // E, C: nullptr when the run never had label 4
+    uint32_t *Cq;                     // cancelled additions of the front rows (always valid; == C when C != nullptr)
     uint8_t *rowflag;                 // [nzl * Y * nseg]
     uint8_t *unitmap;                 // [nzl * nyb * nseg]: 1 if the sweep unit ever held a segmented voxel (never cleared)
     int *dirty;                       // 2 x [front_cap]: rows the next incremental sweep must re-evaluate (built by k_flip)
@@ -706,7 +709,7 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
             a = a0 & dilate_x1(keepv);
             if (active && a != a0) p.F[widx] = r | a;
         }
-        if (p.C != nullptr && active) p.C[widx] = a0 & ~a;
+        if (active) p.Cq[widx] = a0 & ~a;  // == p.C with label 4 (k_absorb reads it); k_quirks reads the front rows' words
         // Flip in place right here.  Safe against the warps that are reading this row as a neighbour: they use
         // S & ~F, and that value is the same before, between and after the two stores (executed flip: F = 1 both
         // times -> 0; cancelled addition: S = 0 both times -> 0; everything else is untouched).
@@ -744,6 +747,72 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
     if (lane == 0 && d_in) {
         atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_IN], (unsigned long long)d_in);
         atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_OUT], (unsigned long long)(-d_in));
+    }
+}
+
+// k_quirks: counts, over the front rows of the iteration k_cancel just applied, the flip patterns on which the
+// reference's sequential list processing is order-dependent (oracle/vrg_oracle.py counts the same
+// sets as `quirk_potential`).  With S' the segmented plane after the flips, Aex / R the executed additions / removals and
+// Cn the cancelled additions:
+//   cancelled         |Cn|                          Q1, VRG:183-190 then :198 (order-free; part of the semantics)
+//   add_to_inside     |Aex & ~dil26(~S' in volume)| an added voxel with no unsegmented neighbour left: the reference labels
+//                                                   it 1 unconditionally (VRG:202) and corrects it only if a later flip looks (Q2)
+//   remove_to_outside |R & ~dil26(S')|              a removed voxel with no segmented neighbour left: labelled 2 (VRG:174), same (Q2);
+//                                                   both kinds drop out of the reference's delta sums (VRG:232-233, Q3)
+//   cancel_repromoted |Cn & dil26(Aex)|             a cancelled addition next to an executed one: the reference adds it after all
+//                                                   if that neighbour precedes it in the band list ("Q4")
+// A run whose last three counters are zero lies inside the domain where the reference's result is order-free, i.e. where
+// bit-identity with it is defined.  Runs after k_cancel and, on slabs, after the halo planes received the neighbours' flips.
+__global__ void __launch_bounds__(BLOCK) k_quirks(Params p) {
+    if (!p.ctrl[C_HALO_GO]) return;  // snapshot of "this iteration applied its flips", left by k_cancel
+    const int sweep = (int)((unsigned long long)p.ctrl[C_HALO_SEQ] & 0xFFFFFFFFull) - 1;
+    const int *fl = front_list(p, sweep & 1);
+    const int n = fl[0];
+    const int lane = threadIdx.x & 31, nwarps = gridDim.x * WARPS;
+    long long q_c = 0, q_a = 0, q_r = 0, q_p = 0;
+    for (int k = blockIdx.x * WARPS + (threadIdx.x >> 5); k < n; k += nwarps) {
+        const int rr = fl[1 + k];
+        const int sg = rr % p.nseg, t = rr / p.nseg, zl = t / p.Y, y = t % p.Y;
+        const int c = sg * p.segw - 1 + lane;
+        const bool inr = c >= 0 && c < p.XW;
+        const bool active = inr && lane >= 1 && lane <= p.segw;
+        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+        const uint32_t s1 = inr ? p.S[widx] : 0u, f = inr ? p.F[widx] : 0u;
+        const uint32_t cn = active ? p.Cq[widx] : 0u;
+        const uint32_t aex = active ? (f & s1) : 0u, r = active ? (f & ~s1) : 0u;
+        const bool need_f = __ballot_sync(FULL, cn != 0u) != 0u;
+        uint32_t o = s1, a = inr ? s1 : 0xFFFFFFFFu, ax = f & s1;
+        if (inr) {
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int zz = zl + dz;
+                if (zz < p.valid_lo || zz >= p.valid_hi) continue;
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int yy = y + dy;
+                    if ((dz == 0 && dy == 0) || yy < 0 || yy >= p.Y) continue;
+                    const long long i = (long long)zz * p.plane_words + (long long)yy * p.WP + c;
+                    const uint32_t sn = p.S[i];
+                    o |= sn; a &= sn;
+                    if (need_f) ax |= p.F[i] & sn;
+                }
+            }
+        }
+        const uint32_t vm = inr ? valid_mask(p, c) : 0u;
+        const uint32_t dil_s = dilate_x1(o), dil_n = dilate_x1(~a & vm);
+        const uint32_t dil_a = need_f ? dilate_x1(ax) : 0u;
+        q_c += __popc(cn);
+        q_a += __popc(aex & ~dil_n);
+        q_r += __popc(r & ~dil_s);
+        q_p += __popc(cn & dil_a);
+    }
+    q_c = warp_sum(q_c); q_a = warp_sum(q_a); q_r = warp_sum(q_r); q_p = warp_sum(q_p);
+    if (lane == 0) {
+        unsigned long long *ex = (unsigned long long *)p.lstats + 2 * p.L;
+        if (q_c) atomicAdd(&ex[ST_Q_CANCELLED], (unsigned long long)q_c);
+        if (q_a) atomicAdd(&ex[ST_Q_ADD_INSIDE], (unsigned long long)q_a);
+        if (q_r) atomicAdd(&ex[ST_Q_REM_OUTSIDE], (unsigned long long)q_r);
+        if (q_p) atomicAdd(&ex[ST_Q_REPROMOTED], (unsigned long long)q_p);
     }
 }
 
@@ -856,13 +925,18 @@ __device__ __forceinline__ void advance_state(const Params &p) {
     c[C_ITER] += 1;
     c[C_TABLE_CHANGED] = 0;  // k_table of the next iteration raises it again if a decision bit moves
     if (c[C_ITER] > c[C_ITER_MAX]) c[C_STATUS] = 3;        // VRG:58,118
+    else if (g[ST_TIME_UP] != 0) c[C_STATUS] = 1;          // VRG:97 on slabs: some rank's host saw the time budget run out and
+                                                           // raised the flag in its statistics; every rank reads the same sum
 }
 __global__ void k_advance(Params p) {
     if (threadIdx.x == 0 && blockIdx.x == 0) advance_state(p);
 }
 
 // ---------------------------------------------------------------------------------------------
-// init branch of update(), VRG:129-145: bit-planes from the uint8 valueMap, one word (32 voxels) per thread
+// init branch of update(), VRG:129-145: bit-planes from the uint8 valueMap, one word (32 voxels) per thread.
+// Seeds are label 0 (VRG:44); a map that already holds band labels (1 inner, 2 outer: the output of an earlier run) is
+// read as the state those labels describe -- segmented = {0, 1}.  (The reference re-seeds such a map from label 0 alone
+// and then dies at VRG:111 once its outer band list runs empty: tests/test_oracle_golden.py keeps that probe.)
 __global__ void __launch_bounds__(BLOCK) k_init_planes(Params p, const uint8_t *__restrict__ vm, uint32_t *eraw) {
     const int nrows = (p.valid_hi - p.valid_lo) * p.Y, lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * WARPS;
@@ -882,19 +956,21 @@ __global__ void __launch_bounds__(BLOCK) k_init_planes(Params p, const uint8_t *
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     // per-byte compares (0xFF where equal), then the four byte flags gathered into four adjacent bits
-                    const uint32_t z = __vcmpeq4(ws[k], 0u), f = __vcmpeq4(ws[k], 0x04040404u), t = __vcmpeq4(ws[k], 0x03030303u);
+                    // labels 0 / 1 are segmented, 2 / 3 are not, 4 is excluded (a map that a run returned can be fed back in:
+                    // the bands are re-derived from the segmented set); anything above 4 is an error
+                    const uint32_t z = __vcmpleu4(ws[k], 0x01010101u), f = __vcmpeq4(ws[k], 0x04040404u);
                     const int sh = h * 16 + k * 4;
                     s |= (((z & 0x01010101u) * 0x10204080u) >> 28) << sh;  // bytes 0..3 -> bits 0..3
                     e |= (((f & 0x01010101u) * 0x10204080u) >> 28) << sh;
-                    bad |= (z | f | t) != 0xFFFFFFFFu;
+                    bad |= __vcmpleu4(ws[k], 0x04040404u) != 0xFFFFFFFFu;
                 }
             }
         } else {
             for (int b = 0; b < n; ++b) {
                 const uint32_t byte = src[b];
-                s |= (uint32_t)(byte == 0u) << b;
+                s |= (uint32_t)(byte <= 1u) << b;
                 e |= (uint32_t)(byte == 4u) << b;
-                bad |= !(byte == 0u || byte == 3u || byte == 4u);
+                bad |= byte > 4u;
             }
         }
         const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
@@ -1038,9 +1114,9 @@ __global__ void k_init_hist_private(Params p, int hw) {
                     else { n_out++; mine[(l >> 1) * 64 + (l & 1)] += 1; }
                 }
             }
+            pending += nw;  // a lane adds at most one count per word: flushed long before a uint16 bin can wrap, whatever X
+            if (pending > 60000) flush();
         }
-        pending += p.XW;
-        if (pending > 60000) flush();
     }
     flush();
     n_in = warp_sum(n_in); n_out = warp_sum(n_out); n_ex = warp_sum(n_ex);
@@ -1277,6 +1353,79 @@ __global__ void __launch_bounds__(BLOCK) k_labels(Params p, uint8_t *__restrict_
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Position-sensitive 64-bit hash of a label volume (one byte per voxel): sum over the voxels of
+// mix64((global linear index << 3) | label) modulo 2^64.  Additive, so the hashes of z-slabs add up to the hash of the whole
+// volume whatever the partition -- multi-GPU runs are compared with the single-volume oracle by one number per slab.
+__global__ void __launch_bounds__(BLOCK) k_hash_labels(const uint8_t *__restrict__ lab, long long n, long long base,
+                                                       unsigned long long *out) {
+    unsigned long long acc = 0;
+    const long long nth = (long long)gridDim.x * BLOCK;
+    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += nth)
+        acc += mix64(((unsigned long long)(base + i) << 3) | (unsigned long long)lab[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+__global__ void __launch_bounds__(BLOCK) k_expand_i64(const uint8_t *__restrict__ src, long long *__restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// update() with caller-chosen flips (VRG:124, flipedPoints given): the listed voxels' bits go into F ...
+__global__ void __launch_bounds__(BLOCK) k_set_flips(Params p, const long long *__restrict__ coords, long long n, long long z_begin) {
+    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) {
+        const long long z = coords[3 * i] - z_begin + p.own_lo, y = coords[3 * i + 1], x = coords[3 * i + 2];
+        if (z < p.own_lo || z >= p.own_hi || y < 0 || y >= p.Y || x < 0 || x >= p.X) continue;  // the host validated the list
+        atomicOr(&p.F[z * p.plane_words + y * p.WP + (x >> 5)], 1u << (x & 31));
+    }
+}
+// ... and are then restricted to the band voxels (a listed voxel that is in neither band does nothing in the reference
+// beyond absorbing label 4 around it, VRG:167-170,198): row flags, front list and the flip count as the sweep leaves them.
+__global__ void __launch_bounds__(BLOCK) k_mask_flips(Params p) {
+    const int lane = threadIdx.x & 31;
+    const int nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+    const long long nunits = (long long)(p.own_hi - p.own_lo) * nyb * p.nseg;
+    const long long nwarps = (long long)gridDim.x * WARPS;
+    long long flips = 0;
+    Strip st;
+    for (long long u = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); u < nunits; u += nwarps) {
+        const Unit un = decode_unit(p, u, p.own_lo, nyb);
+        const int c = un.sg * p.segw - 1 + lane;
+        st.begin(p, un.zl, un.y0, c, lane);
+        for (int y = un.y0; y < un.y1; ++y) {
+            uint32_t s, inner, outer;
+            st.step(y, s, inner, outer);
+            const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
+            const long long ridx = ((long long)un.zl * p.Y + y) * p.nseg + un.sg;
+            if (p.E != nullptr && outer) outer &= ~p.E[widx];
+            const uint32_t raw = st.active ? p.F[widx] : 0u;
+            const uint32_t f = raw & (inner | outer);
+            if (__ballot_sync(FULL, raw != 0u) == 0u) continue;  // the host cleared F, C and the row flags beforehand
+            if (st.active && f != raw) p.F[widx] = f;
+            if (__ballot_sync(FULL, f != 0u) != 0u && lane == 0) {
+                p.rowflag[ridx] = 1;
+                int *fl = front_list(p, (int)(p.ctrl[C_SWEEPS] & 1));
+                fl[1 + atomicAdd(&fl[0], 1)] = (int)ridx;
+            }
+            flips += __popc(f);
+        }
+    }
+    flips = warp_sum(flips);
+    if (lane == 0 && flips) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_FLIPS], (unsigned long long)flips);
+}
+// bookkeeping in front of an applied flip list: the state k_table leaves in front of a sweep, with the flips forced on
+__global__ void k_prepare_apply(Params p) {
+    if (threadIdx.x || blockIdx.x) return;
+    p.ctrl[C_STATUS] = RUNNING;
+    p.ctrl[C_APPLY] = 1;
+    p.ctrl[C_TABLE_CHANGED] = 1;
+    p.lstats[2 * p.L + ST_N_FLIPS] = 0;
+    front_list(p, (int)(p.ctrl[C_SWEEPS] & 1))[0] = 0;
+    dirty_list(p, (int)((p.ctrl[C_SWEEPS] + 1) & 1))[0] = 0;
 }
 
 }  // namespace vrg

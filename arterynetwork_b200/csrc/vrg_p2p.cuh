@@ -173,9 +173,12 @@ __global__ void __launch_bounds__(BLOCK) k_p2p_wait_unpack_halo(Params p, P2P q,
 constexpr int STATS_BLOCK = 1024;
 __device__ __forceinline__ void advance_state(const Params &p);  // defined with k_advance in vrg_kernels.cuh
 
+// seq_zero: 0 = loop exchange (obeys the run status, ends with the loop bookkeeping); 1 = the exchange after init (sequence
+// number 0 of the epoch); 2 = one more exchange after the exit, on every rank alike, which brings the counters that trail the
+// loop's last exchange (k_quirks of the last applied update runs beside it) into the global statistics.
 __global__ void __launch_bounds__(STATS_BLOCK) k_p2p_stats(Params p, P2P q, long long *gstats, int seq_zero) {
     if (!seq_zero && p.ctrl[C_STATUS] != RUNNING) return;
-    const unsigned long long seq = seq_zero ? ((unsigned long long)p.ctrl[C_EPOCH] << 32) : p2p_seq(p);
+    const unsigned long long seq = seq_zero == 1 ? ((unsigned long long)p.ctrl[C_EPOCH] << 32) : p2p_seq(p);
     const int par = (int)(seq & 1ull), n = 2 * p.L + ST_EXTRA;
     for (int r = 0; r < q.world; ++r) {
         long long *dst = q.peer_slots[r] + ((long long)par * q.world + q.rank) * q.slot_words;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(STATS_BLOCK) k_p2p_stats(Params p, P2P q, long
     __threadfence_system();
     __syncthreads();
     if (!ok) {
-        if (threadIdx.x == 0) { p.ctrl[C_PEER_TIMEOUT] = 1; p.ctrl[C_STATUS] = EXIT_PEER_TIMEOUT; }
+        if (threadIdx.x == 0) { p.ctrl[C_PEER_TIMEOUT] = 1; if (seq_zero != 2) p.ctrl[C_STATUS] = EXIT_PEER_TIMEOUT; }
         return;
     }
     const long long *base = q.slots + (long long)par * q.world * q.slot_words;

@@ -22,9 +22,6 @@ NumPy slab engine (world_size 2); on GPUs it drives ``VRGEngine`` over NCCL.
 """
 from __future__ import annotations
 
-import json
-import os
-
 import numpy as np
 
 from . import _native as nat
@@ -261,129 +258,12 @@ class DistributedVRG:
             first = False
             res = self.e.poll()
             if res["exit_reason"] != nat.EXIT_RUNNING:
-                return res
+                # every rank left at the same update; one more all-reduce folds in the counters that are written after the
+                # loop's last exchange (the order-dependence counters of the last applied update)
+                self._allreduce_stats()
+                return self.e.poll()
 
     def trace(self):
         t = np.array(self.e.trace(), copy=True)
         t[0] = self.init_row
         return t
-
-
-# ------------------------------------------------------------------------------------------------
-def run_bench_distributed(args, workloads, metric, algo_bytes, peak):
-    """bench.py --gpus N under torchrun: strong scaling of the named volume over z-slabs."""
-    import torch
-    import torch.distributed as dist
-    from .engine import VRGEngine
-    import bench
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    shape = bench.workload_shape(args, world)
-    nvox = shape[0] * shape[1] * shape[2]
-    b = slab_bounds(shape[0], world)
-    z0, z1 = b[rank], b[rank + 1]
-    e0, e1 = max(0, z0 - HALO), min(shape[0], z1 + HALO)
-    d_data, d_vm = bench.device_phantom(shape, args.seed, e0, e1 - e0, local)
-    torch.cuda.synchronize()
-    side = torch.cuda.Stream()  # CUDA graphs cannot be captured on the default stream
-    transport = os.environ.get("VRG_TRANSPORT", "p2p")       # p2p: peer-memory kernels; collective: NCCL via torch
-    use_graph = os.environ.get("VRG_GRAPH") == "1"            # CUDA-graph replay of the collective path (experimental)
-    with torch.cuda.stream(side):
-        eng = VRGEngine(shape, max_segment_size=10 ** 15, intensity=args.intensity, device=local, z_begin=z0, z_end=z1)
-        eng.set_stream(side.cuda_stream)
-        drv = DistributedVRG(GpuSlabEngine(eng, local), rank, world, check_every=8, use_graph=use_graph,
-                             transport=transport)
-
-        def step():
-            eng.attach_device(d_data.data_ptr(), d_vm.data_ptr())
-            drv.prepare_levels()
-            drv.init()
-            return drv.run()
-
-        def timed(fn, n):
-            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            dist.barrier()
-            torch.cuda.synchronize()
-            start.record()
-            sweeps = 0
-            for _ in range(n):
-                sweeps += fn()["sweeps"]
-            end.record()
-            dist.barrier()
-            torch.cuda.synchronize()
-            ms = torch.tensor([start.elapsed_time(end)], device="cuda")
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # device time, max over ranks
-            return float(ms.item()), sweeps
-
-        for _ in range(args.warmup):
-            res = step()
-        sampler = bench.ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        l0 = eng.poll()["kernel_launches"]
-        ms, sweeps = timed(step, args.steps)
-        launches = eng.poll()["kernel_launches"] - l0
-        clocks = sampler.stop() if rank == 0 else None
-        res = eng.poll()
-        # per-launch time of the sweep: one eager (un-graphed) step with CUDA events around every sweep launch
-        drv.use_graph = False
-        eng.profile(True)
-        step()
-        prof = eng.get_profile()
-        eng.profile(False)
-        drv.use_graph = use_graph
-        # end to end: every rank uploads its extended slab from pinned host memory and reads its labels back
-        h_data = torch.empty(d_data.shape, dtype=torch.float64, pin_memory=True)
-        h_vm = torch.empty(d_vm.shape, dtype=torch.uint8, pin_memory=True)
-        h_out = torch.empty((z1 - z0,) + tuple(shape[1:]), dtype=torch.uint8, pin_memory=True)
-        h_data.copy_(d_data); h_vm.copy_(d_vm)
-        torch.cuda.synchronize()
-
-        def e2e_step():
-            eng.upload(h_data.numpy(), h_vm.numpy())
-            drv.prepare_levels()
-            drv.init()
-            r = drv.run()
-            nat.check(eng.lib.vrg_download_labels(eng._h, h_out.data_ptr()))
-            return r
-        e2e_step()
-        e2e_ms, e2e_sweeps = timed(e2e_step, args.steps)
-        # checksum of the result labels so runs at different N can be compared
-        lab = torch.from_numpy(h_out.numpy()).to("cuda")
-        cs = torch.stack([(lab == k).sum() for k in range(5)]).to(torch.int64)
-        dist.all_reduce(cs)
-        h2d = torch.tensor([h_data.numel() * 8 + h_vm.numel(), h_out.numel()], device="cuda", dtype=torch.int64)
-        dist.all_reduce(h2d)
-    value = nvox * sweeps / (ms * 1e-3) / 1e9
-    if rank == 0:
-        per_launch_ms = prof["decide_ms"] / max(1, prof["decide_launches"])
-        local_vox = (min(shape[0], z1 + 1) - max(0, z0 - 1)) * shape[1] * shape[2]
-        achieved = algo_bytes * local_vox / (per_launch_ms * 1e-3) / 1e9
-        line = {
-            "metric": metric, "value": value, "unit": "Gvoxel-updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s %dx%dx%d vessel-forest phantom, seed %d" % (args.workload, shape[2], shape[1], shape[0], args.seed),
-                       "intensity_mode": args.intensity, "partition": "z-slabs, %d planes per rank, halo %d" % (z1 - z0, HALO),
-                       "sweeps_per_step": sweeps // args.steps, "segmented_voxels": res["n_in"],
-                       "label_histogram": [int(x) for x in cs.tolist()], "transport": transport, "cuda_graph": bool(use_graph or transport == "p2p"),
-                       "l2": "inputs larger than L2; no flush",
-                       "step": "attach resident slab (zero-copy) + level scan/all-gather + init + all iterations"},
-            "clocks": clocks,
-            "e2e": {"value": nvox * e2e_sweeps / (e2e_ms * 1e-3) / 1e9, "unit": "Gvoxel-updates/s",
-                    "h2d_bytes_per_step": int(h2d[0].item()), "d2h_bytes_per_step": int(h2d[1].item()),
-                    "ms_per_step": e2e_ms / args.steps, "intensity_mode": args.intensity},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak[0], "peak_kind": peak[1],
-                         "unit": "GB/s", "frac": achieved / peak[0], "traffic": None, "ms_per_launch": per_launch_ms,
-                         "algorithmic_bytes_per_launch": algo_bytes * local_vox,
-                         "note": "rank 0's slab (own planes +-1), timed in a separate eager step"},
-        }
-        print(json.dumps(line))
-    eng.close()
-    dist.destroy_process_group()

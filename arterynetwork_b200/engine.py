@@ -137,6 +137,16 @@ class VRGEngine:
     def enqueue_advance(self):
         nat.check(self.lib.vrg_enqueue_advance(self._h))
 
+    def enqueue_table(self):
+        nat.check(self.lib.vrg_enqueue_table(self._h))
+
+    def apply_flips(self, coords) -> dict:
+        """One update() with caller-chosen flips (VRG:124,156-259): ``coords`` = rows of (z, y, x)."""
+        c = np.ascontiguousarray(coords, dtype=np.int64).reshape(-1, 3)
+        r = nat.Result()
+        nat.check(self.lib.vrg_apply_flips(self._h, c.ctypes.data if c.size else None, c.shape[0], ctypes.byref(r)))
+        return self._res(r)
+
     def profile(self, enable=True):
         nat.check(self.lib.vrg_profile(self._h, int(bool(enable))))
 
@@ -183,6 +193,20 @@ class VRGEngine:
         out = np.empty((self.own_planes,) + self.shape[1:], dtype=np.uint8)
         nat.check(self.lib.vrg_download_segmented_map(self._h, out.ctypes.data))
         return out
+
+    def segmented_map_i64(self, out=None) -> np.ndarray:
+        """segmentedMap in the reference's dtype (int64 0/1, VRG:45-46), own planes."""
+        if out is None:
+            out = np.empty((self.own_planes,) + self.shape[1:], dtype=np.int64)
+        assert out.dtype == np.int64 and out.flags.c_contiguous and out.size == self.own_planes * self.shape[1] * self.shape[2]
+        nat.check(self.lib.vrg_download_segmented_map_i64(self._h, out.ctypes.data))
+        return out
+
+    def labels_hash(self) -> int:
+        """Position-sensitive 64-bit hash of the own planes' labels; slab hashes add up (mod 2^64) to the whole volume's."""
+        v = ctypes.c_uint64(0)
+        nat.check(self.lib.vrg_labels_hash(self._h, ctypes.byref(v)))
+        return int(v.value)
 
     def labels_device(self, dev_ptr: int):
         nat.check(self.lib.vrg_labels_device(self._h, nat.vp(dev_ptr)))

@@ -30,7 +30,7 @@ typedef enum {
     VRG_ERR_CUDA = -1,       /* a CUDA call failed (text in vrg_last_error) */
     VRG_ERR_ARG = -2,        /* bad argument / call order */
     VRG_ERR_LEVELS = -3,     /* more than VRG_MAX_LEVELS distinct intensities (continuous data) */
-    VRG_ERR_LABEL = -4,      /* initial valueMap holds a label other than 0, 3, 4 */
+    VRG_ERR_LABEL = -4,      /* initial valueMap holds a label above 4 (0 inside, 1 inner band, 2 outer band, 3 outside, 4 excluded) */
     VRG_ERR_EMPTY_SEED = -5, /* no voxel with label 0 (reference: IndexError at VRG:88) */
     VRG_ERR_NO_BAND = -6,    /* seed has no boundary (reference: IndexError at VRG:88) */
     VRG_ERR_NOMEM = -7,
@@ -79,6 +79,16 @@ typedef struct {
     int64_t n_levels;    /* size of the decision table */
     int64_t sweeps;      /* decide passes executed == iterations (voxel-updates = N * sweeps) */
     int64_t kernel_launches;
+    /* Cumulative counts, over all applied updates, of the flip patterns on which the reference's sequential list
+     * processing (VRG:165-233) is order-dependent -- the same sets oracle/vrg_oracle.py reports as quirk_potential.
+     * q_cancelled is part of the order-free semantics (VRG:183-190 then :198); when the other three are zero the run lies
+     * inside the domain where the reference's result does not depend on its list order, i.e. where bit-identity with it
+     * is defined.  Non-zero: the labels returned are those of the order-free reading. */
+    int64_t q_cancelled;         /* outer-band voxels marked to enter whose segmented neighbours all left (Q1) */
+    int64_t q_add_to_inside;     /* added voxels left without an unsegmented neighbour: stale label 1 in the reference (Q2/Q3) */
+    int64_t q_remove_to_outside; /* removed voxels left without a segmented neighbour: stale label 2 in the reference (Q2/Q3) */
+    int64_t q_cancel_repromoted; /* cancelled additions next to an executed addition: added by the reference if that
+                                    neighbour comes first in its band list ("Q4") */
 } vrg_result;
 
 const char *vrg_last_error(void);
@@ -92,7 +102,8 @@ int vrg_set_stream(vrg_handle *h, void *cuda_stream);
 
 /* inputs: replaces reading dataArray / valueMap, VRG:40-46 ------------------ */
 /* Extended slab = planes [max(0, z_begin-VRG_HALO), min(Z, z_end+VRG_HALO)); the pointers address its first plane.
- * data: float64 intensities; value_map: uint8 labels (0 seed, 3 outside, 4 excluded). */
+ * data: float64 intensities; value_map: uint8 labels (0 seed, 3 outside, 4 excluded).  A map an earlier run returned may
+ * be fed back in: 1 (inner band) is read as segmented, 2 (outer band) as outside, and the bands are re-derived. */
 int vrg_upload(vrg_handle *h, const double *data_host, const uint8_t *value_map_host);
 int vrg_upload_device(vrg_handle *h, const double *data_dev, const uint8_t *value_map_dev);
 int vrg_upload_value_map(vrg_handle *h, const uint8_t *value_map_host); /* new seeds, same data */
@@ -118,6 +129,12 @@ int vrg_enqueue_absorb(vrg_handle *h);  /* 4->3 absorption (VRG:167-168,177-179)
 int vrg_enqueue_flip(vrg_handle *h);    /* segmented ^= executed flips (VRG:173,201) */
 int vrg_enqueue_advance(vrg_handle *h); /* exit tests + trace row (VRG:91-117) */
 int vrg_poll(vrg_handle *h, vrg_result *res); /* synchronises the stream */
+/* One update() call with caller-chosen flips, VRG:124,156-259 (flipedPoints given): coords = n rows of global (z, y, x).
+ * Listed voxels that are in neither band are ignored; the band state machine (cancel rule, absorption, region statistics)
+ * is applied once and the decision table of the NEW state is computed (vrg_get_table).  Whole-volume handles only. */
+int vrg_apply_flips(vrg_handle *h, const int64_t *coords_host, int64_t n, vrg_result *res);
+/* decision table of the current state without a sweep (after vrg_init: the sums the reference's init branch stores) */
+int vrg_enqueue_table(vrg_handle *h);
 
 /* per-kernel device time (CUDA events on the launch stream) accumulated over launches that did real work:
  * index 0 = decide (the stencil sweep), 1 = cancel.  For roofline reporting. */
@@ -149,6 +166,9 @@ int vrg_params_signature(vrg_handle *h, uint64_t *signature);
 #define VRG_P2P_HANDLE_BYTES 192
 int vrg_p2p_export(vrg_handle *h, int world, void *handles_out /* VRG_P2P_HANDLE_BYTES */);
 int vrg_p2p_connect(vrg_handle *h, int rank, int world, const void *all_handles /* world * VRG_P2P_HANDLE_BYTES */);
+/* same transport for N handles that live in ONE process (one per device, peer access enabled here instead of CUDA IPC);
+ * vrg_init / vrg_run must then be called on all of them at the same time, one host thread per handle */
+int vrg_p2p_connect_local(vrg_handle **handles, int world);
 int vrg_enqueue_p2p_halo(vrg_handle *h, int phase); /* 0: flips (+cancelled) after cancel, applied to the halo planes (replaces vrg_enqueue_flip); 1: excluded plane after absorb */
 int vrg_enqueue_p2p_stats(vrg_handle *h);           /* statistics all-reduce + the advance step (replaces vrg_enqueue_advance) */
 
@@ -156,6 +176,12 @@ int vrg_enqueue_p2p_stats(vrg_handle *h);           /* statistics all-reduce + t
 int vrg_download_labels(vrg_handle *h, uint8_t *value_map_out);   /* own planes, canonical labels 0..4 */
 int vrg_download_segmented_map(vrg_handle *h, uint8_t *seg_out);  /* own planes, 0/1 */
 int vrg_labels_device(vrg_handle *h, uint8_t *value_map_dev_out); /* same, into a device buffer */
+/* position-sensitive 64-bit hash of the own planes' canonical labels: sum over voxels of
+ * splitmix64_finalizer((global linear voxel index << 3) | label) mod 2^64.  Additive over z-slabs: the per-rank hashes of a
+ * multi-GPU run add up to the hash of the whole label volume (oracle/c_oracle.py computes the same number on the CPU). */
+int vrg_labels_hash(vrg_handle *h, uint64_t *hash_out);
+/* segmentedMap as the reference returns it (VRG:45-46: np.full(shape, 0) -> int64 0/1), own planes, straight into host memory */
+int vrg_download_segmented_map_i64(vrg_handle *h, int64_t *seg_out);
 /* segmented voxel coordinates (z,y,x) of own planes in C order; returns count via n (cap in rows) */
 int vrg_download_segmented(vrg_handle *h, int64_t *coords_out, int64_t cap, int64_t *n);
 int vrg_get_trace(vrg_handle *h, int64_t *rows_out, int64_t cap_rows, int64_t *n_rows); /* (n_flips,n_in,n_out) */

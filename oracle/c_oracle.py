@@ -37,7 +37,27 @@ def _load():
         _lib.vrg_oracle_run.restype = ctypes.c_int
         _lib.vrg_oracle_run.argtypes = [p, p, i64, i64, i64, ctypes.c_double, i64, i64, p, p, p, i64, p, p,
                                         p, i64, p, i64, p, ctypes.c_int]
+        _lib.vrg_oracle_hash_labels.restype = ctypes.c_uint64
+        _lib.vrg_oracle_hash_labels.argtypes = [p, i64, i64, ctypes.c_int]
     return _lib
+
+
+def hash_labels(labels, base=0, nthreads=0) -> int:
+    """Position-sensitive 64-bit hash of a uint8 label volume whose first voxel has global linear index ``base``: the
+    number ``vrg_labels_hash`` (include/vrg_b200.h) computes on the device.  Slab hashes add up modulo 2^64."""
+    lab = np.ascontiguousarray(labels, dtype=np.uint8)
+    return int(_load().vrg_oracle_hash_labels(lab.ctypes.data, lab.size, int(base), int(nthreads)))
+
+
+def hash_labels_numpy(labels, base=0) -> int:
+    """The same hash in NumPy (small volumes; pins the C version in tests/test_oracle_golden.py)."""
+    lab = np.ascontiguousarray(labels, dtype=np.uint8).ravel().astype(np.uint64)
+    with np.errstate(over="ignore"):
+        z = ((np.arange(lab.size, dtype=np.uint64) + np.uint64(base)) << np.uint64(3)) | lab
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int(z.sum(dtype=np.uint64))
 
 
 def vrg_oracle_c(data, value_map, H=2.25, max_segment_size=5000, iter_max=200, record_tables=False,

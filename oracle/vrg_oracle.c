@@ -295,3 +295,16 @@ int vrg_oracle_run(const double *data, uint8_t *labels, int64_t Z, int64_t Y, in
     free(levels); free(dirty.v); free(Rl.v); free(Al.v);
     return rc;
 }
+
+/* Position-sensitive 64-bit hash of a label volume: sum over voxels of mix64(((base + i) << 3) | label) mod 2^64 -- the
+ * same number arterynetwork_b200's vrg_labels_hash computes on the device (checker side of the multi-GPU parity test:
+ * the hashes of z-slabs add up to the hash of the whole volume). */
+uint64_t vrg_oracle_hash_labels(const uint8_t *lab, int64_t n, int64_t base, int nthreads) {
+    uint64_t acc = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for reduction(+ : acc) schedule(static)
+    for (int64_t i = 0; i < n; i++) acc += mix64(((uint64_t)(base + i) << 3) | (uint64_t)lab[i]);
+    return acc;
+}

@@ -53,7 +53,7 @@ class NumpySlabEngine:
     def init(self):
         self._planes()
         S, E = self._np(self.seg), self._np(self.excl)
-        S[:] = (self.vm == 0) & self.inb
+        S[:] = (self.vm <= 1) & self.inb  # a returned map can be fed back in: labels 0 / 1 are segmented
         E[:] = (self.vm == 4) & self.inb
         E[self.own1] &= ~dil3(S)[self.own1]  # like the kernel: absorbed around seeds on own planes +-1 only
         st = self.local_stats.numpy()
@@ -65,7 +65,7 @@ class NumpySlabEngine:
         st[b + nat.ST_N_IN] = so.sum()
         st[b + nat.ST_N_OUT] = (~so & ~eo).sum()
         st[b + nat.ST_N_EXCL] = eo.sum()
-        st[b + nat.ST_BAD_LABEL] = int((~np.isin(self.vm[self.vlo:self.vhi], (0, 3, 4))).any())
+        st[b + nat.ST_BAD_LABEL] = int((self.vm[self.vlo:self.vhi] > 4).any())
         nonseg = ~S & self.inb
         band = (S & dil3(nonseg)) | (nonseg & ~E & dil3(S))
         st[b + nat.ST_N_BAND] = band[self.own].sum()
@@ -131,6 +131,18 @@ class NumpySlabEngine:
             return
         S, F = self._np(self.seg), self._np(self.flips)
         S ^= F & self.inb  # own planes and the (exchanged) halo planes
+        # order-dependence counters of this update (k_quirks): own planes, looking one plane into the exchanged halos
+        C = self._np(self.cancelled)
+        Fv = F & self.inb
+        aex, rem = Fv & S, Fv & ~S
+        nonseg = ~S & self.inb
+        st = self.local_stats.numpy()
+        b = 2 * self.L
+        o = self.own
+        st[b + nat.ST_Q_CANCELLED] += int(C[o].sum())
+        st[b + nat.ST_Q_ADD_INSIDE] += int((aex & ~dil3(nonseg))[o].sum())
+        st[b + nat.ST_Q_REM_OUTSIDE] += int((rem & ~dil3(S))[o].sum())
+        st[b + nat.ST_Q_REPROMOTED] += int((C & dil3(aex))[o].sum())
 
     def advance(self):
         c = self.ctrl
@@ -156,7 +168,9 @@ class NumpySlabEngine:
         b = 2 * self.L
         return {"iterations": self.ctrl["iter"], "exit_reason": self.ctrl["status"], "n_in": int(g[b + nat.ST_N_IN]),
                 "n_out": int(g[b + nat.ST_N_OUT]), "n_excluded": int(g[b + nat.ST_N_EXCL]), "n_levels": self.L,
-                "sweeps": self.ctrl["sweeps"], "kernel_launches": 0}
+                "sweeps": self.ctrl["sweeps"], "kernel_launches": 0,
+                "q_cancelled": int(g[b + nat.ST_Q_CANCELLED]), "q_add_to_inside": int(g[b + nat.ST_Q_ADD_INSIDE]),
+                "q_remove_to_outside": int(g[b + nat.ST_Q_REM_OUTSIDE]), "q_cancel_repromoted": int(g[b + nat.ST_Q_REPROMOTED])}
 
     def trace(self):
         return np.asarray(self.trace_rows, dtype=np.int64)

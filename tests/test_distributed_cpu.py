@@ -60,7 +60,8 @@ def _worker(rank, world, port, name, out_dir):
     drv.init()
     res = drv.run()
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), labels=eng.labels(), trace=drv.trace(),
-             iterations=res["iterations"], exit=res["exit_reason"], n_in=res["n_in"])
+             iterations=res["iterations"], exit=res["exit_reason"], n_in=res["n_in"],
+             quirks=[res["q_add_to_inside"], res["q_remove_to_outside"], res["q_cancel_repromoted"], res["q_cancelled"]])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,6 +78,9 @@ def test_slab_driver_equals_whole_volume_oracle(name, world, tmp_path):
     for p in parts:  # every rank saw the same global trajectory
         assert int(p["iterations"]) == ref["iterations"] and int(p["exit"]) == ref["exit"]
         assert np.array_equal(p["trace"], ref["trace"])
+        # the order-dependence counters are summed over the slabs (one more all-reduce after the exit)
+        q = ref["quirk_potential"]
+        assert p["quirks"].tolist() == [q["add_to_inside"], q["remove_to_outside"], q["cancel_repromoted"], q["cancelled"]]
 
 
 def test_slab_bounds():

@@ -46,7 +46,8 @@ def _worker(rank, world, port, name, mode, transport, out_dir):
     drv.init()
     res = drv.run()
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), labels=eng.labels(), trace=drv.trace(),
-             iterations=res["iterations"], exit=res["exit_reason"])
+             iterations=res["iterations"], exit=res["exit_reason"], hash=np.uint64(eng.labels_hash()),
+             quirks=[res["q_add_to_inside"], res["q_remove_to_outside"], res["q_cancel_repromoted"], res["q_cancelled"]])
     dist.barrier()
     eng.close()
     dist.destroy_process_group()
@@ -69,3 +70,55 @@ def test_slabs_equal_oracle(name, mode, transport, tmp_path):
     for p in parts:
         assert int(p["iterations"]) == ref["iterations"] and int(p["exit"]) == ref["exit"]
         assert np.array_equal(p["trace"], ref["trace"])
+        q = ref["quirk_potential"]  # summed over the slabs by the exchange after the exit
+        assert p["quirks"].tolist() == [q["add_to_inside"], q["remove_to_outside"], q["cancel_repromoted"], q["cancelled"]]
+    from oracle.c_oracle import hash_labels
+    assert sum(int(p["hash"]) for p in parts) % 2 ** 64 == hash_labels(ref["labels"])  # slab hashes add up
+
+
+def _noisy():
+    from arterynetwork_b200.phantom import make_phantom
+    data, vm, _ = make_phantom((48, 30, 34), seed=1, cell=(48, 30, 34), margin=3, depth=3, root_r2=9, min_len=6, max_len=12,
+                               quantum=16, sigma_k=5)
+    vm[10:40, 8:22, 8:26] = 0  # a big seed across every slab boundary: removals, cancelled and re-promoted additions
+    return data, vm
+
+
+@pytest.mark.parametrize("mode", ["index", "f64_dense"])
+def test_dropin_function_runs_on_every_gpu_from_one_process(mode):
+    """variationalRegionGrowing() itself on z-slabs over all GPUs of the box -- no torchrun, one process, one host thread per
+    GPU, peer access instead of CUDA IPC (module switch DEVICES): same labels, stdout and counters as the whole-volume oracle."""
+    import contextlib
+    import io
+    import torch
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from arterynetwork_b200 import variationalRegionGrowing as mod
+    from oracle.c_oracle import vrg_oracle_c
+    keep = (mod.DEVICES, mod.INTENSITY, mod.MAX_SECONDS)
+    try:
+        mod.DEVICES, mod.INTENSITY = "all", mode
+        for case in ("forest", "excl", "noisy"):
+            data, vm = _noisy() if case == "noisy" else _case(case)[:2]
+            ref = vrg_oracle_c(data, vm, max_segment_size=10 ** 12)
+            vm64 = vm.astype(np.int64)
+            with contextlib.redirect_stdout(io.StringIO()) as buf, __import__("warnings").catch_warnings():
+                __import__("warnings").simplefilter("ignore")
+                segmented, seg_map, out = mod.variationalRegionGrowing(data, vm64, maxSegmentSize=10 ** 12)
+            assert out is vm64 and np.array_equal(vm64, ref["labels"]), case
+            assert np.array_equal(seg_map == 1, ref["seg"]) and np.array_equal(segmented, np.argwhere(ref["seg"]))
+            assert buf.getvalue().startswith("Finished at iteration %d\n" % ref["iterations"])
+            q = ref["quirk_potential"]
+            r = mod.LAST_RUN
+            assert (r["q_add_to_inside"], r["q_remove_to_outside"], r["q_cancel_repromoted"], r["q_cancelled"]) == (
+                q["add_to_inside"], q["remove_to_outside"], q["cancel_repromoted"], q["cancelled"]), case
+        # the wall-clock exit is collective on slabs: every rank leaves at the same update (and nobody hangs)
+        mod.MAX_SECONDS = 1e-9
+        data, vm = _case("forest")[:2]
+        vm64 = vm.astype(np.int64)
+        with contextlib.redirect_stdout(io.StringIO()) as buf:
+            mod.variationalRegionGrowing(data, vm64, maxSegmentSize=10 ** 12)
+        assert "(Max time reached)" in buf.getvalue()
+    finally:
+        mod.DEVICES, mod.INTENSITY, mod.MAX_SECONDS = keep

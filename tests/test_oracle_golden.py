@@ -141,3 +141,29 @@ def test_c_oracle_equals_numpy_oracle_on_random_cases(i):
         pytest.skip("a band voxel sits on a numerical tie: summation order decides")
     assert a["iterations"] == b["iterations"] and a["exit"] == b["exit"]
     assert np.array_equal(a["trace"], b["trace"]) and np.array_equal(a["labels"], b["labels"])
+
+
+def test_label_hash_c_equals_numpy_and_adds_over_slabs():
+    """The position-sensitive label hash that carries multi-GPU parity (include/vrg_b200.h: vrg_labels_hash)."""
+    from oracle.c_oracle import hash_labels, hash_labels_numpy
+    lab = np.random.default_rng(0).integers(0, 5, size=(9, 11, 37), dtype=np.uint8)
+    assert hash_labels(lab, base=12345) == hash_labels_numpy(lab, base=12345)
+    plane = 11 * 37
+    parts = [hash_labels(lab[a:b], base=a * plane) for a, b in ((0, 2), (2, 7), (7, 9))]
+    assert sum(parts) % 2 ** 64 == hash_labels(lab)
+    swapped = lab.copy()
+    swapped[0, 0, 0], swapped[0, 0, 1] = 1, 0  # same label histogram, other positions
+    lab[0, 0, 0], lab[0, 0, 1] = 0, 1
+    assert hash_labels(swapped) != hash_labels(lab)
+
+
+@pytest.mark.needs_reference
+def test_reference_dies_on_its_own_output():
+    """Feeding a returned valueMap back in (labels 1 / 2 present): the reference re-seeds from label 0 alone (VRG:44), turns
+    the old inner band into its outer band, never lists the old outer band again (VRG:143: `!= 2`), and dies at VRG:111 once
+    the outer list runs empty.  The drop-in instead resumes from the state the labels describe (tested on the GPU)."""
+    from oracle.ref_harness import run_reference
+    g = load_golden("sphere")
+    with pytest.raises((ValueError, IndexError)):
+        run_reference(g["data"], g["labels"].astype(np.int64), H=g["H"], max_segment_size=g["max_segment_size"],
+                      check_drift=False, record_band=False)
