@@ -342,7 +342,7 @@ def get_neighbours(p, exclude_p=True, shape=None):
 
 def _verdict(name, volume, segmented):
     inside = bool(np.all(volume[tuple(segmented.T)]))
-    complete = np.count_nonzero(volume) == len(segmented)
+    complete = bool(np.count_nonzero(volume) == len(segmented))
     if inside and complete:
         print('{} test passed!'.format(name))
     elif inside:
@@ -351,7 +351,7 @@ def _verdict(name, volume, segmented):
         print('{} test partially failed: Wrong segments included!'.format(name))
     else:
         print('{} test failed!'.format(name))
-    return inside and complete
+    return bool(inside and complete)
 
 
 def test_StraightLine():
