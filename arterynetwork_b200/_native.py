@@ -63,6 +63,7 @@ _SIGS = {
     "vrg_download_segmented_map_i64": [vp, vp],
     "vrg_profile": [vp, ctypes.c_int],
     "vrg_get_profile": [vp, vp, vp],
+    "vrg_get_tail_profile": [vp, vp, ctypes.POINTER(i64)],
     "vrg_buffer_info": [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(i64)],
     "vrg_plane_geometry": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)],
     "vrg_use_separate_global_stats": [vp],

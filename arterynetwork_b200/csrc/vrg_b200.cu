@@ -3,6 +3,7 @@
 #include "../../include/vrg_b200.h"
 #include "vrg_kernels.cuh"
 #include "vrg_p2p.cuh"
+#include "vrg_tail.cuh"
 #include "vrg_parzen.cuh"
 
 #include <algorithm>
@@ -90,6 +91,11 @@ struct vrg_handle {
     uint64_t gsig = 0;
     int64_t glaunches = 0;
     bool graph_ok = true;
+    // fused tail of an iteration (vrg_tail.cuh): one cooperative launch per iteration behind the sweep
+    unsigned int *d_gbar = nullptr;   // device-wide barrier words
+    unsigned long long *d_tail_dbg = nullptr;  // phase timings of the tail kernel (profiling runs)
+    bool tail_ok = true;              // A/B switch VRG_NO_FUSED_TAIL, or the cooperative launch is not available
+    bool tail_checked = false;
 };
 
 static const int HASH_CAP = 1 << 18;
@@ -105,7 +111,7 @@ static const int HASH_CAP = 1 << 18;
     } while (0)
 
 static size_t dense_smem_bytes(const Params &p) {
-    return (size_t)((p.LW * 4 + 127) & ~127) + ((DENSE_WARPS * DENSE_STAGES * 8 + 127) & ~127) +
+    return (size_t)((p.LW * 4 + 127) & ~127) + ((DENSE_WARPS * (DENSE_STAGES * 8 + UNIT_RING * 4) + 127) & ~127) +
            (size_t)DENSE_WARPS * DENSE_STAGES * STAGE_BYTES;
 }
 
@@ -163,6 +169,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     h->grid = h->sms * 8;
     h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;  // A/B switch: plain loads instead of the TMA rings (sweep, init histogram)
     h->graph_ok = getenv("VRG_NO_GRAPH") == nullptr;    // A/B switch: vrg_run stays on plain stream launches
+    h->tail_ok = getenv("VRG_NO_FUSED_TAIL") == nullptr;  // A/B switch: the separate kernels behind the sweep
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     Params &p = h->p;
@@ -183,6 +190,12 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     p.plane_words = (long long)Y * p.WP;
     p.plane_vox = (long long)Y * X;
     p.mhH = -0.5 * cfg->H;
+    p.dirty_lists = cfg->intensity_mode == VRG_INTENSITY_F64_BAND || cfg->intensity_mode == VRG_INTENSITY_INDEX;
+    {   // rows per work unit of the dense sweep: long units on large volumes (fewer window restarts), short ones on thin slabs
+        const long long rows_per_warp = (long long)(h->nz_own + 2) * Y * p.nseg / ((long long)h->sms * DENSE_WARPS);
+        p.dense_rows = rows_per_warp >= 96 ? 8 : 4;  // measured: profiles/README.md (r2b, r2c)
+        if (const char *e = getenv("VRG_DENSE_ROWS")) p.dense_rows = std::max(1, atoi(e));  // A/B switch
+    }
     h->plane_bytes = (size_t)p.nzl * p.plane_words * sizeof(uint32_t);
     h->rowflag_bytes = (size_t)p.nzl * Y * p.nseg;
     const size_t nvox = (size_t)p.nzl * p.plane_vox;
@@ -204,6 +217,10 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     alloc((void **)&h->d_hash, (size_t)HASH_CAP * sizeof(unsigned long long));
     alloc((void **)&h->d_hkeys, (size_t)VRG_MAX_LEVELS * sizeof(unsigned long long));
     alloc((void **)&h->d_hcount, 4 * sizeof(int));
+    alloc((void **)&h->d_gbar, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(h->d_gbar, 0, 4 * sizeof(unsigned int));
+    alloc((void **)&h->d_tail_dbg, (16 + 2 * (size_t)h->sms) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(h->d_tail_dbg, 0, (16 + 2 * (size_t)h->sms) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_ctrl, C_WORDS * sizeof(long long));
     if (e != cudaSuccess) {
         int code = fail(e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA, "allocation: %s", cudaGetErrorString(e));
@@ -224,7 +241,7 @@ int vrg_destroy(vrg_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_data); cudaFree(h->d_vm); cudaFree(h->d_index); cudaFree(h->d_labels);
     cudaFree(h->d_S); cudaFree(h->d_E); cudaFree(h->d_F); cudaFree(h->d_C); cudaFree(h->d_rowflag); cudaFree(h->d_front); cudaFree(h->d_unitmap); cudaFree(h->d_dirty); cudaFree(h->d_stamp);
-    cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hkeys); cudaFree(h->d_hcount);
+    cudaFree(h->d_ctrl); cudaFree(h->d_trace); cudaFree(h->d_hash); cudaFree(h->d_hkeys); cudaFree(h->d_hcount); cudaFree(h->d_gbar); cudaFree(h->d_tail_dbg);
     free_levels(h);
     if (h->cont_alloc) {
         cudaFree(h->cq.pin); cudaFree(h->cq.pout); cudaFree(h->cq.B); cudaFree(h->cq.newlist); cudaFree(h->cq.oldlist);
@@ -543,7 +560,7 @@ static int cont_init(vrg_handle *h) {
     long long c[C_WORDS];
     memset(c, 0, sizeof c);
     c[C_STATUS] = RUNNING; c[C_ITER] = 1; c[C_ITER_MAX] = h->cfg.iter_max; c[C_MAX_SEG] = h->cfg.max_segment_size;
-    c[C_TRACE_N] = 1; c[C_TABLE_CHANGED] = 1; c[C_EPOCH] = ++h->epoch;
+    c[C_TRACE_N] = 1; c[C_FULL_SWEEP] = 1; c[C_EPOCH] = ++h->epoch;
     memcpy(h->h_ctrl, c, sizeof c);
     CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof c, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->d_C, 0, h->plane_bytes, h->stream));
@@ -630,7 +647,7 @@ int vrg_init(vrg_handle *h) {
     memset(c, 0, sizeof c);
     c[C_STATUS] = RUNNING; c[C_ITER] = 1; c[C_ITER_MAX] = h->cfg.iter_max; c[C_MAX_SEG] = h->cfg.max_segment_size;
     c[C_TRACE_N] = 1;
-    c[C_TABLE_CHANGED] = 1;  // the first sweep is a full one
+    c[C_FULL_SWEEP] = 1;  // the first sweep (index 0) is a full one
     c[C_EPOCH] = ++h->epoch;  // same on every rank: sequence numbers of the peer exchanges
     memcpy(h->h_ctrl, c, sizeof c);
     CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof c, cudaMemcpyHostToDevice, h->stream));
@@ -700,7 +717,7 @@ static int enqueue_sweep(vrg_handle *h) {
 }
 int vrg_enqueue_decide(vrg_handle *h) {
     NEED_INIT();
-    k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p);
+    k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p, 0);
     h->launches++;
     return enqueue_sweep(h);
 }
@@ -736,7 +753,7 @@ int vrg_enqueue_flip(vrg_handle *h) {
 int vrg_enqueue_table(vrg_handle *h) {
     NEED_INIT();
     if (h->cfg.intensity_mode == VRG_INTENSITY_CONTINUOUS) return fail(VRG_ERR_ARG, "the continuous mode has no table");
-    k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p);
+    k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p, 0);
     h->launches++;
     CK(cudaGetLastError());
     return VRG_OK;
@@ -789,10 +806,10 @@ int vrg_p2p_export(vrg_handle *h, int world, void *handles_out) {
         const size_t rb = (size_t)2 * P2P_KINDS * 2 * HALO * p.plane_words * sizeof(uint32_t);  // two sequence parities
         const size_t sb = (size_t)2 * world * slot_words * sizeof(long long);
         CK(cudaMalloc((void **)&h->d_recv, rb));
-        CK(cudaMalloc((void **)&h->d_flags, FLAG_WORDS * sizeof(unsigned long long)));
+        CK(cudaMalloc((void **)&h->d_flags, FLAG_WORDS_ALL * sizeof(unsigned long long)));
         CK(cudaMalloc((void **)&h->d_slots, sb));
         CK(cudaMemset(h->d_recv, 0, rb));
-        CK(cudaMemset(h->d_flags, 0, FLAG_WORDS * sizeof(unsigned long long)));
+        CK(cudaMemset(h->d_flags, 0, FLAG_WORDS_ALL * sizeof(unsigned long long)));
         CK(cudaMemset(h->d_slots, 0, sb));
     }
     cudaIpcMemHandle_t *out = (cudaIpcMemHandle_t *)handles_out;
@@ -914,16 +931,75 @@ static int join_halo(vrg_handle *h) {
 }
 
 static int enqueue_table(vrg_handle *h) {
-    k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p);
+    k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p, 0);
     h->launches++;
     return VRG_OK;
 }
 
+// The fused tail serves the table modes without label 4, on a whole volume or on a slab with the peer-memory transport.
+static bool tail_applies(vrg_handle *h) {
+    if (!h->tail_ok || h->cfg.intensity_mode == VRG_INTENSITY_CONTINUOUS || h->p.E != nullptr) return false;
+    if (h->separate_gstats && !h->p2p_on) return false;  // slab driven by a host-side collective transport
+    if (!h->tail_checked) {
+        int coop = 0, nb = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->cfg.device);
+        const int smem_max = TAIL_STAGE_LEVELS * 2 * (int)sizeof(double);
+        cudaFuncSetAttribute(k_tail<MODE_INDEX, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaFuncSetAttribute(k_tail<MODE_INDEX, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaFuncSetAttribute(k_tail<MODE_F64_BAND, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaFuncSetAttribute(k_tail<MODE_F64_BAND, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaFuncSetAttribute(k_tail<MODE_INDEX, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaFuncSetAttribute(k_tail<MODE_INDEX, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaFuncSetAttribute(k_tail<MODE_F64_BAND, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaFuncSetAttribute(k_tail<MODE_F64_BAND, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tail<MODE_F64_BAND, true, false>, TAIL_BLOCK, smem_max);
+        if (!coop || nb < 1 || h->sms < 2) h->tail_ok = false;
+        cudaGetLastError();
+        h->tail_checked = true;
+    }
+    return h->tail_ok;
+}
+
+static int enqueue_tail(vrg_handle *h) {
+    if (h->prof) cudaEventRecord(prof_event(h), h->stream);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(h->sms); cfg.blockDim = dim3(TAIL_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const bool idx = h->cfg.intensity_mode == VRG_INTENSITY_INDEX, lat = h->p.lattice != 0;
+    const int p2p = h->p2p_on ? 1 : 0;
+    const int stage = h->p.L <= TAIL_STAGE_LEVELS ? 1 : 0;
+    cfg.dynamicSmemBytes = stage ? (size_t)2 * h->p.L * sizeof(double) : 0;
+    unsigned long long *dbg = h->prof ? h->d_tail_dbg : nullptr;
+    cudaError_t e;
+#define TAIL_LAUNCH(M, LAT)                                                                                                   \
+    (dbg ? cudaLaunchKernelEx(&cfg, k_tail<M, LAT, true>, h->p, h->q, h->d_gstats, h->d_gbar, p2p, stage, dbg)               \
+         : cudaLaunchKernelEx(&cfg, k_tail<M, LAT, false>, h->p, h->q, h->d_gstats, h->d_gbar, p2p, stage, dbg))
+    if (idx && lat) e = TAIL_LAUNCH(MODE_INDEX, true);
+    else if (idx) e = TAIL_LAUNCH(MODE_INDEX, false);
+    else if (lat) e = TAIL_LAUNCH(MODE_F64_BAND, true);
+    else e = TAIL_LAUNCH(MODE_F64_BAND, false);
+#undef TAIL_LAUNCH
+    if (h->prof) cudaEventRecord(prof_event(h), h->stream);
+    h->launches++;
+    CK(e);
+    return VRG_OK;
+}
+
 static int enqueue_batch(vrg_handle *h, int n) {
+    const bool fused = tail_applies(h);
     for (int k = 0; k < n; ++k) {
         int rc;
         if (h->cfg.intensity_mode == VRG_INTENSITY_CONTINUOUS) {
             if ((rc = cont_enqueue_iteration(h)) != VRG_OK) return rc;
+            continue;
+        }
+        if (fused) {  // the table of this sweep was computed by the previous tail (the first one: vrg_run)
+            if ((rc = enqueue_sweep(h)) != VRG_OK) return rc;
+            if ((rc = enqueue_tail(h)) != VRG_OK) return rc;
             continue;
         }
         const bool overlap = h->p2p_on && h->p2p_overlap && h->p.E == nullptr && h->halo_stream != nullptr;
@@ -963,7 +1039,7 @@ static uint64_t run_signature(const vrg_handle *h) {
     };
     mix(&h->p, sizeof(Params));
     if (h->p2p_on) mix(&h->q, sizeof(P2P));
-    const int64_t extra[3] = {h->cfg.intensity_mode, h->p2p_on, h->force_ldg};
+    const int64_t extra[4] = {h->cfg.intensity_mode, h->p2p_on, h->force_ldg, h->tail_ok};
     mix(extra, sizeof extra);
     return x;
 }
@@ -978,6 +1054,12 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
     const auto t0 = std::chrono::steady_clock::now();
     bool use_graph = !h->prof && h->graph_ok;
     bool first = true, time_flagged = false;
+    if (h->cfg.intensity_mode != VRG_INTENSITY_CONTINUOUS) {
+        // the decision table + bookkeeping in front of the first sweep; every later one is the last phase of the tail kernel
+        // (the separate-kernel path recomputes it in front of each sweep: same stats, same table)
+        int rc = enqueue_table(h);
+        if (rc != VRG_OK) return rc;
+    }
     while (true) {
         bool launched = false;
         if (use_graph && !first) {
@@ -992,7 +1074,11 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
                     h->glaunches = h->launches - l0;
                     h->launches = l0;
                     if (rc == VRG_OK && e == cudaSuccess && cudaGraphInstantiate(&h->gexec, g, 0) == cudaSuccess) h->gsig = sig;
-                    else { h->gexec = nullptr; h->graph_ok = false; }
+                    else {
+                        h->gexec = nullptr; h->graph_ok = false;
+                        if (getenv("VRG_VERBOSE")) fprintf(stderr, "vrg_b200: CUDA graph capture failed (%s / %s): plain stream launches\n",
+                                                           cudaGetErrorString(e), rc == VRG_OK ? "enqueue ok" : vrg_last_error());
+                    }
                     if (g) cudaGraphDestroy(g);
                 } else h->graph_ok = false;  // e.g. the legacy default stream cannot be captured: stay eager
                 cudaGetLastError();
@@ -1043,6 +1129,11 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
         if (rc != VRG_OK) return rc;
         if (h->h_ctrl[C_PEER_TIMEOUT]) return fail(VRG_ERR_CUDA, "peer GPU did not answer (p2p timeout)");
     }
+    if (h->cfg.intensity_mode != VRG_INTENSITY_CONTINUOUS) {  // vrg_get_table: the sums of the state the run leaves behind
+        k_table<<<h->p.LW, TABLE_BLOCK, 0, h->stream>>>(h->p, 1);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     if (res) *res = r;
     return VRG_OK;
 }
@@ -1078,8 +1169,8 @@ int vrg_apply_flips(vrg_handle *h, const int64_t *coords, int64_t n, vrg_result 
     if (rc == VRG_OK) rc = vrg_enqueue_advance(h);
     if (rc == VRG_OK) rc = vrg_enqueue_table(h);  // the sums of the new state; its incremental hint does not hold for foreign flips:
     if (rc == VRG_OK) {
-        static const long long one = 1;
-        CK(cudaMemcpyAsync(h->d_ctrl + C_TABLE_CHANGED, &one, sizeof one, cudaMemcpyHostToDevice, h->stream));
+        k_force_full_sweep<<<1, 32, 0, h->stream>>>(h->p);
+        h->launches++;
         rc = vrg_poll(h, res);
     }
     if (d_coords) { cudaStreamSynchronize(h->stream); cudaFree(d_coords); }
@@ -1099,9 +1190,36 @@ int vrg_params_signature(vrg_handle *h, uint64_t *sig) {
 int vrg_profile(vrg_handle *h, int enable) {
     if (!h) return fail(VRG_ERR_ARG, "null handle");
     h->prof = enable != 0;
+    if (enable) cudaMemsetAsync(h->d_tail_dbg, 0, (16 + 2 * (size_t)h->sms) * sizeof(unsigned long long), h->stream);
     h->ev_used = 0;
     h->prof_ms[0] = h->prof_ms[1] = 0;
     h->prof_n[0] = h->prof_n[1] = 0;
+    return VRG_OK;
+}
+// phase timings of the fused tail kernel, collected while vrg_profile is on: us[0..4] = mean microseconds block 0 spent in
+// phase 1 (cancel rule + flips), the first device-wide barrier, phase 2 (statistics exchange + exit tests; halo exchange on
+// the other blocks), the second barrier, phase 3 (decision table + order-dependence counters); us[5..9] the same for the
+// last block of the grid.
+int vrg_get_tail_profile(vrg_handle *h, double *us, int64_t *launches) {
+    if (!h || !us || !launches) return fail(VRG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long d[16];
+    CK(cudaMemcpy(d, h->d_tail_dbg, sizeof d, cudaMemcpyDeviceToHost));
+    *launches = (int64_t)d[0];
+    if (getenv("VRG_VERBOSE") && d[0]) {  // per-block spread of phase 1 and phase 3
+        std::vector<unsigned long long> b(2 * (size_t)h->sms);
+        CK(cudaMemcpy(b.data(), h->d_tail_dbg + 16, b.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int ph = 0; ph < 2; ++ph) {
+            fprintf(stderr, "vrg_b200: tail phase %d per block (us):", ph ? 3 : 1);
+            for (int i = 0; i < h->sms; ++i) fprintf(stderr, " %.1f", (double)b[(size_t)ph * h->sms + i] / (double)d[0] * 1e-3);
+            fprintf(stderr, "\n");
+        }
+    }
+    for (int i = 0; i < 5; ++i) {
+        us[i] = d[0] ? (double)d[1 + i] / (double)d[0] * 1e-3 : 0.0;
+        us[5 + i] = d[0] ? (double)d[9 + i] / (double)d[0] * 1e-3 : 0.0;
+    }
     return VRG_OK;
 }
 int vrg_get_profile(vrg_handle *h, double *ms_total, int64_t *launches) {

@@ -37,8 +37,13 @@ constexpr int STAGE_BYTES = WORDS_PER_WARP * 32 * 8;
 enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, ST_BAD_LABEL = 5, ST_NONFINITE = 6, ST_TIME_UP = 7,
        // cumulative counts of the flip patterns on which the reference's result depends on its list order (k_quirks)
        ST_Q_CANCELLED = 8, ST_Q_ADD_INSIDE = 9, ST_Q_REM_OUTSIDE = 10, ST_Q_REPROMOTED = 11, ST_EXTRA = 16 };
-enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_TABLE_CHANGED = 8,
-       C_EPOCH = 9, C_PEER_TIMEOUT = 10, C_HALO_SEQ = 11, C_HALO_GO = 12, C_WORDS = 16 };  // 9..12: slab runs (vrg_p2p.cuh)
+enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_FULL_SWEEP = 8,
+       C_EPOCH = 9, C_PEER_TIMEOUT = 10, C_HALO_SEQ = 11, C_HALO_GO = 12,  // 9..12: slab runs (vrg_p2p.cuh)
+       // C_FULL_SWEEP: 1 + index of the latest sweep that must look at every band voxel (first sweep of a run, a sweep behind a
+       // changed decision table, a sweep behind caller-chosen flips); every other band / index sweep is incremental.  A stamp,
+       // not a flag: whoever builds a table writes it, nobody has to clear it.
+       C_NEXT_UNIT = 13,  // dense sweep: work-unit counter (units beyond the statically assigned ones are handed out dynamically)
+       C_WORDS = 16 };
 constexpr long long RUNNING = -1;
 
 enum { MODE_F64_DENSE = 0, MODE_F64_BAND = 1, MODE_INDEX = 2, MODE_CONT = 3 };  // MODE_CONT: no level table (vrg_parzen.cuh)
@@ -47,6 +52,8 @@ struct Params {
     // geometry
     int Y, X, XW, WP, nseg, segw;    // rows, voxels/row, words/row, word pitch, warp segments per row, words per segment (<= 30)
     int nzl;                          // local planes incl. halos
+    int dense_rows;                   // rows per work unit of the dense sweep (8 on large volumes, 4 on thin slabs)
+    int dirty_lists;                  // 1: the band / index sweeps' incremental pass wants the dirty-row lists (k_cancel builds them)
     int own_lo, own_hi;               // local plane range owned
     int valid_lo, valid_hi;           // local planes that lie inside the global volume
     uint32_t tail_mask;               // valid bits of word XW-1
@@ -165,50 +172,89 @@ __global__ void __launch_bounds__(BLOCK) k_kmat(Params p, double *kmat) {
 // k_table: one block per 32 levels; a warp sums one level's two Parzen sums over all levels.
 // Fixed order: lane-strided partial sums, then an xor-shuffle tree -> deterministic.
 constexpr int TABLE_BLOCK = 1024;  // 32 warps: one level per warp, one decision word per block
-__global__ void __launch_bounds__(TABLE_BLOCK) k_table(Params p) {
-    if (p.ctrl[C_STATUS] != RUNNING) return;
-    const long long *g = p.gstats;
-    const long long n_in = g[2 * p.L + ST_N_IN], n_out = g[2 * p.L + ST_N_OUT];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        p.ctrl[C_APPLY] = n_in < p.ctrl[C_MAX_SEG];  // cap is tested before the flips are applied, VRG:101
-        p.lstats[2 * p.L + ST_N_FLIPS] = 0;
-        front_list(p, (int)(p.ctrl[C_SWEEPS] & 1))[0] = 0;
-        dirty_list(p, (int)((p.ctrl[C_SWEEPS] + 1) & 1))[0] = 0;  // this iteration's flips fill it for the next sweep
+
+// loop bookkeeping in front of a sweep (one thread): the cap test of VRG:101 and the resets of what the sweep accumulates
+__device__ __forceinline__ void prepare_sweep(const Params &p) {
+    p.ctrl[C_APPLY] = p.gstats[2 * p.L + ST_N_IN] < p.ctrl[C_MAX_SEG];  // cap is tested before the flips are applied, VRG:101
+    p.lstats[2 * p.L + ST_N_FLIPS] = 0;
+    front_list(p, (int)(p.ctrl[C_SWEEPS] & 1))[0] = 0;
+    dirty_list(p, (int)((p.ctrl[C_SWEEPS] + 1) & 1))[0] = 0;  // this iteration's flips fill it for the next sweep
+    p.ctrl[C_NEXT_UNIT] = 0;
+}
+
+// the two normalised Parzen sums of level b (one warp; fixed order: lane-strided partial sums in increasing level order, then
+// an xor tree) and its decision bit.  A level absent from both regions is never looked up: bit 0, sums untouched.
+// hist(c, hi, ho) hands out the two region counts of level c as doubles (global statistics, or a copy staged in shared
+// memory).  Loads come in batches with nothing conditional between them: a `skip the empty level` branch in front of
+// the kernel-matrix load made every step two dependent L2 round trips, 15 us for 468 levels.  Batches of eight.  (Adding the +0.0 of an empty
+// level changes no bit of the sums.)
+template <typename Hist>
+__device__ __forceinline__ uint32_t table_level_from(const Params &p, int b, int lane, double n_in, double n_out, Hist hist) {
+    {
+        double hb, ob;
+        hist(b, hb, ob);
+        if (hb + ob == 0.0) return 0u;
     }
+    const double lb = p.levels[b];
+    const double *krow = p.kmat != nullptr ? p.kmat + (size_t)b * p.L : nullptr;
+    double si = 0.0, so = 0.0;
+    constexpr int TB = 8;  // kernel-matrix loads in flight per lane
+    for (int c0 = lane; c0 < p.L; c0 += 32 * TB) {
+        double kv[TB];
+#pragma unroll
+        for (int k = 0; k < TB; ++k) {
+            const int c = c0 + 32 * k;
+            kv[k] = 0.0;
+            if (c < p.L) {
+                if (krow != nullptr) kv[k] = krow[c];  // same expression, evaluated once per level set
+                else {
+                    const double diff = p.levels[c] - lb;
+                    kv[k] = 0.3989422804014327 * exp(p.mhH * (diff * diff));  // A * exp(-0.5*H*d^2), VRG:7,154
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TB; ++k) {
+            const int c = c0 + 32 * k;
+            double hi = 0.0, ho = 0.0;
+            if (c < p.L) hist(c, hi, ho);
+            si += hi * kv[k];
+            so += ho * kv[k];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        si += __shfl_xor_sync(FULL, si, o);
+        so += __shfl_xor_sync(FULL, so, o);
+    }
+    const double pi = si / n_in, po = so / n_out;  // VRG:81-82
+    if (lane == 0) { p.pin[b] = pi; p.pout[b] = po; }
+    return pi >= po ? 1u : 0u;  // ties go inside, VRG:87
+}
+__device__ __forceinline__ uint32_t table_level(const Params &p, int b, int lane) {
+    const long long *g = p.gstats;  // read through L2
+    const double n_in = (double)__ldcg(g + 2 * p.L + ST_N_IN), n_out = (double)__ldcg(g + 2 * p.L + ST_N_OUT);
+    return table_level_from(p, b, lane, n_in, n_out, [&](int c, double &hi, double &ho) {
+        hi = (double)__ldcg(g + c);
+        ho = (double)__ldcg(g + p.L + c);
+    });
+}
+
+// final: the table of the state a finished run leaves behind (no bookkeeping, whatever the status) -- vrg_get_table then
+// describes the final state on every path
+__global__ void __launch_bounds__(TABLE_BLOCK) k_table(Params p, int final) {
+    if (!final && p.ctrl[C_STATUS] != RUNNING) return;
+    if (!final && blockIdx.x == 0 && threadIdx.x == 0) prepare_sweep(p);
     __shared__ uint32_t s_bits[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 32 + warp;
-    uint32_t mybit = 0;
-    if (b < p.L && g[b] + g[p.L + b] != 0) {  // a level absent from both regions is never looked up
-        const double lb = p.levels[b];
-        double si = 0.0, so = 0.0;
-        for (int c = lane; c < p.L; c += 32) {
-            const long long hi = g[c], ho = g[p.L + c];
-            if ((hi | ho) == 0) continue;
-            double kv;
-            if (p.kmat != nullptr) kv = p.kmat[(size_t)b * p.L + c];  // same expression, evaluated once per level set
-            else {
-                const double diff = p.levels[c] - lb;
-                kv = 0.3989422804014327 * exp(p.mhH * (diff * diff));  // A * exp(-0.5*H*d^2), VRG:7,154
-            }
-            si += (double)hi * kv;
-            so += (double)ho * kv;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            si += __shfl_xor_sync(FULL, si, o);
-            so += __shfl_xor_sync(FULL, so, o);
-        }
-        const double pi = si / (double)n_in, po = so / (double)n_out;  // VRG:81-82
-        if (lane == 0) { p.pin[b] = pi; p.pout[b] = po; }
-        if (pi >= po) mybit = 1u << warp;  // ties go inside, VRG:87
-    }
+    const uint32_t mybit = b < p.L ? table_level(p, b, lane) << warp : 0u;
     if (lane == 0) s_bits[warp] = mybit;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t w = 0;
         for (int i = 0; i < 32; ++i) w |= s_bits[i];
-        if (p.dbits[blockIdx.x] != w) p.ctrl[C_TABLE_CHANGED] = 1;  // the next sweep must look at every band voxel
+        if (p.dbits[blockIdx.x] != w) p.ctrl[C_FULL_SWEEP] = p.ctrl[C_SWEEPS] + 1;  // the sweep behind this table looks at every band voxel
         p.dbits[blockIdx.x] = w;
     }
 }
@@ -360,7 +406,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
     long long flips = 0;
     Strip st;
     const bool single_slab = p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
-    if (single_slab && p.ctrl[C_TABLE_CHANGED] == 0) {
+    if (single_slab && p.ctrl[C_FULL_SWEEP] != p.ctrl[C_SWEEPS] + 1) {
         const int *dl = dirty_list(p, (int)(p.ctrl[C_SWEEPS] & 1));  // built by the previous iteration's k_flip
         const int n = dl[0];
         for (int i = (int)warp0; i < n; i += (int)nwarps) {
@@ -413,51 +459,14 @@ __device__ __forceinline__ void tma_bulk_load(void *smem_dst, const void *gmem_s
                  : "memory");
 }
 
-// The rows of one warp of the dense sweep, walked twice (TMA prefetcher, consumer).  Two partitions of the row space:
-//  * round-robin units of ROWS_PER_UNIT rows (large volumes: at any moment the whole machine streams one compact
-//    window of memory, which is kind to the TLB and the DRAM pages);
-//  * one contiguous range of rows per warp, all of the same length +-1 (slabs with few planes, where whole units
-//    would leave the warps with 2 or 3 units each and a 20-30 % tail).
-// `fresh` marks the rows at which the sliding window must be (re)started.
-struct RowCursor {
-    bool rr, fresh;
-    int zlo, nyb, zl, sg, y, y1;
-    long long u, nunits, stride;  // round-robin
-    long long r, r_end;           // contiguous: flattened row index ((zl - zlo) * nseg + sg) * Y + y
-    __device__ __forceinline__ void load_unit(const Params &p) {
-        if (u < nunits) { const Unit un = decode_unit(p, u, zlo, nyb); zl = un.zl; sg = un.sg; y = un.y0; y1 = un.y1; }
-    }
-    __device__ __forceinline__ void start(const Params &p, long long w, long long nwarps, int zlo_, int zhi_) {
-        zlo = zlo_; fresh = true;
-        nyb = (p.Y + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
-        nunits = (long long)(zhi_ - zlo_) * nyb * p.nseg;
-        rr = nunits >= 8 * nwarps;
-        if (rr) { u = w; stride = nwarps; load_unit(p); }
-        else {
-            const long long nrows = (long long)(zhi_ - zlo_) * p.nseg * p.Y;
-            r = nrows * w / nwarps; r_end = nrows * (w + 1) / nwarps;
-            if (r < r_end) {
-                y = (int)(r % p.Y);
-                const long long t = r / p.Y;
-                sg = (int)(t % p.nseg);
-                zl = zlo + (int)(t / p.nseg);
-            }
-        }
-    }
-    __device__ __forceinline__ bool valid() const { return rr ? u < nunits : r < r_end; }
-    __device__ __forceinline__ void next(const Params &p) {
-        fresh = false;
-        if (rr) {
-            if (++y >= y1) { u += stride; fresh = true; load_unit(p); }
-        } else {
-            ++r;
-            if (++y >= p.Y) {
-                y = 0; fresh = true;
-                if (++sg >= p.nseg) { sg = 0; ++zl; }
-            }
-        }
-    }
-};
+// Work distribution of the dense sweep.  A work unit = `dense_rows` consecutive rows of one (plane, segment) column; units are
+// numbered so that consecutive units are consecutive in memory.  Every warp starts with two statically assigned units
+// (w, w + nwarps) and then draws further units from a device-wide counter: at any moment the whole machine streams one
+// compact window of the volume (kind to the TLB and the DRAM pages), and a warp on a slow SM simply takes fewer units, so
+// the kernel has no tail (on an 82-plane slab the static split left the average SM idle for 12 % of the kernel).
+// Lane 0 walks the unit sequence first, as the TMA prefetcher, and hands the unit numbers to the consuming warp through a
+// small ring in shared memory; the counter's latency hides behind a whole unit of work.
+constexpr int UNIT_RING = 8;  // the prefetcher is at most DENSE_STAGES + 1 rows, hence (one-row units) 3 units ahead
 
 // k_sweep_dense: the stencil sweep of the F64_DENSE mode.  Every voxel's decision is evaluated from its fp64 intensity
 // every iteration: the volume is streamed at 8 B/voxel by 1-D TMA bulk copies, one row segment (<= 7680 B) per stage,
@@ -470,10 +479,12 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     uint32_t *s_dbits = (uint32_t *)smem_raw;
     const int dbits_bytes = (p.LW * 4 + 127) & ~127;
     uint64_t *bars = (uint64_t *)(smem_raw + dbits_bytes);                                     // [DENSE_WARPS][DENSE_STAGES]
-    double *stages = (double *)(smem_raw + dbits_bytes + ((DENSE_WARPS * DENSE_STAGES * 8 + 127) & ~127));
+    int *rings = (int *)(bars + DENSE_WARPS * DENSE_STAGES);                                   // [DENSE_WARPS][UNIT_RING]
+    double *stages = (double *)(smem_raw + dbits_bytes + ((DENSE_WARPS * (DENSE_STAGES * 8 + UNIT_RING * 4) + 127) & ~127));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < p.LW; i += DENSE_WARPS * 32) s_dbits[i] = p.dbits[i];
     uint64_t *mybar = bars + warp * DENSE_STAGES;
+    int *myring = rings + warp * UNIT_RING;
     double *mystage = stages + (size_t)warp * DENSE_STAGES * (STAGE_BYTES / 8);
     // the part of a stage that no row segment ever overwrites (beyond the shortest segment: the row's tail, and the
     // words up to the batch width) must hold a valid intensity, since the evaluation below is branch-free
@@ -491,42 +502,66 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy fill before the async-proxy copies
     __syncthreads();
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
-    const long long nwarps = (long long)gridDim.x * DENSE_WARPS;
-    const long long w = (long long)blockIdx.x * DENSE_WARPS + warp;
-    RowCursor pre, cur;
-    pre.start(p, w, nwarps, zlo, zhi);
-    cur.start(p, w, nwarps, zlo, zhi);
-    auto issue = [&](const RowCursor &rc, int s) {  // lane 0 only
-        const int x0 = rc.sg * p.segw * 32;
+    const int R = p.dense_rows;
+    const int nyb = (p.Y + R - 1) / R;
+    const int nwarps = gridDim.x * DENSE_WARPS;
+    const int w = blockIdx.x * DENSE_WARPS + warp;
+    const int nunits = (zhi - zlo) * nyb * p.nseg;
+    unsigned long long *next_unit = (unsigned long long *)&p.ctrl[C_NEXT_UNIT];
+    auto decode = [&](int u, int &zl, int &sg, int &y, int &y1) {
+        sg = u % p.nseg;
+        const int t = u / p.nseg;
+        y = (t % nyb) * R;
+        zl = zlo + t / nyb;
+        y1 = min(p.Y, y + R);
+    };
+    // ---- lane 0: the prefetcher's walk ----
+    int pu = w, pu_next = w + nwarps, pzl = 0, psg = 0, py = 0, py1 = 0, phead = 0;
+    auto pre_enter = [&]() {  // announce the unit to the consumer; ids >= nunits end its walk
+        myring[phead++ & (UNIT_RING - 1)] = pu;
+        if (pu < nunits) decode(pu, pzl, psg, py, py1);
+    };
+    auto pre_issue = [&](int s) {  // one row segment into stage s, then step to the next row
+        const int x0 = psg * p.segw * 32;
         const uint32_t bytes = (uint32_t)min(p.segw * 32, p.X - x0) * 8u;
-        const double *src = p.data + (long long)rc.zl * p.plane_vox + (long long)rc.y * p.X + x0;
+        const double *src = p.data + (long long)pzl * p.plane_vox + (long long)py * p.X + x0;
         mbar_expect_tx(mybar + s, bytes);
         tma_bulk_load(mystage + (size_t)s * (STAGE_BYTES / 8), src, bytes, mybar + s);
-    };
-#pragma unroll
-    for (int s = 0; s < DENSE_STAGES; ++s) {
-        if (pre.valid()) {
-            if (lane == 0) issue(pre, s);
-            pre.next(p);
+        if (++py >= py1) {
+            pu = pu_next;
+            pu_next = pu_next < nunits ? 2 * nwarps + (int)atomicAdd(next_unit, 1ull) : pu_next;  // used a whole unit later
+            pre_enter();
         }
+    };
+    if (lane == 0) {
+        pre_enter();
+#pragma unroll
+        for (int s = 0; s < DENSE_STAGES; ++s)
+            if (pu < nunits) pre_issue(s);
     }
+    __syncwarp();
+    // ---- the consuming warp ----
+    int ctail = 0, cu = myring[ctail++ & (UNIT_RING - 1)], czl = 0, csg = 0, cy = 0, cy1 = 0;
+    bool fresh = true;
+    if (cu < nunits) decode(cu, czl, csg, cy, cy1);
     int stage = 0;
     uint32_t parity = 0;
     long long flips = 0;
     Strip st;
     int c0 = 0;
     bool own = false;
-    while (cur.valid()) {
-        const int y = cur.y;
-        if (cur.fresh) {  // range start or new (plane, segment) column: (re)start the window
-            c0 = cur.sg * p.segw - 1;
-            own = cur.zl >= p.own_lo && cur.zl < p.own_hi;
-            st.begin(p, cur.zl, y, c0 + lane, lane);
+    while (cu < nunits) {
+        const int y = cy;
+        if (fresh) {  // new unit: (re)start the window
+            c0 = csg * p.segw - 1;
+            own = czl >= p.own_lo && czl < p.own_hi;
+            st.begin(p, czl, y, c0 + lane, lane);
+            fresh = false;
         }
         uint32_t s, inner, outer;
         st.step(y, s, inner, outer);
-        const long long widx = (long long)cur.zl * p.plane_words + (long long)y * p.WP + c0 + lane;
-        const long long ridx = ((long long)cur.zl * p.Y + y) * p.nseg + cur.sg;
+        const long long widx = (long long)czl * p.plane_words + (long long)y * p.WP + c0 + lane;
+        const long long ridx = ((long long)czl * p.Y + y) * p.nseg + csg;
         const uint8_t was = p.rowflag[ridx];
         if (p.E != nullptr && outer) outer &= ~p.E[widx];
         const uint32_t band = inner | outer;
@@ -548,27 +583,29 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
             if (jb / BW >= nbatch) break;  // warp-uniform (words past segw hold valid stale data, masked by the band)
             double v[BW];
             int l[BW];
-            uint32_t w[BW];
+            uint32_t wd[BW];
 #pragma unroll
             for (int k = 0; k < BW; ++k) v[k] = sv[(jb + k) * 32];
 #pragma unroll
             for (int k = 0; k < BW; ++k) l[k] = level_of<LATTICE>(p, v[k]);
 #pragma unroll
-            for (int k = 0; k < BW; ++k) w[k] = s_dbits[l[k] >> 5];
+            for (int k = 0; k < BW; ++k) wd[k] = s_dbits[l[k] >> 5];
 #pragma unroll
-            for (int k = 0; k < BW; ++k) mine |= ((w[k] >> (l[k] & 31)) & 1u) << (jb + k + 1);
+            for (int k = 0; k < BW; ++k) mine |= ((wd[k] >> (l[k] & 31)) & 1u) << (jb + k + 1);
         }
         const uint32_t D = transpose32(mine, lane);
         __syncwarp();
-        if (pre.valid()) {  // the stage is drained (values are in registers): re-arm it for a later row
-            if (lane == 0) issue(pre, stage);
-            pre.next(p);
-        }
+        if (lane == 0 && pu < nunits) pre_issue(stage);  // the stage is drained (values are in registers): re-arm it for a later row
         if (++stage == DENSE_STAGES) { stage = 0; parity ^= 1u; }
         const uint32_t f = band & (D ^ s);
         store_flips(p, widx, ridx, was, f, st.active, own, lane);
         if (own) flips += __popc(f);
-        cur.next(p);
+        if (++cy >= cy1) {  // next unit of this warp's sequence (lane 0 wrote it at least a row ago)
+            __syncwarp();
+            cu = myring[ctail++ & (UNIT_RING - 1)];
+            if (cu < nunits) decode(cu, czl, csg, cy, cy1);
+            fresh = true;
+        }
     }
     flips = warp_sum(flips);
     if (lane == 0 && flips) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_FLIPS], (unsigned long long)flips);
@@ -668,6 +705,106 @@ __device__ __forceinline__ void claim_dirty_rows(const Params &p, int zl, int y,
 // iteration (VRG:183-190 then VRG:198).  Rewrites F to the executed flips (race-free: only non-segmented bits are
 // cleared, neighbours read F & S), keeps the cancelled ones in C for the absorb rule, and applies the integer
 // histogram deltas that replace the reference's incremental float sums (VRG:232-247).
+// cancel_row: one front row, one warp.  d_in accumulates this lane's change of the inside region's size.
+// s, f: this lane's words of the segmented and flip planes (0 outside the row), loaded by the caller -- k_tail fetches them for
+// a warp's next row while it works on the current one
+template <int MODE, bool LATTICE>
+__device__ __forceinline__ void cancel_row_loaded(const Params &p, int zl, int y, int sg, int lane, bool dirty, long long &d_in,
+                                                  uint32_t s, uint32_t f) {
+    unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
+    const int c0 = sg * p.segw - 1, c = c0 + lane;
+    const bool inr = c >= 0 && c < p.XW;
+    const bool active = inr && lane >= 1 && lane <= p.segw;
+    const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+    const uint32_t a0 = active ? (f & ~s) : 0u, r = active ? (f & s) : 0u;
+    // The levels of the flipped voxels feed the histogram deltas below (the continuous mode has none: see k_cont_incr).
+    // Word-cooperative: for every 32-voxel word that holds a candidate (removals + additions before the cancel rule) the
+    // whole warp fetches the word's 32 levels in one coalesced load -- a thick vessel's front puts 10-16 flips into one word,
+    // which one lane gathering its own word's voxels paid for with four dependent DRAM round trips.  Four words are in flight
+    // at once, and they start here, beside the neighbour loads of the cancel rule instead of behind them.
+    const long long rowvox0 = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c0 * 32 + lane;
+    unsigned wm = MODE == MODE_CONT ? 0u : __ballot_sync(FULL, (r | a0) != 0u);
+    int wj[4], wl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        wj[k] = wm ? __ffs(wm) - 1 : -1;
+        wm &= wm - 1;  // 0 stays 0
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        wl[k] = (wj[k] >= 0 && (c0 + wj[k]) * 32 + lane < p.X) ? level_at<MODE, LATTICE>(p, rowvox0 + (long long)wj[k] * 32) : 0;
+    uint32_t a = 0;
+    if (__ballot_sync(FULL, a0 != 0u)) {
+        uint32_t keepv = s & ~f;
+        if (inr) {
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int zz = zl + dz;
+                if (zz < p.valid_lo || zz >= p.valid_hi) continue;
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int yy = y + dy;
+                    if ((dz == 0 && dy == 0) || yy < 0 || yy >= p.Y) continue;
+                    const long long i = (long long)zz * p.plane_words + (long long)yy * p.WP + c;
+                    keepv |= p.S[i] & ~p.F[i];
+                }
+            }
+        }
+        a = a0 & dilate_x1(keepv);
+        if (active && a != a0) p.F[widx] = r | a;
+    }
+    if (active) p.Cq[widx] = a0 & ~a;  // == p.C with label 4 (k_absorb reads it); the quirk counters read the front rows' words
+    // Flip in place right here.  Safe against the warps that are reading this row as a neighbour: they use
+    // S & ~F, and that value is the same before, between and after the two stores (executed flip: F = 1 both
+    // times -> 0; cancelled addition: S = 0 both times -> 0; everything else is untouched).
+    const uint32_t done = r | a;  // executed flips
+    if (active && done) {
+        p.S[widx] = s ^ done;
+        p.unitmap[unit_index(p, zl, y, c)] = 1;
+    }
+    if (dirty) claim_dirty_rows(p, zl, y, sg, lane);
+    d_in += __popc(a) - __popc(r);
+    // histogram deltas: lane b of the warp owns voxel b of each fetched word
+    auto deltas = [&](int j, int level) {
+        const uint32_t md = __shfl_sync(FULL, done, j), ma = __shfl_sync(FULL, a, j);
+        if ((md >> lane) & 1u) {
+            const unsigned long long d = (ma >> lane) & 1u ? 1ull : ~0ull;  // entered: +1 inside, -1 outside; left: the reverse
+            atomicAdd(&hin[level], d);
+            atomicAdd(&hout[level], 0ull - d);
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (wj[k] >= 0) deltas(wj[k], wl[k]);  // warp-uniform
+    while (wm) {  // more than four words with flips in one row segment
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            wj[k] = wm ? __ffs(wm) - 1 : -1;
+            wm &= wm - 1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            wl[k] = (wj[k] >= 0 && (c0 + wj[k]) * 32 + lane < p.X) ? level_at<MODE, LATTICE>(p, rowvox0 + (long long)wj[k] * 32) : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (wj[k] >= 0) deltas(wj[k], wl[k]);
+    }
+}
+template <int MODE, bool LATTICE>
+__device__ __forceinline__ void cancel_row(const Params &p, int zl, int y, int sg, int lane, bool dirty, long long &d_in) {
+    const int c = sg * p.segw - 1 + lane;
+    const bool inr = c >= 0 && c < p.XW;
+    const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+    cancel_row_loaded<MODE, LATTICE>(p, zl, y, sg, lane, dirty, d_in, inr ? p.S[widx] : 0u, inr ? p.F[widx] : 0u);
+}
+__device__ __forceinline__ void cancel_finish(const Params &p, long long d_in, int lane) {
+    d_in = warp_sum(d_in);
+    if (lane == 0 && d_in) {
+        atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_IN], (unsigned long long)d_in);
+        atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_OUT], (unsigned long long)(-d_in));
+    }
+}
+
 template <int MODE, bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
     const bool go = p.ctrl[C_STATUS] == RUNNING && p.ctrl[C_APPLY];
@@ -680,74 +817,9 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
     if (!go) return;
     const int lane = threadIdx.x & 31;
     long long d_in = 0;
-    unsigned long long *hin = (unsigned long long *)p.lstats, *hout = hin + p.L;
-    const bool single_slab = p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
-    for_front_rows(p, [&](int zl, int y, int sg) {
-        const int c = sg * p.segw - 1 + lane;
-        const bool inr = c >= 0 && c < p.XW;
-        const bool active = inr && lane >= 1 && lane <= p.segw;
-        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
-        const uint32_t s = inr ? p.S[widx] : 0u, f = inr ? p.F[widx] : 0u;
-        const uint32_t a0 = active ? (f & ~s) : 0u, r = active ? (f & s) : 0u;
-        uint32_t a = 0;
-        if (__ballot_sync(FULL, a0 != 0u)) {
-            uint32_t keepv = s & ~f;
-            if (inr) {
-#pragma unroll
-                for (int dz = -1; dz <= 1; ++dz) {
-                    const int zz = zl + dz;
-                    if (zz < p.valid_lo || zz >= p.valid_hi) continue;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int yy = y + dy;
-                        if ((dz == 0 && dy == 0) || yy < 0 || yy >= p.Y) continue;
-                        const long long i = (long long)zz * p.plane_words + (long long)yy * p.WP + c;
-                        keepv |= p.S[i] & ~p.F[i];
-                    }
-                }
-            }
-            a = a0 & dilate_x1(keepv);
-            if (active && a != a0) p.F[widx] = r | a;
-        }
-        if (active) p.Cq[widx] = a0 & ~a;  // == p.C with label 4 (k_absorb reads it); k_quirks reads the front rows' words
-        // Flip in place right here.  Safe against the warps that are reading this row as a neighbour: they use
-        // S & ~F, and that value is the same before, between and after the two stores (executed flip: F = 1 both
-        // times -> 0; cancelled addition: S = 0 both times -> 0; everything else is untouched).
-        if (active && (r | a)) {
-            p.S[widx] = s ^ (r | a);
-            p.unitmap[unit_index(p, zl, y, c)] = 1;
-        }
-        if (single_slab) claim_dirty_rows(p, zl, y, sg, lane);
-        if (active) {
-            d_in += __popc(a) - __popc(r);
-            const long long rowvox = (long long)zl * p.plane_vox + (long long)y * p.X + (long long)c * 32;
-            // histogram deltas of the flipped voxels (the continuous mode has none: see k_cont_incr).  Their levels are
-            // gathered four at a time: the loads of one batch are independent, a plain bit loop would wait for each.
-            uint32_t m = MODE == MODE_CONT ? 0u : (r | a);
-            while (m) {
-                int bs[4], ls[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    bs[k] = m ? __ffs(m) - 1 : -1;
-                    m &= m - 1;  // 0 stays 0
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) ls[k] = level_at<MODE, LATTICE>(p, rowvox + max(bs[k], 0));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (bs[k] < 0) continue;
-                    const unsigned long long d = (a >> bs[k]) & 1u ? 1ull : ~0ull;  // entered: +1 inside, -1 outside; left: the reverse
-                    atomicAdd(&hin[ls[k]], d);
-                    atomicAdd(&hout[ls[k]], 0ull - d);
-                }
-            }
-        }
-    });
-    d_in = warp_sum(d_in);
-    if (lane == 0 && d_in) {
-        atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_IN], (unsigned long long)d_in);
-        atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_OUT], (unsigned long long)(-d_in));
-    }
+    const bool dirty = p.dirty_lists && p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
+    for_front_rows(p, [&](int zl, int y, int sg) { cancel_row<MODE, LATTICE>(p, zl, y, sg, lane, dirty, d_in); });
+    cancel_finish(p, d_in, lane);
 }
 
 // k_quirks: counts, over the front rows of the iteration k_cancel just applied, the flip patterns on which the
@@ -763,57 +835,65 @@ __global__ void __launch_bounds__(BLOCK) k_cancel(Params p) {
 //                                                   if that neighbour precedes it in the band list ("Q4")
 // A run whose last three counters are zero lies inside the domain where the reference's result is order-free, i.e. where
 // bit-identity with it is defined.  Runs after k_cancel and, on slabs, after the halo planes received the neighbours' flips.
+struct QuirkCounts { int c = 0, a = 0, r = 0, p = 0; };  // per warp and launch: far below 2^31
+__device__ __forceinline__ void quirks_row(const Params &p, int zl, int y, int sg, int lane, QuirkCounts &q) {
+    const int c = sg * p.segw - 1 + lane;
+    const bool inr = c >= 0 && c < p.XW;
+    const bool active = inr && lane >= 1 && lane <= p.segw;
+    const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
+    // read through L2: inside k_tail other blocks wrote these words earlier in the same launch
+    const uint32_t s1 = inr ? __ldcg(p.S + widx) : 0u, f = inr ? __ldcg(p.F + widx) : 0u;
+    const uint32_t cn = active ? __ldcg(p.Cq + widx) : 0u;
+    const uint32_t aex = active ? (f & s1) : 0u, r = active ? (f & ~s1) : 0u;
+    const bool need_f = __ballot_sync(FULL, cn != 0u) != 0u;
+    uint32_t o = s1, a = inr ? s1 : 0xFFFFFFFFu, ax = f & s1;
+    if (inr) {
+#pragma unroll
+        for (int dz = -1; dz <= 1; ++dz) {
+            const int zz = zl + dz;
+            if (zz < p.valid_lo || zz >= p.valid_hi) continue;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = y + dy;
+                if ((dz == 0 && dy == 0) || yy < 0 || yy >= p.Y) continue;
+                const long long i = (long long)zz * p.plane_words + (long long)yy * p.WP + c;
+                const uint32_t sn = __ldcg(p.S + i);
+                o |= sn; a &= sn;
+                if (need_f) ax |= __ldcg(p.F + i) & sn;
+            }
+        }
+    }
+    const uint32_t vm = inr ? valid_mask(p, c) : 0u;
+    const uint32_t dil_s = dilate_x1(o), dil_n = dilate_x1(~a & vm);
+    const uint32_t dil_a = need_f ? dilate_x1(ax) : 0u;
+    q.c += __popc(cn);
+    q.a += __popc(aex & ~dil_n);
+    q.r += __popc(r & ~dil_s);
+    q.p += __popc(cn & dil_a);
+}
+__device__ __forceinline__ void quirks_finish(const Params &p, QuirkCounts q, int lane) {
+    const int qc = __reduce_add_sync(FULL, q.c), qa = __reduce_add_sync(FULL, q.a), qr = __reduce_add_sync(FULL, q.r), qp = __reduce_add_sync(FULL, q.p);
+    if (lane == 0) {
+        unsigned long long *ex = (unsigned long long *)p.lstats + 2 * p.L;
+        if (qc) atomicAdd(&ex[ST_Q_CANCELLED], (unsigned long long)qc);
+        if (qa) atomicAdd(&ex[ST_Q_ADD_INSIDE], (unsigned long long)qa);
+        if (qr) atomicAdd(&ex[ST_Q_REM_OUTSIDE], (unsigned long long)qr);
+        if (qp) atomicAdd(&ex[ST_Q_REPROMOTED], (unsigned long long)qp);
+    }
+}
 __global__ void __launch_bounds__(BLOCK) k_quirks(Params p) {
     if (!p.ctrl[C_HALO_GO]) return;  // snapshot of "this iteration applied its flips", left by k_cancel
     const int sweep = (int)((unsigned long long)p.ctrl[C_HALO_SEQ] & 0xFFFFFFFFull) - 1;
     const int *fl = front_list(p, sweep & 1);
     const int n = fl[0];
     const int lane = threadIdx.x & 31, nwarps = gridDim.x * WARPS;
-    long long q_c = 0, q_a = 0, q_r = 0, q_p = 0;
+    QuirkCounts q;
     for (int k = blockIdx.x * WARPS + (threadIdx.x >> 5); k < n; k += nwarps) {
         const int rr = fl[1 + k];
-        const int sg = rr % p.nseg, t = rr / p.nseg, zl = t / p.Y, y = t % p.Y;
-        const int c = sg * p.segw - 1 + lane;
-        const bool inr = c >= 0 && c < p.XW;
-        const bool active = inr && lane >= 1 && lane <= p.segw;
-        const long long widx = (long long)zl * p.plane_words + (long long)y * p.WP + c;
-        const uint32_t s1 = inr ? p.S[widx] : 0u, f = inr ? p.F[widx] : 0u;
-        const uint32_t cn = active ? p.Cq[widx] : 0u;
-        const uint32_t aex = active ? (f & s1) : 0u, r = active ? (f & ~s1) : 0u;
-        const bool need_f = __ballot_sync(FULL, cn != 0u) != 0u;
-        uint32_t o = s1, a = inr ? s1 : 0xFFFFFFFFu, ax = f & s1;
-        if (inr) {
-#pragma unroll
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int zz = zl + dz;
-                if (zz < p.valid_lo || zz >= p.valid_hi) continue;
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int yy = y + dy;
-                    if ((dz == 0 && dy == 0) || yy < 0 || yy >= p.Y) continue;
-                    const long long i = (long long)zz * p.plane_words + (long long)yy * p.WP + c;
-                    const uint32_t sn = p.S[i];
-                    o |= sn; a &= sn;
-                    if (need_f) ax |= p.F[i] & sn;
-                }
-            }
-        }
-        const uint32_t vm = inr ? valid_mask(p, c) : 0u;
-        const uint32_t dil_s = dilate_x1(o), dil_n = dilate_x1(~a & vm);
-        const uint32_t dil_a = need_f ? dilate_x1(ax) : 0u;
-        q_c += __popc(cn);
-        q_a += __popc(aex & ~dil_n);
-        q_r += __popc(r & ~dil_s);
-        q_p += __popc(cn & dil_a);
+        const int sg = rr % p.nseg, t = rr / p.nseg;
+        quirks_row(p, t / p.Y, t % p.Y, sg, lane, q);
     }
-    q_c = warp_sum(q_c); q_a = warp_sum(q_a); q_r = warp_sum(q_r); q_p = warp_sum(q_p);
-    if (lane == 0) {
-        unsigned long long *ex = (unsigned long long *)p.lstats + 2 * p.L;
-        if (q_c) atomicAdd(&ex[ST_Q_CANCELLED], (unsigned long long)q_c);
-        if (q_a) atomicAdd(&ex[ST_Q_ADD_INSIDE], (unsigned long long)q_a);
-        if (q_r) atomicAdd(&ex[ST_Q_REM_OUTSIDE], (unsigned long long)q_r);
-        if (q_p) atomicAdd(&ex[ST_Q_REPROMOTED], (unsigned long long)q_p);
-    }
+    quirks_finish(p, q, lane);
 }
 
 // k_flip_halo (slab runs only, after the F exchange): S ^= F on the halo planes, so the halo copy of the segmented
@@ -923,7 +1003,6 @@ __device__ __forceinline__ void advance_state(const Params &p) {
     c[C_TRACE_N] = t + 1;
     c[C_APPLIED] += 1;
     c[C_ITER] += 1;
-    c[C_TABLE_CHANGED] = 0;  // k_table of the next iteration raises it again if a decision bit moves
     if (c[C_ITER] > c[C_ITER_MAX]) c[C_STATUS] = 3;        // VRG:58,118
     else if (g[ST_TIME_UP] != 0) c[C_STATUS] = 1;          // VRG:97 on slabs: some rank's host saw the time budget run out and
                                                            // raised the flag in its statistics; every rank reads the same sum
@@ -1422,10 +1501,15 @@ __global__ void k_prepare_apply(Params p) {
     if (threadIdx.x || blockIdx.x) return;
     p.ctrl[C_STATUS] = RUNNING;
     p.ctrl[C_APPLY] = 1;
-    p.ctrl[C_TABLE_CHANGED] = 1;
+    p.ctrl[C_FULL_SWEEP] = p.ctrl[C_SWEEPS] + 1;
     p.lstats[2 * p.L + ST_N_FLIPS] = 0;
     front_list(p, (int)(p.ctrl[C_SWEEPS] & 1))[0] = 0;
     dirty_list(p, (int)((p.ctrl[C_SWEEPS] + 1) & 1))[0] = 0;
+}
+
+// the next sweep must look at every band voxel (after caller-chosen flips)
+__global__ void k_force_full_sweep(Params p) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) p.ctrl[C_FULL_SWEEP] = p.ctrl[C_SWEEPS] + 1;
 }
 
 }  // namespace vrg

@@ -156,6 +156,15 @@ class VRGEngine:
         nat.check(self.lib.vrg_get_profile(self._h, ctypes.addressof(ms), ctypes.addressof(n)))
         return {"decide_ms": ms[0], "decide_launches": int(n[0]), "cancel_ms": ms[1], "cancel_launches": int(n[1])}
 
+    def get_tail_profile(self) -> dict:
+        """Mean microseconds per phase of the fused tail kernel (first / last block of its grid), see vrg_get_tail_profile."""
+        us = (ctypes.c_double * 10)()
+        n = nat.i64(0)
+        nat.check(self.lib.vrg_get_tail_profile(self._h, ctypes.addressof(us), ctypes.byref(n)))
+        names = ("cancel", "barrier1", "stats_exit_halo", "barrier2", "table_counters")
+        return {"launches": int(n.value), "first_block_us": {k: us[i] for i, k in enumerate(names)},
+                "last_block_us": {k: us[5 + i] for i, k in enumerate(names)}}
+
     def use_separate_global_stats(self):
         nat.check(self.lib.vrg_use_separate_global_stats(self._h))
 

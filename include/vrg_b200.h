@@ -137,9 +137,15 @@ int vrg_apply_flips(vrg_handle *h, const int64_t *coords_host, int64_t n, vrg_re
 int vrg_enqueue_table(vrg_handle *h);
 
 /* per-kernel device time (CUDA events on the launch stream) accumulated over launches that did real work:
- * index 0 = decide (the stencil sweep), 1 = cancel.  For roofline reporting. */
+ * index 0 = decide (the stencil sweep), 1 = what follows it (vrg_run: the fused tail kernel -- cancel rule, statistics and
+ * halo exchange, exit tests, next decision table; host-driven iteration: the cancel kernel).  For roofline reporting. */
 int vrg_profile(vrg_handle *h, int enable);
 int vrg_get_profile(vrg_handle *h, double *ms_total /*[2]*/, int64_t *launches /*[2]*/);
+/* phase timings inside the fused tail kernel while vrg_profile is on (device clock): us[0..4] = mean microseconds the
+ * grid's first block spent in phase 1 (cancel rule, flips), the first device-wide barrier, phase 2 (statistics exchange +
+ * exit tests; the other blocks exchange halos), the second barrier, phase 3 (decision table, order-dependence counters);
+ * us[5..9] = the same for the grid's last block. */
+int vrg_get_tail_profile(vrg_handle *h, double *us /*[10]*/, int64_t *launches);
 
 /* device buffers a multi-GPU host exchanges between the enqueue calls ------- */
 typedef enum {

@@ -14,10 +14,11 @@ def main():
     ap.add_argument("--intensity", default="f64_dense")
     ap.add_argument("--iters", type=int, default=12)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--shape", default=None, help="ZxYxX instead of a named workload")
     a = ap.parse_args()
     import torch
     from arterynetwork_b200.engine import VRGEngine
-    shape = bench.WORKLOADS[a.workload]
+    shape = tuple(int(t) for t in a.shape.split("x")) if a.shape else bench.WORKLOADS[a.workload]
     d, v = bench.device_phantom(shape, a.seed, 0, shape[0], 0)
     torch.cuda.synchronize()
     torch.cuda.set_stream(torch.cuda.Stream())

@@ -49,11 +49,12 @@ def main():
                 torch.cuda.synchronize()
                 ms_eager = s.elapsed_time(e)
                 prof = eng.get_profile()
+                tail = eng.get_tail_profile()
                 eng.profile(False)
             per = prof["decide_ms"] / max(1, prof["decide_launches"])
             print(json.dumps({"shape": shape, "bw": bw, "sweeps": res["sweeps"], "sweep_ms": per,
                               "sweep_10B_GBps": 10.0 * nvox / (per * 1e-3) / 1e9, "real_8B_GBps": 8.13 * nvox / (per * 1e-3) / 1e9,
-                              "cancel_ms": prof["cancel_ms"] / max(1, prof["cancel_launches"]),
+                              "cancel_ms": prof["cancel_ms"] / max(1, prof["cancel_launches"]), "tail_phases_us": tail,
                               "run_ms_graph": ms_graph, "run_ms_eager_profiled": ms_eager,
                               "Gvox_s_graph": nvox * res["sweeps"] / ms_graph / 1e6,
                               "per_iter_us_graph": 1e3 * ms_graph / res["sweeps"]}), flush=True)

@@ -451,3 +451,25 @@ def test_attach_device_with_an_8_byte_aligned_buffer():
             res = eng.run()
             assert res["iterations"] == g["iterations"]
             assert np.array_equal(eng.labels(), g["labels"]) and np.array_equal(eng.trace(), g["trace"])
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", ["forest40", "removal32", "cancel32", "maxseg", "forest_two_trees"])
+def test_fused_tail_equals_the_separate_kernels(name, mode, monkeypatch):
+    """vrg_run's production path (sweep + ONE cooperative tail kernel per iteration, vrg_tail.cuh) against the same run on the
+    separate kernels (k_cancel, k_quirks, k_advance, k_table: the path the host-driven API and the label-4 runs use): labels,
+    trace, exit, counters and -- bit for bit -- the decision table's Parzen sums."""
+    if name not in golden_names():
+        pytest.skip("fixture %s not present" % name)
+    g = load_golden(name)
+    a = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], mode)
+    monkeypatch.setenv("VRG_NO_FUSED_TAIL", "1")
+    b = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], mode)
+    monkeypatch.delenv("VRG_NO_FUSED_TAIL")
+    assert a["iterations"] == b["iterations"] == g["iterations"] and a["exit_reason"] == b["exit_reason"]
+    assert np.array_equal(a["labels"], b["labels"]) and np.array_equal(a["trace"], b["trace"])
+    for k in ("q_cancelled", "q_add_to_inside", "q_remove_to_outside", "q_cancel_repromoted", "n_in", "n_out", "sweeps"):
+        assert a[k] == b[k], k
+    for x, y in zip(a["table"], b["table"]):
+        assert np.array_equal(np.asarray(x).view(np.uint64), np.asarray(y).view(np.uint64))
+    assert a["kernel_launches"] < b["kernel_launches"]
