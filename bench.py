@@ -386,10 +386,24 @@ def bench_volume(ctx, shape, seed, intensity, steps, warmup, want_e2e, want_pari
         res = eng.poll()
         launches = res["kernel_launches"] - l0
         out["clocks"] = sampler.stop() if sampler else None
-        # per-launch time of the sweep: one extra step with CUDA events around every sweep launch (plain stream launches)
+        # per-launch time of the sweep: one extra step with CUDA events around every sweep launch (plain stream launches);
+        # the same step gives the phases of the tail kernel (device clock) and a host-side split of the step
         eng.profile(True)
-        step()
+        ctx.barrier(); torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        eng.attach_device(d_data.data_ptr(), d_vm.data_ptr())
+        if drv is None:
+            eng.set_levels(eng.scan_levels())  # vrg_init would do both; called here so that they can be timed on their own
+        else:
+            drv.prepare_levels()
+        torch.cuda.synchronize(); w1 = time.perf_counter()
+        eng.init() if drv is None else drv.init()
+        torch.cuda.synchronize(); w2 = time.perf_counter()
+        eng.run() if drv is None else drv.run()
+        torch.cuda.synchronize(); w3 = time.perf_counter()
         prof = eng.get_profile()
+        prof["tail_phases_us"] = eng.get_tail_profile()
+        prof["step_split_ms"] = {"levels": (w1 - w0) * 1e3, "init": (w2 - w1) * 1e3, "iterations_eager": (w3 - w2) * 1e3}
         eng.profile(False)
         out.update(ms=ms, sweeps=sweeps, res=res, prof=prof, launches=launches, value=nvox * sweeps / (ms * 1e-3) / 1e9,
                    planes=(z0, z1), local_vox=(min(shape[0], z1 + 1) - max(0, z0 - 1)) * shape[1] * shape[2])
@@ -474,7 +488,8 @@ def roofline_of(r, peak, peak_kind, traffic=None, traffic_source=None, kernel="k
             "algorithmic_bytes_per_launch": algo, "ms_per_launch": per_launch_ms, "launches_timed": prof["decide_launches"],
             "timed": "CUDA events around every sweep launch of one extra step on plain stream launches (the timed steps replay CUDA graphs)",
             "share_of_step": per_launch_ms * sweeps_per_step / (r["ms"] / max(1, r["steps"])),
-            "cancel_ms_per_launch": prof["cancel_ms"] / max(1, prof["cancel_launches"]),
+            "tail_ms_per_launch": prof["cancel_ms"] / max(1, prof["cancel_launches"]),
+            "tail_phases_us": prof.get("tail_phases_us"), "step_split_ms": prof.get("step_split_ms"),
             "note": "rank 0's slab (own planes +-1)"}
 
 
