@@ -34,7 +34,7 @@ class Config(ctypes.Structure):
 class Result(ctypes.Structure):
     _fields_ = [("iterations", i64), ("exit_reason", i64), ("n_in", i64), ("n_out", i64), ("n_excluded", i64),
                 ("n_levels", i64), ("sweeps", i64), ("kernel_launches", i64), ("q_cancelled", i64),
-                ("q_add_to_inside", i64), ("q_remove_to_outside", i64), ("q_cancel_repromoted", i64)]
+                ("q_add_to_inside", i64), ("q_remove_to_outside", i64), ("q_cancel_repromoted", i64), ("redone_sweeps", i64)]
 
 
 _SIGS = {

@@ -96,6 +96,8 @@ struct vrg_handle {
     unsigned long long *d_tail_dbg = nullptr;  // phase timings of the tail kernel (profiling runs)
     bool tail_ok = true;              // A/B switch VRG_NO_FUSED_TAIL, or the cooperative launch is not available
     bool tail_checked = false;
+    bool pipe_ok = true;              // A/B switch VRG_NO_PIPELINE: statistics + next table beside the next sweep (vrg_tail.cuh)
+    bool async_pending = false;       // the second stream holds work the next tail kernel has to wait for
 };
 
 static const int HASH_CAP = 1 << 18;
@@ -170,6 +172,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;  // A/B switch: plain loads instead of the TMA rings (sweep, init histogram)
     h->graph_ok = getenv("VRG_NO_GRAPH") == nullptr;    // A/B switch: vrg_run stays on plain stream launches
     h->tail_ok = getenv("VRG_NO_FUSED_TAIL") == nullptr;  // A/B switch: the separate kernels behind the sweep
+    h->pipe_ok = getenv("VRG_NO_PIPELINE") == nullptr;    // A/B switch: in-order iterations (table before every sweep)
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     Params &p = h->p;
@@ -417,7 +420,8 @@ int vrg_set_levels(vrg_handle *h, const double *lv, int64_t n) {
         CK(cudaMalloc((void **)&h->d_levels, p.L * sizeof(double)));
         CK(cudaMalloc((void **)&h->d_pin, p.L * sizeof(double)));
         CK(cudaMalloc((void **)&h->d_pout, p.L * sizeof(double)));
-        CK(cudaMalloc((void **)&h->d_dbits, p.LW * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&h->d_dbits, 2 * (size_t)p.LW * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(h->d_dbits, 0, 2 * (size_t)p.LW * sizeof(uint32_t), h->stream));
         CK(cudaMalloc((void **)&h->d_lstats, sb));
         h->d_gstats = h->d_lstats;
         if (p.L <= 2048) CK(cudaMalloc((void **)&h->d_kmat, (size_t)p.L * p.L * sizeof(double)));
@@ -915,6 +919,7 @@ int vrg_poll(vrg_handle *h, vrg_result *res) {
         res->kernel_launches = h->launches;
         res->q_cancelled = ex[ST_Q_CANCELLED]; res->q_add_to_inside = ex[ST_Q_ADD_INSIDE];
         res->q_remove_to_outside = ex[ST_Q_REM_OUTSIDE]; res->q_cancel_repromoted = ex[ST_Q_REPROMOTED];
+        res->redone_sweeps = h->h_ctrl[C_REDOS];
     }
     return VRG_OK;
 }
@@ -989,12 +994,85 @@ static int enqueue_tail(vrg_handle *h) {
     return VRG_OK;
 }
 
+// second stream + events of the pipelined run (the slab transport creates them when it connects)
+static int ensure_side_stream(vrg_handle *h) {
+    if (!h->halo_stream) {
+        CK(cudaStreamCreateWithFlags(&h->halo_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    return VRG_OK;
+}
+
+static int enqueue_tail_pipe(vrg_handle *h) {
+    if (h->prof) cudaEventRecord(prof_event(h), h->stream);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(h->sms); cfg.blockDim = dim3(TAIL_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const bool idx = h->cfg.intensity_mode == VRG_INTENSITY_INDEX, lat = h->p.lattice != 0;
+    const int p2p = h->p2p_on ? 1 : 0;
+    unsigned long long *dbg = h->prof ? h->d_tail_dbg : nullptr;
+    cudaError_t e;
+#define TAIL_LAUNCH(M, LAT)                                                                              \
+    (dbg ? cudaLaunchKernelEx(&cfg, k_tail_pipe<M, LAT, true>, h->p, h->q, h->d_gbar, p2p, dbg)         \
+         : cudaLaunchKernelEx(&cfg, k_tail_pipe<M, LAT, false>, h->p, h->q, h->d_gbar, p2p, dbg))
+    if (idx && lat) e = TAIL_LAUNCH(MODE_INDEX, true);
+    else if (idx) e = TAIL_LAUNCH(MODE_INDEX, false);
+    else if (lat) e = TAIL_LAUNCH(MODE_F64_BAND, true);
+    else e = TAIL_LAUNCH(MODE_F64_BAND, false);
+#undef TAIL_LAUNCH
+    if (h->prof) cudaEventRecord(prof_event(h), h->stream);
+    h->launches++;
+    CK(e);
+    return VRG_OK;
+}
+
+// One pipelined iteration: the sweep goes first, only then does the main stream wait for the statistics / table kernels of
+// the previous update (they have been running beside this sweep), then the tail kernel; the statistics + table kernels of
+// this update are forked to the second stream.
+static int enqueue_pipelined(vrg_handle *h) {
+    int rc;
+    if ((rc = enqueue_sweep(h)) != VRG_OK) return rc;
+    if (h->async_pending) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        h->async_pending = false;
+    }
+    if ((rc = enqueue_tail_pipe(h)) != VRG_OK) return rc;
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->halo_stream, h->ev_fork, 0));
+    k_async_stats<<<1, ASYNC_BLOCK, 0, h->halo_stream>>>(h->p, h->q, h->d_gstats, h->p2p_on ? 1 : 0);
+    k_async_table<<<h->p.LW, ASYNC_BLOCK, 0, h->halo_stream>>>(h->p);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_join, h->halo_stream));
+    h->async_pending = true;
+    return VRG_OK;
+}
+
+static int join_async(vrg_handle *h) {
+    if (h->async_pending) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        h->async_pending = false;
+    }
+    return VRG_OK;
+}
+
 static int enqueue_batch(vrg_handle *h, int n) {
     const bool fused = tail_applies(h);
+    const bool piped = fused && h->pipe_ok;
+    if (piped) { int rc_ = ensure_side_stream(h); if (rc_ != VRG_OK) return rc_; }
     for (int k = 0; k < n; ++k) {
         int rc;
         if (h->cfg.intensity_mode == VRG_INTENSITY_CONTINUOUS) {
             if ((rc = cont_enqueue_iteration(h)) != VRG_OK) return rc;
+            continue;
+        }
+        if (piped) {
+            if ((rc = enqueue_pipelined(h)) != VRG_OK) return rc;
             continue;
         }
         if (fused) {  // the table of this sweep was computed by the previous tail (the first one: vrg_run)
@@ -1028,6 +1106,7 @@ static int enqueue_batch(vrg_handle *h, int n) {
             if ((rc = vrg_enqueue_advance(h)) != VRG_OK) return rc;
         }
     }
+    { int rc_ = join_async(h); if (rc_ != VRG_OK) return rc_; }
     return join_halo(h);  // a batch ends joined: it may be a captured graph, and the host polls the main stream
 }
 
@@ -1039,7 +1118,7 @@ static uint64_t run_signature(const vrg_handle *h) {
     };
     mix(&h->p, sizeof(Params));
     if (h->p2p_on) mix(&h->q, sizeof(P2P));
-    const int64_t extra[4] = {h->cfg.intensity_mode, h->p2p_on, h->force_ldg, h->tail_ok};
+    const int64_t extra[5] = {h->cfg.intensity_mode, h->p2p_on, h->force_ldg, h->tail_ok, h->pipe_ok};
     mix(extra, sizeof extra);
     return x;
 }
@@ -1196,10 +1275,10 @@ int vrg_profile(vrg_handle *h, int enable) {
     h->prof_n[0] = h->prof_n[1] = 0;
     return VRG_OK;
 }
-// phase timings of the fused tail kernel, collected while vrg_profile is on: us[0..4] = mean microseconds block 0 spent in
-// phase 1 (cancel rule + flips), the first device-wide barrier, phase 2 (statistics exchange + exit tests; halo exchange on
-// the other blocks), the second barrier, phase 3 (decision table + order-dependence counters); us[5..9] the same for the
-// last block of the grid.
+// phase timings of the tail kernel, collected while vrg_profile is on: us[0..6] = mean microseconds block 0 spent in
+// phase 1 (cancel rule + flips), the first device-wide barrier, phase 2 (in-order run: statistics exchange + exit tests, halo
+// exchange on the other blocks; pipelined run: halo wait + unpack), the second barrier, phase 3, and for the pipelined run the
+// halo push and the counters (the first two parts of its phase 2); us[7..13] the same for the last block of the grid.
 int vrg_get_tail_profile(vrg_handle *h, double *us, int64_t *launches) {
     if (!h || !us || !launches) return fail(VRG_ERR_ARG, "null argument");
     CK(cudaSetDevice(h->cfg.device));
@@ -1216,9 +1295,9 @@ int vrg_get_tail_profile(vrg_handle *h, double *us, int64_t *launches) {
             fprintf(stderr, "\n");
         }
     }
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < 7; ++i) {
         us[i] = d[0] ? (double)d[1 + i] / (double)d[0] * 1e-3 : 0.0;
-        us[5 + i] = d[0] ? (double)d[9 + i] / (double)d[0] * 1e-3 : 0.0;
+        us[7 + i] = d[0] ? (double)d[9 + i] / (double)d[0] * 1e-3 : 0.0;
     }
     return VRG_OK;
 }

@@ -36,14 +36,21 @@ constexpr int STAGE_BYTES = WORDS_PER_WARP * 32 * 8;
 
 enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, ST_BAD_LABEL = 5, ST_NONFINITE = 6, ST_TIME_UP = 7,
        // cumulative counts of the flip patterns on which the reference's result depends on its list order (k_quirks)
-       ST_Q_CANCELLED = 8, ST_Q_ADD_INSIDE = 9, ST_Q_REM_OUTSIDE = 10, ST_Q_REPROMOTED = 11, ST_EXTRA = 16 };
+       ST_Q_CANCELLED = 8, ST_Q_ADD_INSIDE = 9, ST_Q_REM_OUTSIDE = 10, ST_Q_REPROMOTED = 11,
+       ST_N_FLIPS_SNAP = 12,  // pipelined run (vrg_tail.cuh): the flip count of the update just applied, set aside by the tail kernel
+                              // while the next sweep already counts into ST_N_FLIPS
+       ST_EXTRA = 16 };
 enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_FULL_SWEEP = 8,
        C_EPOCH = 9, C_PEER_TIMEOUT = 10, C_HALO_SEQ = 11, C_HALO_GO = 12,  // 9..12: slab runs (vrg_p2p.cuh)
        // C_FULL_SWEEP: 1 + index of the latest sweep that must look at every band voxel (first sweep of a run, a sweep behind a
        // changed decision table, a sweep behind caller-chosen flips); every other band / index sweep is incremental.  A stamp,
        // not a flag: whoever builds a table writes it, nobody has to clear it.
        C_NEXT_UNIT = 13,  // dense sweep: work-unit counter (units beyond the statically assigned ones are handed out dynamically)
-       C_WORDS = 16 };
+       // pipelined run (vrg_tail.cuh): which of the two decision-table buffers the sweeps read; `the table built beside the last
+       // sweep differs from the one it read`; `the last tail kernel applied its update` (statistics kernels have work)
+       C_TABLE_BUF = 14, C_TABLE_NEW = 15, C_TAIL_APPLIED = 16,
+       C_REDOS = 17,  // sweeps of the pipelined run that were repeated because the table changed beside them
+       C_WORDS = 24 };
 constexpr long long RUNNING = -1;
 
 enum { MODE_F64_DENSE = 0, MODE_F64_BAND = 1, MODE_INDEX = 2, MODE_CONT = 3 };  // MODE_CONT: no level table (vrg_parzen.cuh)
@@ -77,7 +84,8 @@ struct Params {
     double lev0, inv_step;
     const double *levels;             // [L]
     const double *kmat;               // [L][L] Parzen kernel values A*exp(-0.5*H*(lev_b-lev_c)^2), or nullptr (L too large)
-    uint32_t *dbits;                  // [LW]
+    uint32_t *dbits;                  // 2 x [LW]: decision bits; ctrl[C_TABLE_BUF] says which buffer is current (always 0 outside
+                                      // the pipelined run, which builds the next table in the other one beside the running sweep)
     double *pin, *pout;               // [L] normalised Parzen sums of the last table
     double mhH;                       // -0.5 * H
     long long *lstats;                // local  [2L + ST_EXTRA]
@@ -86,6 +94,7 @@ struct Params {
     long long *trace;                 // [3 * (iter_max + 2)]
 };
 
+__device__ __forceinline__ uint32_t *table_bits(const Params &p) { return p.dbits + (size_t)p.ctrl[C_TABLE_BUF] * p.LW; }
 __device__ __forceinline__ int *front_list(const Params &p, int which) { return p.front + (size_t)which * p.front_cap; }
 __device__ __forceinline__ int *dirty_list(const Params &p, int which) { return p.dirty + (size_t)which * p.front_cap; }
 
@@ -254,8 +263,9 @@ __global__ void __launch_bounds__(TABLE_BLOCK) k_table(Params p, int final) {
     if (threadIdx.x == 0) {
         uint32_t w = 0;
         for (int i = 0; i < 32; ++i) w |= s_bits[i];
-        if (p.dbits[blockIdx.x] != w) p.ctrl[C_FULL_SWEEP] = p.ctrl[C_SWEEPS] + 1;  // the sweep behind this table looks at every band voxel
-        p.dbits[blockIdx.x] = w;
+        uint32_t *bits = table_bits(p);
+        if (bits[blockIdx.x] != w) p.ctrl[C_FULL_SWEEP] = p.ctrl[C_SWEEPS] + 1;  // the sweep behind this table looks at every band voxel
+        bits[blockIdx.x] = w;
     }
 }
 
@@ -396,7 +406,7 @@ template <int MODE, bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
     extern __shared__ uint32_t s_dbits[];
-    for (int i = threadIdx.x; i < p.LW; i += BLOCK) s_dbits[i] = p.dbits[i];
+    for (int i = threadIdx.x; i < p.LW; i += BLOCK) s_dbits[i] = table_bits(p)[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);
@@ -482,7 +492,7 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     int *rings = (int *)(bars + DENSE_WARPS * DENSE_STAGES);                                   // [DENSE_WARPS][UNIT_RING]
     double *stages = (double *)(smem_raw + dbits_bytes + ((DENSE_WARPS * (DENSE_STAGES * 8 + UNIT_RING * 4) + 127) & ~127));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < p.LW; i += DENSE_WARPS * 32) s_dbits[i] = p.dbits[i];
+    for (int i = threadIdx.x; i < p.LW; i += DENSE_WARPS * 32) s_dbits[i] = table_bits(p)[i];
     uint64_t *mybar = bars + warp * DENSE_STAGES;
     int *myring = rings + warp * UNIT_RING;
     double *mystage = stages + (size_t)warp * DENSE_STAGES * (STAGE_BYTES / 8);
@@ -616,7 +626,7 @@ template <bool LATTICE>
 __global__ void __launch_bounds__(BLOCK) k_sweep_dense_ldg(Params p) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
     extern __shared__ uint32_t s_dbits[];
-    for (int i = threadIdx.x; i < p.LW; i += BLOCK) s_dbits[i] = p.dbits[i];
+    for (int i = threadIdx.x; i < p.LW; i += BLOCK) s_dbits[i] = table_bits(p)[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int zlo = max(p.valid_lo, p.own_lo - 1), zhi = min(p.valid_hi, p.own_hi + 1);

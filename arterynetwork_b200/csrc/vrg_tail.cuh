@@ -99,7 +99,8 @@ __device__ __forceinline__ void table_words(const Params &p, int t, int T, long 
         kv0[k] = (pre && c < p.L) ? p.kmat[(size_t)b0 * p.L + c] : 0.0;
     }
     const double n_in = (double)__ldcg(g + 2 * p.L + ST_N_IN), n_out = (double)__ldcg(g + 2 * p.L + ST_N_OUT);
-    uint32_t oldw = threadIdx.x == 0 ? __ldcg(p.dbits + w) : 0u;
+    uint32_t *bits = table_bits(p);
+    uint32_t oldw = threadIdx.x == 0 ? __ldcg(bits + w) : 0u;
     if (stage_hist) {  // the two histograms once per block, as doubles, in shared memory: one coalesced round trip
         for (int i = threadIdx.x; i < 2 * p.L; i += TAIL_BLOCK) s_hist[i] = (double)__ldcg(g + i);
         __syncthreads();
@@ -152,21 +153,22 @@ __device__ __forceinline__ void table_words(const Params &p, int t, int T, long 
                 }
             } else bit = table_level_from(p, b, lane, n_in, n_out, hist);
         }
-        if (!first && threadIdx.x == 0) oldw = __ldcg(p.dbits + w);
+        if (!first && threadIdx.x == 0) oldw = __ldcg(bits + w);
         if (lane == 0) s_bits[warp] = bit << warp;
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t word = 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) word |= s_bits[i];
-            if (word != oldw) { p.dbits[w] = word; p.ctrl[C_FULL_SWEEP] = next_sweep + 1; }  // that sweep looks at every band voxel
+            if (word != oldw) { bits[w] = word; p.ctrl[C_FULL_SWEEP] = next_sweep + 1; }  // that sweep looks at every band voxel
         }
         __syncthreads();
     }
 }
 
 // dbg (profiling runs only, else nullptr): [0] launches, [1..5] nanoseconds block 0 spent in phase 1 / barrier / phase 2 /
-// barrier / phase 3, [9..13] the same for the last block; [16 + b], [16 + grid + b]: block b's phase 1 / phase 3.
+// barrier / phase 3 ([6], [7]: k_tail_pipe's halo push and counters, the first two parts of its phase 2; [3] is then the wait +
+// unpack), [9..15] the same for the last block; [16 + b], [16 + grid + b]: block b's phase 1 / phase 3.
 template <int MODE, bool LATTICE, bool TIMED>
 __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail(Params p, P2P q, long long *gstats, unsigned int *gbar, int p2p,
                                                         int stage_hist, unsigned long long *dbg) {
@@ -362,6 +364,277 @@ __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail(Params p, P2P q, long lo
     __syncthreads();
     stamp(5);
     if (TIMED && threadIdx.x == 0) dbg[16 + gridDim.x + blockIdx.x] += tail_clock() - tb3;
+}
+
+// =====================================================================================================================
+// The pipelined run: statistics, exit tests and the next decision table travel BESIDE the next sweep.
+//
+// The decision table depends on the regions only through their normalised Parzen sums, and those barely move from one
+// update to the next: on the bench phantom not one decision bit changes in 118 updates.  So sweep k+1 does not wait for the
+// table of update k: it starts right behind the tail kernel of update k and reads the table it already has, while on a
+// second stream two small kernels (they fit on the SMs beside the sweep's blocks) exchange update k's statistics, run the
+// exit tests and build the table of update k+1 into the OTHER table buffer.  The tail kernel of update k+1 waits for them
+// (stream event) and looks at the result before it touches any state:
+//   * run over (converged, cap reached, ...)            -> it returns; the sweep was one too many and is not counted
+//   * a decision bit changed                            -> it switches the table buffers, marks the next sweep `full` and
+//                                                          returns; the stream's next sweep / tail pair redoes update k+1
+//   * otherwise (the rule)                              -> update k+1 is applied exactly as the in-order run would
+// The sweep only writes flip flags, row flags and the front list, all of which the redone sweep rewrites; nothing it writes
+// is read by the statistics kernels (the flip count of update k is set aside in ST_N_FLIPS_SNAP by the tail kernel).
+// Results are identical to the in-order run by construction: every applied update used the table of the statistics before it.
+// What the iteration waits for is down to: sweep -> cancel rule -> halo exchange with the two neighbours.  The all-to-all
+// statistics exchange has a whole sweep of slack, which also absorbs the ranks' skew.
+//
+// k_tail_pipe: phase 1 cancel rule + flips; barrier; phase 2 halo exchange (slabs) + order-dependence counters; on slabs a
+// second barrier and the counters of the rows next to a halo plane; bookkeeping of the next sweep.
+template <int MODE, bool LATTICE, bool TIMED>
+__global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail_pipe(Params p, P2P q, unsigned int *gbar, int p2p, unsigned long long *dbg) {
+    __shared__ long long s_ctl[6];
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        s_ctl[0] = p.ctrl[C_STATUS]; s_ctl[1] = p.ctrl[C_APPLY]; s_ctl[2] = p.ctrl[C_SWEEPS]; s_ctl[3] = p.ctrl[C_EPOCH];
+        s_ctl[4] = p.ctrl[C_TABLE_NEW]; s_ctl[5] = p.ctrl[C_TABLE_BUF];
+    }
+    __syncthreads();
+    // nothing else runs on this device's handle while the tail kernel does: the control words are stable
+    if (s_ctl[0] != RUNNING) return;  // the run ended with the previous update; the sweep in front of this kernel is not counted
+    const int sweep = (int)s_ctl[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = (int)gridDim.x;
+    if (s_ctl[4] != 0) {
+        // the sweep read a table that update `sweep - 1` has changed: switch to the new one, redo the sweep (a full one)
+        grid_barrier(gbar, gridDim.x);  // every block has read the control words
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            p.ctrl[C_TABLE_BUF] = 1 - s_ctl[5];
+            p.ctrl[C_TABLE_NEW] = 0;
+            p.ctrl[C_FULL_SWEEP] = sweep + 1;
+            p.ctrl[C_TAIL_APPLIED] = 0;
+            p.ctrl[C_REDOS] += 1;
+            p.lstats[2 * p.L + ST_N_FLIPS] = 0;
+            front_list(p, sweep & 1)[0] = 0;
+            p.ctrl[C_NEXT_UNIT] = 0;
+        }
+        return;
+    }
+    const bool go = s_ctl[1] != 0;  // the cap of VRG:101 is tested before the flips are applied
+    const unsigned long long seq = ((unsigned long long)s_ctl[3] << 32) | (unsigned long long)(sweep + 1);
+    const int gw = blockIdx.x * TAIL_WARPS + warp, nw = G * TAIL_WARPS;
+    const int *fl = front_list(p, sweep & 1);
+    const int nfront = go ? fl[0] : 0;
+    QuirkCounts qc;
+    auto quirk_rows = [&](bool boundary) {
+        for (int k = gw; k < nfront; k += nw) {
+            const int rr = fl[1 + k];
+            const int sg = rr % p.nseg, t = rr / p.nseg, zl = t / p.Y;
+            const bool at_halo = (zl - 1 < p.own_lo && zl - 1 >= p.valid_lo) || (zl + 1 >= p.own_hi && zl + 1 < p.valid_hi);
+            if (at_halo == boundary) quirks_row(p, zl, t % p.Y, sg, lane, qc);
+        }
+    };
+    const bool timing = TIMED && threadIdx.x == 0 && (blockIdx.x == 0 || (int)blockIdx.x == G - 1);
+    unsigned long long *tdst = dbg + (blockIdx.x == 0 ? 0 : 8);
+    unsigned long long t_prev = timing ? tail_clock() : 0ull;
+    auto stamp = [&](int slot) {
+        if (TIMED && timing) { const unsigned long long tc = tail_clock(); tdst[slot] += tc - t_prev; t_prev = tc; }
+    };
+    const unsigned long long tb0 = (TIMED && threadIdx.x == 0) ? tail_clock() : 0ull;
+    if (TIMED && timing && blockIdx.x == 0) dbg[0] += 1;
+
+    // ---- phase 1: cancel rule, flips, histogram deltas ------------------------------------------------------------
+    if (go) {
+        const bool dirty = p.dirty_lists && p.valid_lo == p.own_lo && p.valid_hi == p.own_hi;
+        long long d_in = 0;
+        auto fetch = [&](int rr, uint32_t &s, uint32_t &f) {
+            s = 0u; f = 0u;
+            if (rr < 0) return;
+            const int sg = rr % p.nseg, t = rr / p.nseg;
+            const int c = sg * p.segw - 1 + lane;
+            if (c >= 0 && c < p.XW) {
+                const long long widx = (long long)(t / p.Y) * p.plane_words + (long long)(t % p.Y) * p.WP + c;
+                s = p.S[widx]; f = p.F[widx];
+            }
+        };
+        int k = gw;
+        int rrA = k < nfront ? fl[1 + k] : -1, rrB = k + nw < nfront ? fl[1 + k + nw] : -1;
+        uint32_t sA, fA, sB, fB;
+        fetch(rrA, sA, fA);
+        fetch(rrB, sB, fB);
+        while (rrA >= 0) {
+            const int kC = k + 2 * nw;
+            const int rrC = kC < nfront ? fl[1 + kC] : -1;
+            const int sg = rrA % p.nseg, t = rrA / p.nseg;
+            cancel_row_loaded<MODE, LATTICE>(p, t / p.Y, t % p.Y, sg, lane, dirty, d_in, sA, fA);
+            rrA = rrB; sA = sB; fA = fB;
+            rrB = rrC;
+            fetch(rrB, sB, fB);
+            k += nw;
+        }
+        cancel_finish(p, d_in, lane);
+    }
+    stamp(1);
+    if (TIMED) { __syncthreads(); if (threadIdx.x == 0) dbg[16 + blockIdx.x] += tail_clock() - tb0; }
+    grid_barrier(gbar, gridDim.x);
+    stamp(2);
+
+    // ---- phase 2: halo exchange with the two neighbour slabs; order-dependence counters ---------------------------------
+    if (go && !p2p) quirk_rows(false);
+    else if (go) {
+        const long long n = (long long)HALO * p.plane_words;
+        const int nch = min(G, MAX_CHUNKS);
+        const long long par_off = (long long)(seq & 1ull) * P2P_KINDS * 2 * n;
+        const int j = (int)blockIdx.x;  // this block's chunk of the halo planes (blocks beyond MAX_CHUNKS have none)
+        const long long lo = j < nch ? n * j / nch : 0, hi = j < nch ? n * (j + 1) / nch : 0;
+        if (j < nch) {
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {  // side 0: to the lower neighbour (lands in its "from above" region)
+                uint32_t *dst = q.peer_recv[side];
+                if (dst == nullptr) continue;
+                dst += par_off + ((long long)PK_F * 2 + (side ^ 1)) * n;
+                const uint32_t *src = p.F + (long long)(side == 0 ? p.own_lo : p.own_hi - HALO) * p.plane_words;
+                for (long long i = lo + threadIdx.x; i < hi; i += TAIL_BLOCK) dst[i] = __ldcg(src + i);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (q.peer_recv[0]) st_release_sys(q.peer_flags[q.rank - 1] + CHUNK_FLAGS + 1 * MAX_CHUNKS + j, seq);
+                if (q.peer_recv[1]) st_release_sys(q.peer_flags[q.rank + 1] + CHUNK_FLAGS + 0 * MAX_CHUNKS + j, seq);
+            }
+        }
+        stamp(6);
+        quirk_rows(false);  // while the neighbours' chunks travel
+        stamp(7);
+        if (j < nch) {
+            if (threadIdx.x == 0) {
+                int ok = 1;
+                if (q.peer_recv[0] && !p2p_wait(q.flags + CHUNK_FLAGS + 0 * MAX_CHUNKS + j, seq)) ok = 0;
+                if (ok && q.peer_recv[1] && !p2p_wait(q.flags + CHUNK_FLAGS + 1 * MAX_CHUNKS + j, seq)) ok = 0;
+                if (!ok) { p.ctrl[C_PEER_TIMEOUT] = 1; p.ctrl[C_STATUS] = EXIT_PEER_TIMEOUT; }
+                s_ok = ok;
+                __threadfence_system();
+            }
+            __syncthreads();
+            if (s_ok) {
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {  // side 0: data from the lower neighbour -> my lower halo planes
+                    if (q.peer_recv[side] == nullptr) continue;
+                    const uint32_t *src = q.recv + par_off + ((long long)PK_F * 2 + side) * n;
+                    const int z0 = side == 0 ? p.own_lo - HALO : p.own_hi;
+                    uint32_t *fdst = p.F + (long long)z0 * p.plane_words, *sdst = p.S + (long long)z0 * p.plane_words;
+                    for (long long i = lo + threadIdx.x; i < hi; i += TAIL_BLOCK) {
+                        const uint32_t f = __ldcg(src + i);
+                        fdst[i] = f;
+                        if (f) {  // the halo copy of the segmented plane follows the neighbour slab
+                            sdst[i] = __ldcg(sdst + i) ^ f;
+                            const int zl = z0 + (int)(i / p.plane_words), y = (int)((i % p.plane_words) / p.WP), c = (int)(i % p.WP);
+                            p.unitmap[unit_index(p, zl, y, c)] = 1;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    stamp(3);
+    if (p2p) {
+        grid_barrier(gbar, gridDim.x);
+        stamp(4);
+        if (go) quirk_rows(true);  // rows next to a halo plane: their neighbours' flips have arrived
+    }
+    if (go) quirks_finish(p, qc, lane);
+    // bookkeeping of the next sweep (the other blocks read the control words at their start and are past them)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.lstats[2 * p.L + ST_N_FLIPS_SNAP] = p.lstats[2 * p.L + ST_N_FLIPS];  // the sweep's atomics are complete
+        p.lstats[2 * p.L + ST_N_FLIPS] = 0;
+        p.ctrl[C_SWEEPS] = sweep + 1;
+        front_list(p, (sweep + 1) & 1)[0] = 0;
+        dirty_list(p, (sweep + 2) & 1)[0] = 0;
+        p.ctrl[C_NEXT_UNIT] = 0;
+        p.ctrl[C_TAIL_APPLIED] = 1;
+    }
+    __syncthreads();
+    stamp(5);
+}
+
+// k_async_stats (second stream, one small block beside the running sweep): the statistics all-reduce of the update the tail
+// kernel just applied (slabs), then the exit tests of VRG:91-104,118 and the loop bookkeeping of VRG:113-117.
+constexpr int ASYNC_BLOCK = 256;
+__global__ void __launch_bounds__(ASYNC_BLOCK) k_async_stats(Params p, P2P q, long long *gstats, int p2p) {
+    __shared__ int s_ok;
+    if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_TAIL_APPLIED]) return;
+    const long long k = p.ctrl[C_SWEEPS] - 1;  // the update just applied (the tail kernel moved C_SWEEPS on)
+    const unsigned long long seq = ((unsigned long long)p.ctrl[C_EPOCH] << 32) | (unsigned long long)(k + 1);
+    bool ok = true;
+    if (p2p) {
+        const int par = (int)(seq & 1ull), n = 2 * p.L + ST_EXTRA;
+        for (int r = 0; r < q.world; ++r) {
+            long long *dst = q.peer_slots[r] + ((long long)par * q.world + q.rank) * q.slot_words;
+            for (int i = threadIdx.x; i < n; i += ASYNC_BLOCK) dst[i] = __ldcg(p.lstats + i);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) s_ok = 1;
+        if (threadIdx.x < q.world) st_release_sys(q.peer_flags[threadIdx.x] + STATS_FLAGS + par * P2P_MAX_WORLD + q.rank, seq);
+        __syncthreads();
+        if (threadIdx.x < q.world && !p2p_wait(q.flags + STATS_FLAGS + par * P2P_MAX_WORLD + threadIdx.x, seq)) s_ok = 0;
+        __threadfence_system();
+        __syncthreads();
+        ok = s_ok != 0;
+        if (ok) {
+            const long long *base = q.slots + (long long)par * q.world * q.slot_words;
+            for (int i = threadIdx.x; i < n; i += ASYNC_BLOCK) {
+                long long sum = 0;
+                for (int r = 0; r < q.world; ++r) sum += __ldcg(base + (long long)r * q.slot_words + i);
+                gstats[i] = sum;
+            }
+            __threadfence();
+            __syncthreads();
+        }
+    }
+    if (!ok) {
+        if (threadIdx.x == 0) { p.ctrl[C_PEER_TIMEOUT] = 1; p.ctrl[C_STATUS] = EXIT_PEER_TIMEOUT; }
+        return;
+    }
+    if (threadIdx.x < 32) {  // advance_state by one warp; C_SWEEPS and the sweep's accumulators belong to the tail kernel
+        const int lane = threadIdx.x;
+        const long long *g = p.gstats + 2 * p.L;
+        const long long v = lane < 16 ? __ldcg(p.ctrl + lane) : __ldcg(g + (lane - 16));
+        const long long apply = __shfl_sync(FULL, v, C_APPLY), tn = __shfl_sync(FULL, v, C_TRACE_N);
+        const long long iter = __shfl_sync(FULL, v, C_ITER), itmax = __shfl_sync(FULL, v, C_ITER_MAX);
+        const long long applied = __shfl_sync(FULL, v, C_APPLIED), maxseg = __shfl_sync(FULL, v, C_MAX_SEG);
+        const long long nfl = __shfl_sync(FULL, v, 16 + ST_N_FLIPS_SNAP), nin = __shfl_sync(FULL, v, 16 + ST_N_IN);
+        const long long nout = __shfl_sync(FULL, v, 16 + ST_N_OUT), tup = __shfl_sync(FULL, v, 16 + ST_TIME_UP);
+        if (lane != 0) return;
+        long long *c = p.ctrl;
+        if (nfl == 0) { c[C_STATUS] = 0; return; }     // converged, VRG:91
+        if (!apply) { c[C_STATUS] = 2; return; }       // max segment size, VRG:101
+        p.trace[3 * tn] = nfl; p.trace[3 * tn + 1] = nin; p.trace[3 * tn + 2] = nout;
+        c[C_TRACE_N] = tn + 1; c[C_APPLIED] = applied + 1; c[C_ITER] = iter + 1;
+        if (iter + 1 > itmax) { c[C_STATUS] = 3; return; }  // VRG:58,118
+        if (tup != 0) { c[C_STATUS] = 1; return; }          // VRG:97 on slabs (see advance_state)
+        c[C_APPLY] = nin < maxseg;                          // the cap of VRG:101 for the next update
+    }
+}
+
+// k_async_table (second stream, behind k_async_stats): the decision table of the new statistics into the table buffer the
+// sweeps do NOT read; raises C_TABLE_NEW if a bit differs from the current one.  One decision word (32 levels) per block of
+// eight warps -- its latency hides behind the sweep, its footprint has to fit beside the sweep's blocks.
+__global__ void __launch_bounds__(ASYNC_BLOCK) k_async_table(Params p) {
+    __shared__ uint32_t s_bits[ASYNC_BLOCK / 32];
+    if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_TAIL_APPLIED]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, w = blockIdx.x;
+    uint32_t mine = 0u;
+    for (int i = 0; i < 32 / (ASYNC_BLOCK / 32); ++i) {
+        const int j = warp * (32 / (ASYNC_BLOCK / 32)) + i, b = w * 32 + j;
+        if (b < p.L) mine |= table_level(p, b, lane) << j;
+    }
+    if (lane == 0) s_bits[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < ASYNC_BLOCK / 32; ++i) word |= s_bits[i];
+        const long long cur = p.ctrl[C_TABLE_BUF];
+        p.dbits[(size_t)(1 - cur) * p.LW + w] = word;
+        if (word != p.dbits[(size_t)cur * p.LW + w]) p.ctrl[C_TABLE_NEW] = 1;
+    }
 }
 
 }  // namespace vrg

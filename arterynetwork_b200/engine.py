@@ -158,12 +158,12 @@ class VRGEngine:
 
     def get_tail_profile(self) -> dict:
         """Mean microseconds per phase of the fused tail kernel (first / last block of its grid), see vrg_get_tail_profile."""
-        us = (ctypes.c_double * 10)()
+        us = (ctypes.c_double * 14)()
         n = nat.i64(0)
         nat.check(self.lib.vrg_get_tail_profile(self._h, ctypes.addressof(us), ctypes.byref(n)))
-        names = ("cancel", "barrier1", "stats_exit_halo", "barrier2", "table_counters")
+        names = ("cancel", "barrier1", "phase2", "barrier2", "phase3", "pipe_halo_push", "pipe_counters")
         return {"launches": int(n.value), "first_block_us": {k: us[i] for i, k in enumerate(names)},
-                "last_block_us": {k: us[5 + i] for i, k in enumerate(names)}}
+                "last_block_us": {k: us[7 + i] for i, k in enumerate(names)}}
 
     def use_separate_global_stats(self):
         nat.check(self.lib.vrg_use_separate_global_stats(self._h))

@@ -402,7 +402,12 @@ def bench_volume(ctx, shape, seed, intensity, steps, warmup, want_e2e, want_pari
         eng.run() if drv is None else drv.run()
         torch.cuda.synchronize(); w3 = time.perf_counter()
         prof = eng.get_profile()
-        prof["tail_phases_us"] = eng.get_tail_profile()
+        tp = eng.get_tail_profile()
+        names = list(tp["first_block_us"])
+        allr = ctx.gather_i64([int(tp["first_block_us"][k] * 1e3) for k in names] + [int(tp["last_block_us"][k] * 1e3) for k in names])
+        prof["tail_phases_us"] = {"launches": tp["launches"], "phases": names,
+                                  "first_block_per_rank": [[round(v / 1e3, 2) for v in row[:len(names)]] for row in allr.tolist()],
+                                  "last_block_per_rank": [[round(v / 1e3, 2) for v in row[len(names):]] for row in allr.tolist()]}
         prof["step_split_ms"] = {"levels": (w1 - w0) * 1e3, "init": (w2 - w1) * 1e3, "iterations_eager": (w3 - w2) * 1e3}
         eng.profile(False)
         out.update(ms=ms, sweeps=sweeps, res=res, prof=prof, launches=launches, value=nvox * sweeps / (ms * 1e-3) / 1e9,

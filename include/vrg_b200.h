@@ -89,6 +89,9 @@ typedef struct {
     int64_t q_remove_to_outside; /* removed voxels left without a segmented neighbour: stale label 2 in the reference (Q2/Q3) */
     int64_t q_cancel_repromoted; /* cancelled additions next to an executed addition: added by the reference if that
                                     neighbour comes first in its band list ("Q4") */
+    int64_t redone_sweeps;       /* vrg_run starts each sweep on the decision table it has while the statistics of the previous
+                                    update are still being exchanged; a sweep whose table turned out to have changed is repeated
+                                    with the new one.  Repeats (and the one sweep in flight when the run ends) are not in `sweeps`. */
 } vrg_result;
 
 const char *vrg_last_error(void);
@@ -141,11 +144,12 @@ int vrg_enqueue_table(vrg_handle *h);
  * halo exchange, exit tests, next decision table; host-driven iteration: the cancel kernel).  For roofline reporting. */
 int vrg_profile(vrg_handle *h, int enable);
 int vrg_get_profile(vrg_handle *h, double *ms_total /*[2]*/, int64_t *launches /*[2]*/);
-/* phase timings inside the fused tail kernel while vrg_profile is on (device clock): us[0..4] = mean microseconds the
- * grid's first block spent in phase 1 (cancel rule, flips), the first device-wide barrier, phase 2 (statistics exchange +
- * exit tests; the other blocks exchange halos), the second barrier, phase 3 (decision table, order-dependence counters);
- * us[5..9] = the same for the grid's last block. */
-int vrg_get_tail_profile(vrg_handle *h, double *us /*[10]*/, int64_t *launches);
+/* phase timings inside the tail kernel while vrg_profile is on (device clock): us[0..6] = mean microseconds the grid's first
+ * block spent in phase 1 (cancel rule, flips), the first device-wide barrier, phase 2 (in-order run: statistics exchange +
+ * exit tests while the other blocks exchange halos; pipelined run: halo wait + unpack), the second barrier, phase 3 (decision
+ * table / counters of the rows next to a halo plane), and for the pipelined run its halo push and its counters (the first two
+ * parts of its phase 2); us[7..13] = the same for the grid's last block. */
+int vrg_get_tail_profile(vrg_handle *h, double *us /*[14]*/, int64_t *launches);
 
 /* device buffers a multi-GPU host exchanges between the enqueue calls ------- */
 typedef enum {

@@ -34,3 +34,19 @@ def random_case(i):
     H = float(rng.choice([1.0, 2.25, 4.0]))
     max_seg = int(rng.choice([10 ** 12, 10 ** 12, 5000, 60]))
     return data.astype(np.float64), vm, H, max_seg
+
+
+def table_shift_case():
+    """A vessel whose first stretch is darker than the rest, with in-between intensities along its wall: the inside mean
+    rises while the region grows, the crossover of the two Parzen densities moves, and the decision bits of the in-between
+    levels change in the middle of the run (iterations 7 and 11; voxels that entered leave again).  The pipelined run has to
+    notice (a sweep is repeated on the new table)."""
+    d = np.zeros((20, 24, 64))
+    d[8:12, 10:14, 4:60] = 1.0
+    d[8:12, 10:14, 4:10] = 0.75
+    d[7, 10:14, 4:60:3] = 0.4375
+    d[12, 10:14, 5:60:4] = 0.40625
+    d[2:4, 2:4, 2:30] = 0.4375
+    vm = np.full(d.shape, 3, dtype=np.uint8)
+    vm[9:11, 11:13, 5:7] = 0
+    return d, vm

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     # vrg_config: 3+2 int64, 2 int32, double, 2 int64, double ; vrg_result: 12 int64
     import ctypes
     assert ctypes.sizeof(nat.Config) == 8 * 5 + 4 * 2 + 8 + 8 * 2 + 8
-    assert ctypes.sizeof(nat.Result) == 96
+    assert ctypes.sizeof(nat.Result) == 104
 
 
 def test_create_rejects_bad_arguments_without_gpu():

@@ -24,6 +24,10 @@ def _case(name):
     if name == "excl":
         return make_phantom((40, 60, 100), seed=1, cell=(40, 60, 100), margin=4, depth=3, root_r2=9, min_len=8, max_len=16,
                             exclude_below_k=40)[:2] + (10 ** 12,)
+    if name == "shift":  # the decision table changes twice in the middle of the run: the pipelined run repeats two sweeps
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from random_cases import table_shift_case
+        return table_shift_case() + (10 ** 12,)
     raise KeyError(name)
 
 
@@ -54,7 +58,8 @@ def _worker(rank, world, port, name, mode, transport, out_dir):
 
 
 @pytest.mark.parametrize("transport", ["p2p", "collective"])
-@pytest.mark.parametrize("name,mode", [("forest", "f64_dense"), ("forest", "index"), ("excl", "f64_band")])
+@pytest.mark.parametrize("name,mode", [("forest", "f64_dense"), ("forest", "index"), ("excl", "f64_band"), ("shift", "f64_dense"),
+                                       ("shift", "index")])
 def test_slabs_equal_oracle(name, mode, transport, tmp_path):
     import torch
     import torch.multiprocessing as mp

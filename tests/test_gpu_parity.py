@@ -456,20 +456,48 @@ def test_attach_device_with_an_8_byte_aligned_buffer():
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", ["forest40", "removal32", "cancel32", "maxseg", "forest_two_trees"])
 def test_fused_tail_equals_the_separate_kernels(name, mode, monkeypatch):
-    """vrg_run's production path (sweep + ONE cooperative tail kernel per iteration, vrg_tail.cuh) against the same run on the
-    separate kernels (k_cancel, k_quirks, k_advance, k_table: the path the host-driven API and the label-4 runs use): labels,
-    trace, exit, counters and -- bit for bit -- the decision table's Parzen sums."""
-    if name not in golden_names():
-        pytest.skip("fixture %s not present" % name)
+    """vrg_run's production path (pipelined: sweep + ONE cooperative tail kernel per iteration, statistics and next table
+    beside the next sweep, vrg_tail.cuh) against the in-order fused tail (VRG_NO_PIPELINE) and against the separate kernels
+    (VRG_NO_FUSED_TAIL: k_cancel, k_quirks, k_advance, k_table -- the path the host-driven API and the label-4 runs use):
+    labels, trace, exit, counters and -- bit for bit -- the decision table's Parzen sums."""
     g = load_golden(name)
     a = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], mode)
+    monkeypatch.setenv("VRG_NO_PIPELINE", "1")
+    c = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], mode)
+    monkeypatch.delenv("VRG_NO_PIPELINE")
     monkeypatch.setenv("VRG_NO_FUSED_TAIL", "1")
     b = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], mode)
     monkeypatch.delenv("VRG_NO_FUSED_TAIL")
-    assert a["iterations"] == b["iterations"] == g["iterations"] and a["exit_reason"] == b["exit_reason"]
-    assert np.array_equal(a["labels"], b["labels"]) and np.array_equal(a["trace"], b["trace"])
-    for k in ("q_cancelled", "q_add_to_inside", "q_remove_to_outside", "q_cancel_repromoted", "n_in", "n_out", "sweeps"):
-        assert a[k] == b[k], k
-    for x, y in zip(a["table"], b["table"]):
-        assert np.array_equal(np.asarray(x).view(np.uint64), np.asarray(y).view(np.uint64))
-    assert a["kernel_launches"] < b["kernel_launches"]
+    assert b["redone_sweeps"] == 0 and c["redone_sweeps"] == 0
+    for o in (b, c):
+        assert a["iterations"] == o["iterations"] == g["iterations"] and a["exit_reason"] == o["exit_reason"]
+        assert np.array_equal(a["labels"], o["labels"]) and np.array_equal(a["trace"], o["trace"])
+        for k in ("q_cancelled", "q_add_to_inside", "q_remove_to_outside", "q_cancel_repromoted", "n_in", "n_out", "sweeps"):
+            assert a[k] == o[k], k
+        for x, y in zip(a["table"], o["table"]):
+            assert np.array_equal(np.asarray(x).view(np.uint64), np.asarray(y).view(np.uint64))
+    assert c["kernel_launches"] < b["kernel_launches"]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_pipelined_run_repeats_a_sweep_when_the_table_changes(mode, monkeypatch):
+    """The decision table of tests/random_cases.table_shift_case changes twice in the middle of the run.  The pipelined run
+    starts each sweep before the previous update's table is known: it must notice the change (redone_sweeps), repeat the sweep
+    on the new table, and end bit-identical to the oracle and to the in-order paths."""
+    from oracle.vrg_oracle import vrg_oracle
+    from random_cases import table_shift_case
+    data, vm = table_shift_case()
+    ref = vrg_oracle(data, vm, H=2.25, max_segment_size=10 ** 9, record_tables=True)
+    changes = 0
+    for (pa, qa), (pb, qb) in zip(ref["tables"][:-1], ref["tables"][1:]):
+        changes += not np.array_equal(np.asarray(pa) >= np.asarray(qa), np.asarray(pb) >= np.asarray(qb))
+    assert changes >= 2
+    a = run_engine(data, vm, 2.25, 10 ** 9, mode)
+    assert a["redone_sweeps"] == changes
+    monkeypatch.setenv("VRG_NO_PIPELINE", "1")
+    b = run_engine(data, vm, 2.25, 10 ** 9, mode)
+    monkeypatch.delenv("VRG_NO_PIPELINE")
+    for o in (a, b):
+        assert o["iterations"] == ref["iterations"] and o["sweeps"] == ref["iterations"]
+        assert np.array_equal(o["labels"], ref["labels"]) and np.array_equal(o["trace"], ref["trace"])
+    assert b["redone_sweeps"] == 0
