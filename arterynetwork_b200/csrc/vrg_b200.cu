@@ -96,7 +96,8 @@ struct vrg_handle {
     unsigned long long *d_tail_dbg = nullptr;  // phase timings of the tail kernel (profiling runs)
     bool tail_ok = true;              // A/B switch VRG_NO_FUSED_TAIL, or the cooperative launch is not available
     bool tail_checked = false;
-    bool pipe_ok = true;              // A/B switch VRG_NO_PIPELINE: statistics + next table beside the next sweep (vrg_tail.cuh)
+    int pipe_mode = -1;               // statistics + next table beside the next sweep (vrg_tail.cuh): -1 = on slabs (where the
+                                      // all-to-all exchange is worth hiding), 0 = never, 1 = always (switch VRG_PIPELINE=0|1)
     bool async_pending = false;       // the second stream holds work the next tail kernel has to wait for
 };
 
@@ -172,7 +173,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;  // A/B switch: plain loads instead of the TMA rings (sweep, init histogram)
     h->graph_ok = getenv("VRG_NO_GRAPH") == nullptr;    // A/B switch: vrg_run stays on plain stream launches
     h->tail_ok = getenv("VRG_NO_FUSED_TAIL") == nullptr;  // A/B switch: the separate kernels behind the sweep
-    h->pipe_ok = getenv("VRG_NO_PIPELINE") == nullptr;    // A/B switch: in-order iterations (table before every sweep)
+    if (const char *e = getenv("VRG_PIPELINE")) h->pipe_mode = atoi(e) != 0;  // A/B switch (default: pipelined on slabs only)
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     Params &p = h->p;
@@ -807,7 +808,8 @@ int vrg_p2p_export(vrg_handle *h, int world, void *handles_out) {
     const Params &p = h->p;
     const int slot_words = 2 * VRG_MAX_LEVELS + ST_EXTRA;
     if (!h->d_recv) {
-        const size_t rb = (size_t)2 * P2P_KINDS * 2 * HALO * p.plane_words * sizeof(uint32_t);  // two sequence parities
+        const size_t rb = (size_t)2 * P2P_KINDS * 2 * HALO * p.plane_words * sizeof(uint32_t)   // two sequence parities
+                          + (size_t)2 * 2 * HALO * p.plane_words * sizeof(unsigned long long);      // + the tagged slots (p2p_ll_region)
         const size_t sb = (size_t)2 * world * slot_words * sizeof(long long);
         CK(cudaMalloc((void **)&h->d_recv, rb));
         CK(cudaMalloc((void **)&h->d_flags, FLAG_WORDS_ALL * sizeof(unsigned long long)));
@@ -1063,7 +1065,7 @@ static int join_async(vrg_handle *h) {
 
 static int enqueue_batch(vrg_handle *h, int n) {
     const bool fused = tail_applies(h);
-    const bool piped = fused && h->pipe_ok;
+    const bool piped = fused && (h->pipe_mode < 0 ? h->p2p_on : h->pipe_mode != 0);
     if (piped) { int rc_ = ensure_side_stream(h); if (rc_ != VRG_OK) return rc_; }
     for (int k = 0; k < n; ++k) {
         int rc;
@@ -1118,7 +1120,7 @@ static uint64_t run_signature(const vrg_handle *h) {
     };
     mix(&h->p, sizeof(Params));
     if (h->p2p_on) mix(&h->q, sizeof(P2P));
-    const int64_t extra[5] = {h->cfg.intensity_mode, h->p2p_on, h->force_ldg, h->tail_ok, h->pipe_ok};
+    const int64_t extra[5] = {h->cfg.intensity_mode, h->p2p_on, h->force_ldg, h->tail_ok, h->pipe_mode};
     mix(extra, sizeof extra);
     return x;
 }

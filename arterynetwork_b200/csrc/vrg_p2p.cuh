@@ -39,6 +39,7 @@ struct P2P {
     unsigned long long *flags;                       // my flag words
     long long *slots;                                // my mailbox: [2 parities][world][slot_words]
     uint32_t *recv;                                  // my halo receive buffer: [2 parities][P2P_KINDS][2 sides][HALO][plane_words]
+                                                     // uint32, then [2 parities][2 sides][HALO][plane_words] tagged 8-byte slots
     unsigned long long *peer_flags[P2P_MAX_WORLD];   // every rank's flag words (mine included)
     long long *peer_slots[P2P_MAX_WORLD];
     uint32_t *peer_recv[2];                          // lower / upper neighbour's receive buffer (nullptr at the ends)
@@ -54,6 +55,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *addr, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *addr) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+    return v;
+}
+// the receive buffer's second part: tagged 8-byte slots [2 parities][2 sides][n] of the pipelined run's halo exchange
+// (n = HALO * plane_words); it starts behind the [2][P2P_KINDS][2][n] uint32 words of the flag-based exchange
+__device__ __forceinline__ unsigned long long *p2p_ll_region(uint32_t *recv, long long n) {
+    return (unsigned long long *)(recv + 2 * P2P_KINDS * 2 * n);
 }
 // spin until *flag >= seq; false on timeout (the caller raises the peer-timeout exit)
 __device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigned long long seq) {

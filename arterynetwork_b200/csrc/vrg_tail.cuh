@@ -262,9 +262,9 @@ __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail(Params p, P2P q, long lo
                 long long *dst = q.peer_slots[r] + ((long long)par * q.world + q.rank) * q.slot_words;
                 for (int i = threadIdx.x; i < n; i += TAIL_BLOCK) dst[i] = p.lstats[i];
             }
-            __threadfence_system();
             __syncthreads();
             if (threadIdx.x == 0) s_ok = 1;
+            if (threadIdx.x < q.world) __threadfence_system();  // the block's stores precede it through the barrier
             if (threadIdx.x < q.world) st_release_sys(q.peer_flags[threadIdx.x] + STATS_FLAGS + par * P2P_MAX_WORLD + q.rank, seq);
             __syncthreads();
             if (threadIdx.x < q.world && !p2p_wait(q.flags + STATS_FLAGS + par * P2P_MAX_WORLD + threadIdx.x, seq)) s_ok = 0;
@@ -308,9 +308,9 @@ __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail(Params p, P2P q, long lo
                     const uint32_t *src = p.F + (long long)(side == 0 ? p.own_lo : p.own_hi - HALO) * p.plane_words;
                     for (long long i = lo + threadIdx.x; i < hi; i += TAIL_BLOCK) dst[i] = __ldcg(src + i);
                 }
-                __threadfence_system();
-                __syncthreads();
+                __syncthreads();  // the block's stores are ordered before thread 0's fence by the barrier (cumulativity)
                 if (threadIdx.x == 0) {
+                    __threadfence_system();
                     if (q.peer_recv[0]) st_release_sys(q.peer_flags[q.rank - 1] + CHUNK_FLAGS + 1 * MAX_CHUNKS + j, seq);
                     if (q.peer_recv[1]) st_release_sys(q.peer_flags[q.rank + 1] + CHUNK_FLAGS + 0 * MAX_CHUNKS + j, seq);
                 }
@@ -390,7 +390,6 @@ __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail(Params p, P2P q, long lo
 template <int MODE, bool LATTICE, bool TIMED>
 __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail_pipe(Params p, P2P q, unsigned int *gbar, int p2p, unsigned long long *dbg) {
     __shared__ long long s_ctl[6];
-    __shared__ int s_ok;
     if (threadIdx.x == 0) {
         s_ctl[0] = p.ctrl[C_STATUS]; s_ctl[1] = p.ctrl[C_APPLY]; s_ctl[2] = p.ctrl[C_SWEEPS]; s_ctl[3] = p.ctrl[C_EPOCH];
         s_ctl[4] = p.ctrl[C_TABLE_NEW]; s_ctl[5] = p.ctrl[C_TABLE_BUF];
@@ -478,59 +477,53 @@ __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail_pipe(Params p, P2P q, un
     // ---- phase 2: halo exchange with the two neighbour slabs; order-dependence counters ---------------------------------
     if (go && !p2p) quirk_rows(false);
     else if (go) {
+        // Halo exchange, self-validating: every 32-bit word of the two boundary planes travels as one 8-byte store that
+        // carries the update's tag in its upper half (what NCCL calls the LL protocol).  No fence and no flag: a system-scope
+        // fence behind stores to a peer costs a full NVLink round trip per block (8 us measured here), an 8-byte store is
+        // visible as a whole.  The receiver polls each slot until the tag matches.  Slots are double-buffered by update parity
+        // (a neighbour may be one update ahead); a tag never repeats within 2048 runs x 2^20 updates.
         const long long n = (long long)HALO * p.plane_words;
-        const int nch = min(G, MAX_CHUNKS);
-        const long long par_off = (long long)(seq & 1ull) * P2P_KINDS * 2 * n;
-        const int j = (int)blockIdx.x;  // this block's chunk of the halo planes (blocks beyond MAX_CHUNKS have none)
-        const long long lo = j < nch ? n * j / nch : 0, hi = j < nch ? n * (j + 1) / nch : 0;
-        if (j < nch) {
+        const unsigned long long tag = (unsigned long long)((((uint32_t)s_ctl[3] & 0x7FFu) << 20) | ((uint32_t)(sweep + 1) & 0xFFFFFu) | 0x80000000u);
+        const long long par_off = (long long)((sweep + 1) & 1) * 2 * n;
+        const long long lo = n * blockIdx.x / G, hi = n * (blockIdx.x + 1) / G;  // this block's chunk of the halo planes
 #pragma unroll
-            for (int side = 0; side < 2; ++side) {  // side 0: to the lower neighbour (lands in its "from above" region)
-                uint32_t *dst = q.peer_recv[side];
-                if (dst == nullptr) continue;
-                dst += par_off + ((long long)PK_F * 2 + (side ^ 1)) * n;
-                const uint32_t *src = p.F + (long long)(side == 0 ? p.own_lo : p.own_hi - HALO) * p.plane_words;
-                for (long long i = lo + threadIdx.x; i < hi; i += TAIL_BLOCK) dst[i] = __ldcg(src + i);
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                if (q.peer_recv[0]) st_release_sys(q.peer_flags[q.rank - 1] + CHUNK_FLAGS + 1 * MAX_CHUNKS + j, seq);
-                if (q.peer_recv[1]) st_release_sys(q.peer_flags[q.rank + 1] + CHUNK_FLAGS + 0 * MAX_CHUNKS + j, seq);
-            }
+        for (int side = 0; side < 2; ++side) {  // side 0: to the lower neighbour (lands in its "from above" region)
+            if (q.peer_recv[side] == nullptr) continue;
+            unsigned long long *dst = p2p_ll_region(q.peer_recv[side], n) + par_off + (long long)(side ^ 1) * n;
+            const uint32_t *src = p.F + (long long)(side == 0 ? p.own_lo : p.own_hi - HALO) * p.plane_words;
+            for (long long i = lo + threadIdx.x; i < hi; i += TAIL_BLOCK)
+                st_relaxed_sys(dst + i, (tag << 32) | (unsigned long long)__ldcg(src + i));
         }
         stamp(6);
-        quirk_rows(false);  // while the neighbours' chunks travel
+        quirk_rows(false);  // while the neighbours' words travel
         stamp(7);
-        if (j < nch) {
-            if (threadIdx.x == 0) {
-                int ok = 1;
-                if (q.peer_recv[0] && !p2p_wait(q.flags + CHUNK_FLAGS + 0 * MAX_CHUNKS + j, seq)) ok = 0;
-                if (ok && q.peer_recv[1] && !p2p_wait(q.flags + CHUNK_FLAGS + 1 * MAX_CHUNKS + j, seq)) ok = 0;
-                if (!ok) { p.ctrl[C_PEER_TIMEOUT] = 1; p.ctrl[C_STATUS] = EXIT_PEER_TIMEOUT; }
-                s_ok = ok;
-                __threadfence_system();
-            }
-            __syncthreads();
-            if (s_ok) {
+        bool ok = true;
 #pragma unroll
-                for (int side = 0; side < 2; ++side) {  // side 0: data from the lower neighbour -> my lower halo planes
-                    if (q.peer_recv[side] == nullptr) continue;
-                    const uint32_t *src = q.recv + par_off + ((long long)PK_F * 2 + side) * n;
-                    const int z0 = side == 0 ? p.own_lo - HALO : p.own_hi;
-                    uint32_t *fdst = p.F + (long long)z0 * p.plane_words, *sdst = p.S + (long long)z0 * p.plane_words;
-                    for (long long i = lo + threadIdx.x; i < hi; i += TAIL_BLOCK) {
-                        const uint32_t f = __ldcg(src + i);
-                        fdst[i] = f;
-                        if (f) {  // the halo copy of the segmented plane follows the neighbour slab
-                            sdst[i] = __ldcg(sdst + i) ^ f;
-                            const int zl = z0 + (int)(i / p.plane_words), y = (int)((i % p.plane_words) / p.WP), c = (int)(i % p.WP);
-                            p.unitmap[unit_index(p, zl, y, c)] = 1;
-                        }
+        for (int side = 0; side < 2; ++side) {  // side 0: data from the lower neighbour -> my lower halo planes
+            if (q.peer_recv[side] == nullptr) continue;
+            const unsigned long long *src = p2p_ll_region(q.recv, n) + par_off + (long long)side * n;
+            const int z0 = side == 0 ? p.own_lo - HALO : p.own_hi;
+            uint32_t *fdst = p.F + (long long)z0 * p.plane_words, *sdst = p.S + (long long)z0 * p.plane_words;
+            for (long long i = lo + threadIdx.x; i < hi; i += TAIL_BLOCK) {
+                unsigned long long v = ld_relaxed_sys(src + i);
+                if ((v >> 32) != tag) {
+                    const long long t0 = clock64();
+                    while (((v = ld_relaxed_sys(src + i)) >> 32) != tag) {
+                        if (clock64() - t0 > P2P_SPIN_LIMIT) { ok = false; break; }
+                        __nanosleep(32);
                     }
+                    if (!ok) break;
+                }
+                const uint32_t f = (uint32_t)v;
+                fdst[i] = f;
+                if (f) {  // the halo copy of the segmented plane follows the neighbour slab
+                    sdst[i] = __ldcg(sdst + i) ^ f;
+                    const int zl = z0 + (int)(i / p.plane_words), y = (int)((i % p.plane_words) / p.WP), c = (int)(i % p.WP);
+                    p.unitmap[unit_index(p, zl, y, c)] = 1;
                 }
             }
         }
+        if (!ok) { p.ctrl[C_PEER_TIMEOUT] = 1; p.ctrl[C_STATUS] = EXIT_PEER_TIMEOUT; }
     }
     stamp(3);
     if (p2p) {
@@ -568,9 +561,9 @@ __global__ void __launch_bounds__(ASYNC_BLOCK) k_async_stats(Params p, P2P q, lo
             long long *dst = q.peer_slots[r] + ((long long)par * q.world + q.rank) * q.slot_words;
             for (int i = threadIdx.x; i < n; i += ASYNC_BLOCK) dst[i] = __ldcg(p.lstats + i);
         }
-        __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) s_ok = 1;
+        if (threadIdx.x < q.world) __threadfence_system();  // the block's stores precede it through the barrier
         if (threadIdx.x < q.world) st_release_sys(q.peer_flags[threadIdx.x] + STATS_FLAGS + par * P2P_MAX_WORLD + q.rank, seq);
         __syncthreads();
         if (threadIdx.x < q.world && !p2p_wait(q.flags + STATS_FLAGS + par * P2P_MAX_WORLD + threadIdx.x, seq)) s_ok = 0;

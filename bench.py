@@ -405,6 +405,10 @@ def bench_volume(ctx, shape, seed, intensity, steps, warmup, want_e2e, want_pari
         tp = eng.get_tail_profile()
         names = list(tp["first_block_us"])
         allr = ctx.gather_i64([int(tp["first_block_us"][k] * 1e3) for k in names] + [int(tp["last_block_us"][k] * 1e3) for k in names])
+        per_rank = ctx.gather_i64([int(prof["decide_ms"] / max(1, prof["decide_launches"]) * 1e6),
+                                   int(prof["cancel_ms"] / max(1, prof["cancel_launches"]) * 1e6)])
+        prof["sweep_us_per_rank"] = [round(v / 1e3, 2) for v in per_rank[:, 0].tolist()]
+        prof["tail_us_per_rank"] = [round(v / 1e3, 2) for v in per_rank[:, 1].tolist()]
         prof["tail_phases_us"] = {"launches": tp["launches"], "phases": names,
                                   "first_block_per_rank": [[round(v / 1e3, 2) for v in row[:len(names)]] for row in allr.tolist()],
                                   "last_block_per_rank": [[round(v / 1e3, 2) for v in row[len(names):]] for row in allr.tolist()]}
@@ -495,6 +499,7 @@ def roofline_of(r, peak, peak_kind, traffic=None, traffic_source=None, kernel="k
             "share_of_step": per_launch_ms * sweeps_per_step / (r["ms"] / max(1, r["steps"])),
             "tail_ms_per_launch": prof["cancel_ms"] / max(1, prof["cancel_launches"]),
             "tail_phases_us": prof.get("tail_phases_us"), "step_split_ms": prof.get("step_split_ms"),
+            "sweep_us_per_rank": prof.get("sweep_us_per_rank"), "tail_us_per_rank_eager": prof.get("tail_us_per_rank"),
             "note": "rank 0's slab (own planes +-1)"}
 
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # gpurun --gpus N -- bash scripts/gpu_multi_ab.sh N [TAG] : multi-GPU parity tests, then the N-GPU bench on the production path
-# (pipelined: statistics + table beside the next sweep) and, for comparison, in order (VRG_NO_PIPELINE=1: fused tail kernel) and
+# (pipelined: statistics + table beside the next sweep) and, for comparison, in order (VRG_PIPELINE=0: fused tail kernel) and
 # on the separate kernels (VRG_NO_FUSED_TAIL=1: halo exchange on a second stream)
 N=${1:-2}
 TAG=${2:-r2}
@@ -15,5 +15,5 @@ run() {  # port, name, env
   tail -c 1500 gpurun_out/${TAG}_scale_${N}_$2.json; tail -n 3 gpurun_out/${TAG}_scale_${N}_$2.err
 }
 run 29511 pipelined VRG_X=1
-run 29512 inorder VRG_NO_PIPELINE=1
+run 29512 inorder VRG_PIPELINE=0
 run 29513 separate VRG_NO_FUSED_TAIL=1

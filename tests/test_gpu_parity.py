@@ -456,15 +456,15 @@ def test_attach_device_with_an_8_byte_aligned_buffer():
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", ["forest40", "removal32", "cancel32", "maxseg", "forest_two_trees"])
 def test_fused_tail_equals_the_separate_kernels(name, mode, monkeypatch):
-    """vrg_run's production path (pipelined: sweep + ONE cooperative tail kernel per iteration, statistics and next table
-    beside the next sweep, vrg_tail.cuh) against the in-order fused tail (VRG_NO_PIPELINE) and against the separate kernels
-    (VRG_NO_FUSED_TAIL: k_cancel, k_quirks, k_advance, k_table -- the path the host-driven API and the label-4 runs use):
-    labels, trace, exit, counters and -- bit for bit -- the decision table's Parzen sums."""
+    """vrg_run's paths against each other: the in-order fused tail (sweep + ONE cooperative tail kernel per iteration, the
+    default on one GPU), the pipelined run (statistics and next table beside the next sweep, the default on slabs; forced here
+    with VRG_PIPELINE=1) and the separate kernels (VRG_NO_FUSED_TAIL: k_cancel, k_quirks, k_advance, k_table -- the path the
+    host-driven API and the label-4 runs use): labels, trace, exit, counters and -- bit for bit -- the decision table's sums."""
     g = load_golden(name)
-    a = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], mode)
-    monkeypatch.setenv("VRG_NO_PIPELINE", "1")
     c = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], mode)
-    monkeypatch.delenv("VRG_NO_PIPELINE")
+    monkeypatch.setenv("VRG_PIPELINE", "1")
+    a = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], mode)
+    monkeypatch.delenv("VRG_PIPELINE")
     monkeypatch.setenv("VRG_NO_FUSED_TAIL", "1")
     b = run_engine(g["data"], g["value_map_in"], g["H"], g["max_segment_size"], mode)
     monkeypatch.delenv("VRG_NO_FUSED_TAIL")
@@ -492,11 +492,11 @@ def test_pipelined_run_repeats_a_sweep_when_the_table_changes(mode, monkeypatch)
     for (pa, qa), (pb, qb) in zip(ref["tables"][:-1], ref["tables"][1:]):
         changes += not np.array_equal(np.asarray(pa) >= np.asarray(qa), np.asarray(pb) >= np.asarray(qb))
     assert changes >= 2
+    monkeypatch.setenv("VRG_PIPELINE", "1")
     a = run_engine(data, vm, 2.25, 10 ** 9, mode)
+    monkeypatch.delenv("VRG_PIPELINE")
     assert a["redone_sweeps"] == changes
-    monkeypatch.setenv("VRG_NO_PIPELINE", "1")
-    b = run_engine(data, vm, 2.25, 10 ** 9, mode)
-    monkeypatch.delenv("VRG_NO_PIPELINE")
+    b = run_engine(data, vm, 2.25, 10 ** 9, mode)  # one GPU: in order
     for o in (a, b):
         assert o["iterations"] == ref["iterations"] and o["sweeps"] == ref["iterations"]
         assert np.array_equal(o["labels"], ref["labels"]) and np.array_equal(o["trace"], ref["trace"])
