@@ -55,6 +55,8 @@ struct vrg_handle {
     uint32_t *d_dbits = nullptr;
     long long *d_lstats = nullptr, *d_gstats = nullptr, *d_ctrl = nullptr, *d_trace = nullptr;
     long long *h_ctrl = nullptr;  // pinned
+    long long *h_poll = nullptr;  // pinned, 2 x C_WORDS: the control block as it stood behind the last two batches of vrg_run
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr};
     unsigned long long *d_hash = nullptr, *d_hkeys = nullptr;
     int *d_hcount = nullptr;
     std::vector<double> levels;  // distinct levels seen (sorted)
@@ -226,6 +228,8 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     alloc((void **)&h->d_tail_dbg, (16 + 2 * (size_t)h->sms) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(h->d_tail_dbg, 0, (16 + 2 * (size_t)h->sms) * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_ctrl, C_WORDS * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_poll, 2 * C_WORDS * sizeof(long long));
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         int code = fail(e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA, "allocation: %s", cudaGetErrorString(e));
         vrg_destroy(h);
@@ -258,6 +262,8 @@ int vrg_destroy(vrg_handle *h) {
     for (void *o : h->ipc_opened) cudaIpcCloseMemHandle(o);
     cudaFree(h->d_recv); cudaFree(h->d_flags); cudaFree(h->d_slots);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+    if (h->h_poll) cudaFreeHost(h->h_poll);
+    for (int i = 0; i < 2; ++i) if (h->ev_poll[i]) cudaEventDestroy(h->ev_poll[i]);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1135,6 +1141,7 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
     const auto t0 = std::chrono::steady_clock::now();
     bool use_graph = !h->prof && h->graph_ok;
     bool first = true, time_flagged = false;
+    long long nbatch = 0;
     if (h->cfg.intensity_mode != VRG_INTENSITY_CONTINUOUS) {
         // the decision table + bookkeeping in front of the first sweep; every later one is the last phase of the tail kernel
         // (the separate-kernel path recomputes it in front of each sweep: same stats, same table)
@@ -1176,11 +1183,22 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
             if (rc != VRG_OK) return rc;
         }
         first = false;
-        int rc = vrg_poll(h, &r);
-        if (rc != VRG_OK) return rc;
-        if (r.exit_reason == EXIT_PEER_TIMEOUT) return fail(VRG_ERR_CUDA, "peer GPU did not answer (p2p timeout)");
-        if (r.exit_reason == EXIT_CONT_OVERFLOW) return fail(VRG_ERR_ARG, "continuous mode: band list overflow (%d voxels)", h->cq.cap);
-        if (r.exit_reason != VRG_EXIT_RUNNING) break;
+        // The status word of this batch travels to the host behind it.  With graph replay the host does not wait for it: it
+        // queues the next batch first and only then looks at the previous one, so the device never idles between batches (a
+        // stream synchronise + a poll + a graph launch cost about 30 us per batch of 8 iterations); the price is one batch of
+        // no-op launches after the exit.
+        const int slot = (int)(nbatch & 1);
+        CK(cudaMemcpyAsync(h->h_poll + slot * C_WORDS, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_poll[slot], h->stream));
+        ++nbatch;
+        const bool ahead = use_graph && h->gexec != nullptr;
+        if (ahead && nbatch < 2) continue;  // nothing older to look at yet
+        const int look = ahead ? (int)((nbatch - 2) & 1) : slot;
+        CK(cudaEventSynchronize(h->ev_poll[look]));
+        const long long st = h->h_poll[look * C_WORDS + C_STATUS];
+        if (st == EXIT_PEER_TIMEOUT) return fail(VRG_ERR_CUDA, "peer GPU did not answer (p2p timeout)");
+        if (st == EXIT_CONT_OVERFLOW) return fail(VRG_ERR_ARG, "continuous mode: band list overflow (%d voxels)", h->cq.cap);
+        if (st != VRG_EXIT_RUNNING) break;
         if (h->cfg.max_seconds > 0 &&
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() >= h->cfg.max_seconds) {
             // VRG:97: stop before applying the next flips; the state is that of the last applied update
@@ -1194,12 +1212,21 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
                 }
                 continue;
             }
-            h->h_ctrl[C_STATUS] = VRG_EXIT_MAX_TIME;
-            CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            r.exit_reason = VRG_EXIT_MAX_TIME;
+            CK(cudaStreamSynchronize(h->stream));  // a batch queued ahead finishes first
+            CK(cudaMemcpy(h->h_ctrl, h->d_ctrl, sizeof(long long), cudaMemcpyDeviceToHost));
+            if (h->h_ctrl[C_STATUS] == VRG_EXIT_RUNNING) {
+                h->h_ctrl[C_STATUS] = VRG_EXIT_MAX_TIME;
+                CK(cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+            }
             break;
         }
+    }
+    {   // drain whatever was queued ahead and read the final state
+        int rc = vrg_poll(h, &r);
+        if (rc != VRG_OK) return rc;
+        if (r.exit_reason == EXIT_PEER_TIMEOUT) return fail(VRG_ERR_CUDA, "peer GPU did not answer (p2p timeout)");
+        if (r.exit_reason == EXIT_CONT_OVERFLOW) return fail(VRG_ERR_ARG, "continuous mode: band list overflow (%d voxels)", h->cq.cap);
     }
     if (h->p2p_on) {
         // every rank left the loop at the same update: one more statistics exchange folds in what trailed the last one
