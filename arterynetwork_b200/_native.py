@@ -64,6 +64,8 @@ _SIGS = {
     "vrg_profile": [vp, ctypes.c_int],
     "vrg_get_profile": [vp, vp, vp],
     "vrg_get_tail_profile": [vp, vp, ctypes.POINTER(i64)],
+    "vrg_get_exp_evals": [vp, ctypes.POINTER(i64)],
+    "vrg_exp_peak": [ctypes.c_int, ctypes.POINTER(ctypes.c_double)],
     "vrg_buffer_info": [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(i64)],
     "vrg_plane_geometry": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)],
     "vrg_use_separate_global_stats": [vp],

@@ -1295,6 +1295,42 @@ int vrg_params_signature(vrg_handle *h, uint64_t *sig) {
     return VRG_OK;
 }
 
+// fp64 Parzen-kernel evaluations per second this device sustains (k_exp_peak): the continuous mode's roofline
+int vrg_exp_peak(int device, double *evals_per_second) {
+    if (!evals_per_second) return fail(VRG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    double *out = nullptr;
+    CK(cudaMalloc((void **)&out, (size_t)grid * BLOCK * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_exp_peak<<<grid, BLOCK>>>(-1.125, 64, out);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_exp_peak<<<grid, BLOCK>>>(-1.125, iters, out);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *evals_per_second = (double)grid * BLOCK * iters * 8.0 / ((double)best * 1e-3);
+    return VRG_OK;
+}
+int vrg_get_exp_evals(vrg_handle *h, int64_t *evals) {
+    NEED_INIT();
+    if (!evals) return fail(VRG_ERR_ARG, "null argument");
+    long long v = 0;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(&v, h->d_lstats + 2 * h->p.L + ST_EXP_EVALS, sizeof v, cudaMemcpyDeviceToHost));
+    *evals = v;
+    return VRG_OK;
+}
+
 int vrg_profile(vrg_handle *h, int enable) {
     if (!h) return fail(VRG_ERR_ARG, "null handle");
     h->prof = enable != 0;

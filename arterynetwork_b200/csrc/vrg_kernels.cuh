@@ -39,6 +39,7 @@ enum { ST_N_IN = 0, ST_N_OUT = 1, ST_N_EXCL = 2, ST_N_FLIPS = 3, ST_N_BAND = 4, 
        ST_Q_CANCELLED = 8, ST_Q_ADD_INSIDE = 9, ST_Q_REM_OUTSIDE = 10, ST_Q_REPROMOTED = 11,
        ST_N_FLIPS_SNAP = 12,  // pipelined run (vrg_tail.cuh): the flip count of the update just applied, set aside by the tail kernel
                               // while the next sweep already counts into ST_N_FLIPS
+       ST_EXP_EVALS = 13,     // continuous mode: Parzen kernel evaluations (fp64 exp) so far -- its roofline is the exp rate
        ST_EXTRA = 16 };
 enum { C_STATUS = 0, C_ITER = 1, C_ITER_MAX = 2, C_MAX_SEG = 3, C_APPLY = 4, C_APPLIED = 5, C_TRACE_N = 6, C_SWEEPS = 7, C_FULL_SWEEP = 8,
        C_EPOCH = 9, C_PEER_TIMEOUT = 10, C_HALO_SEQ = 11, C_HALO_GO = 12,  // 9..12: slab runs (vrg_p2p.cuh)

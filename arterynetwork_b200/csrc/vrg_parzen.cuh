@@ -20,7 +20,9 @@ namespace vrg {
 
 enum { CC_NEW = 0, CC_OLD = 1, CC_ROWS = 2, CC_OVERFLOW = 3, CC_ABROWS = 4, CC_WORDS = 8 };
 constexpr int CONT_TILE = 16;    // new voxels whose sums one block accumulates while streaming the volume
-constexpr int CONT_SPLIT = 8;    // volume partitions per tile (second-stage sum in partition order)
+constexpr int CONT_SPLIT = 32;   // volume partitions per tile (second-stage sum in partition order): a few hundred entering voxels
+                                 // are 10-20 tiles, and 20 x 8 blocks left most of the 148 SMs with one block of 8 warps (33 % of the
+                                 // fp64 exp rate); 32 partitions fill them
 constexpr long long EXIT_CONT_OVERFLOW = 98;
 
 struct Cont {
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(BLOCK) k_cont_incr(Params p, Cont q) {
         const int vox = q.oldlist[i];
         const double v = p.data[vox];
         double sum_a = 0.0, sum_r = 0.0;
+        unsigned long long nev = 0;
         for (int k = 0; k < nrows; ++k) {
             const int rr = q.rowlist[k];
             const int sg = rr % p.nseg, t = rr / p.nseg, y = t % p.Y, zl = t / p.Y;
@@ -180,6 +183,7 @@ __global__ void __launch_bounds__(BLOCK) k_cont_incr(Params p, Cont q) {
                 uint32_t f = p.F[wrow + c];  // executed flips (k_cancel rewrote the word)
                 if (!f) continue;
                 const uint32_t snew = p.S[wrow + c];
+                nev += __popc(f);
                 while (f) {
                     const int b = __ffs(f) - 1;
                     f &= f - 1;
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__(BLOCK) k_cont_incr(Params p, Cont q) {
             const long long vrow = (long long)zl * p.plane_vox + (long long)y * p.X;
             for (int c = sg * p.segw; c < min((sg + 1) * p.segw, p.XW); ++c) {
                 uint32_t ab = q.AB[wrow + c];
+                nev += __popc(ab);
                 while (ab) {
                     const int b = __ffs(ab) - 1;
                     ab &= ab - 1;
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(BLOCK) k_cont_incr(Params p, Cont q) {
         }
         q.pin[vox] = q.pin[vox] + sum_a - sum_r;            // innerProb += innerCorrection; innerProb -= outerCorrection
         q.pout[vox] = q.pout[vox] - sum_a + sum_r + sum_ab;  // outerProb -= inner...; += outer...; += addedCorrection
+        if (nev) atomicAdd((unsigned long long *)&p.lstats[ST_EXP_EVALS], nev);
     }
 }
 
@@ -268,6 +274,9 @@ __global__ void __launch_bounds__(BLOCK) k_cont_full1(Params p, Cont q) {
 __global__ void __launch_bounds__(BLOCK) k_cont_full2(Params p, Cont q) {
     if (p.ctrl[C_STATUS] != RUNNING) return;
     const int n_new = min(q.count[CC_NEW], q.cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0)  // every entering voxel met every voxel of the two regions once
+        atomicAdd((unsigned long long *)&p.lstats[ST_EXP_EVALS],
+                  (unsigned long long)n_new * (unsigned long long)(p.gstats[ST_N_IN] + p.gstats[ST_N_OUT]));
     for (int j = blockIdx.x * BLOCK + threadIdx.x; j < n_new; j += gridDim.x * BLOCK) {
         const int tile = j / CONT_TILE, k = j % CONT_TILE;
         double si = 0.0, so = 0.0;
@@ -320,6 +329,24 @@ __global__ void __launch_bounds__(BLOCK) k_cont_decide(Params p, Cont q) {
     }
     flips = warp_sum(flips);
     if (lane == 0 && flips) atomicAdd((unsigned long long *)&p.lstats[ST_N_FLIPS], (unsigned long long)flips);
+}
+
+// fp64 exp rate of the device with nothing else in the way: the roofline of the continuous mode (independent chains, the same
+// expression as parzen()).  out[thread] keeps the compiler honest.
+__global__ void __launch_bounds__(BLOCK) k_exp_peak(double mhH, int iters, double *out) {
+    const double a = (double)threadIdx.x * 1e-3, b = (double)blockIdx.x * 1e-6;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double d = a - (b + (double)(i * 8 + k) * 1e-7);
+            acc[k] += 0.3989422804014327 * exp(mhH * (d * d));
+        }
+    }
+    double t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += acc[k];
+    out[(size_t)blockIdx.x * BLOCK + threadIdx.x] = t;
 }
 
 }  // namespace vrg

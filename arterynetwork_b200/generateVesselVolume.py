@@ -47,6 +47,9 @@ def distance_transform_edt(input, device: int = 0) -> np.ndarray:
 def labelVolume(volume, minSize=1, maxHop=3, device: int = 0):
     """GVV:108-136: 26-connected components (``skimage.measure.label(volume, return_num=True, connectivity=maxHop)``).
 
+    Exact for binary volumes (background 0, one foreground value), which is what the reference passes; a volume with several
+    distinct non-zero values raises ``ValueError`` (skimage would label per value).
+
     Returns ``(labeled, labelResult)``: ``labeled`` holds 0 on the background and 1..K on the components, numbered in
     raster order of their first voxel; ``labelResult`` is ``[(label, size), ...]`` over every label present, the
     background entry ``(0, n0)`` included, exactly as the reference builds it from ``np.bincount`` (``minSize`` is
@@ -54,7 +57,17 @@ def labelVolume(volume, minSize=1, maxHop=3, device: int = 0):
     """
     if maxHop != 3:
         raise ValueError("labelVolume: only maxHop=3 (26-connectivity), the value the reference uses (GVV:196)")
-    b = np.ascontiguousarray(np.asarray(volume) != 0, dtype=np.uint8)  # skimage labels the non-zero voxels
+    vol = np.asarray(volume)
+    nz = vol != 0
+    # skimage.measure.label joins neighbours of EQUAL value: two touching regions with different non-zero values get different
+    # labels there.  This drop-in labels the non-zero mask, which is the same thing only for two-valued volumes -- all the
+    # reference ever passes (GVV:195 binarises first; skeletonization.py:108 passes a 0/1 mask).  Anything else is refused.
+    if nz.any():
+        vals = vol[nz]
+        if vals.min() != vals.max():
+            raise ValueError("labelVolume: the volume holds more than one non-zero value; skimage.measure.label would split "
+                             "touching regions of different value, this drop-in is exact for binary (0 / v) volumes only")
+    b = np.ascontiguousarray(nz, dtype=np.uint8)
     n = ctypes.c_int64(0)
     labeled = np.empty(b.shape, dtype=np.int32)
     sizes = np.zeros(max(1, b.size // 2 + 1), dtype=np.int64) if b.size < (1 << 22) else None

@@ -151,6 +151,11 @@ int vrg_get_profile(vrg_handle *h, double *ms_total /*[2]*/, int64_t *launches /
  * parts of its phase 2); us[7..13] = the same for the grid's last block. */
 int vrg_get_tail_profile(vrg_handle *h, double *us /*[14]*/, int64_t *launches);
 
+/* continuous mode (VRG_INTENSITY_CONTINUOUS): Parzen kernel evaluations (fp64 exp, VRG:154,253-254) of the run so far, and the
+ * rate of the same expression on an otherwise idle device -- its roofline is the exp rate, not HBM */
+int vrg_get_exp_evals(vrg_handle *h, int64_t *evals);
+int vrg_exp_peak(int device, double *evals_per_second);
+
 /* device buffers a multi-GPU host exchanges between the enqueue calls ------- */
 typedef enum {
     VRG_BUF_SEG = 0,          /* segmented bit-plane */

@@ -28,9 +28,19 @@ def main():
             torch.cuda.synchronize()
             out.append(time.perf_counter() - t0)
         seg = eng.segmented_map()
+        import ctypes
+        from arterynetwork_b200 import _native as nat
+        ev = nat.i64(0)
+        nat.check(eng.lib.vrg_get_exp_evals(eng._h, ctypes.byref(ev)))
+        peak = ctypes.c_double(0)
+        nat.check(eng.lib.vrg_exp_peak(0, ctypes.byref(peak)))
     print(json.dumps({"workload": "128^3 continuous phantom (2,097,152 distinct intensities)", "seconds": out,
                       "iterations": res["iterations"], "segmented": res["n_in"], "tube_voxels": info["tube_voxels"],
                       "segmented_equals_tube": bool(seg.sum() == info["tube_voxels"]),
+                      "roofline": {"bound": "fp64 exp", "unit": "G kernel evaluations/s", "evaluations_per_run": int(ev.value),
+                                   "achieved": ev.value / min(out) / 1e9, "peak": peak.value / 1e9,
+                                   "frac": ev.value / min(out) / peak.value,
+                                   "peak_how": "k_exp_peak: the same A*exp(-H/2 d^2) in eight independent chains per thread, idle device"},
                       "reference_seconds_same_shape_quantised": 596.0}))
 
 

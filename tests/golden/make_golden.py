@@ -143,6 +143,12 @@ def case_excl_cont():  # continuous intensities AND label 4: absorbed voxels joi
     return data, 0, vm, dict(H=2.25, max_segment_size=None)
 
 
+def case_forest64_cont():  # a 64^3 forest with the lattice broken by hash noise (262144 distinct values): the continuous mode at
+    # a size where its lists and its volume partition are exercised; stored as lattice + noise scale (tests/golden_util.py)
+    data, vm, _ = make_phantom((64, 64, 64), seed=2, cell=(64, 64, 64), margin=5, depth=3, root_r2=9, min_len=10, max_len=18)
+    return np.rint(data * 256).astype(np.int64), 256, vm.astype(np.int64), dict(H=2.25, max_segment_size=None, noise_scale=1e-3)
+
+
 def _tube_k(seed, q=128, sigma=0.12, shape=(16, 16, 28)):
     data = np.zeros(shape)
     data[6:10, 6:10, 4:24] = 1.0
@@ -217,6 +223,7 @@ CASES = {
     "tube_cont": case_tube_cont,
     "forest_cont": case_forest_cont,
     "excl_cont": case_excl_cont,
+    "forest64_cont": case_forest64_cont,
     "forest48_s1": case_forest48_s1,
     "forest_two_trees": case_forest_two_trees,
     "tube_h4": case_tube_h4,
@@ -225,7 +232,7 @@ CASES = {
     "excl32_b": case_excl32_b,
     "tube_fat_seed": case_tube_fat_seed,
 }
-SMALL = [c for c in CASES if c != "c1_128"]
+SMALL = [c for c in CASES if c not in ("c1_128", "forest64_cont")]
 
 
 def level_tables(res, data, max_levels=None):
@@ -248,9 +255,14 @@ def generate(name):
     k, q, vm, kw = CASES[name]()
     continuous = q == 0  # the case returns float64 data itself
     data = k if q in (0, 1) else k.astype(np.float64) / q
+    noise_scale = float(kw.get("noise_scale", 0.0))
+    if noise_scale > 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from golden_util import hash_noise
+        data = data + hash_noise(k.size, noise_scale).reshape(k.shape)
     t0 = time.time()
     res = run_reference(data, vm, H=kw["H"], max_segment_size=kw["max_segment_size"],
-                        check_drift=(name != "c1_128"))
+                        check_drift=(name not in ("c1_128", "forest64_cont")))
     wall = time.time() - t0
     tb_it, tb_lev, tb_pin, tb_pout = level_tables(res, data, max_levels=48 if k.size > 50 ** 3 else None)
     seg_rows = res["segmented"]
@@ -259,6 +271,7 @@ def generate(name):
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),
         k=(np.zeros(1, np.int16) if continuous else k.astype(np.int16)), quantum=np.int64(q), data_is_int=np.bool_(q == 1),
+        noise_scale=np.float64(noise_scale),
         data_f64=(data.astype(np.float64) if continuous else np.zeros(1)),
         value_map_in=np.asarray(vm, dtype=np.uint8),
         H=np.float64(kw["H"]),

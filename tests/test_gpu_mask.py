@@ -142,3 +142,61 @@ def test_argument_errors():
     with pytest.raises(ValueError):
         gvv().labelVolume(np.ones((4, 4, 4)), maxHop=1)
     assert nat.load().vrg_edt(0, None, None, None) == nat.ERR_ARG
+
+
+def test_component_merge_on_every_pair_of_seven_voxel_rows():
+    """The kernel-side twin of tests/test_mask_host.py::test_run_pair_pruning_rule_of_the_component_merge (which checks a Python
+    transcription of k_cc_merge's linking rule): all 2^14 pairs of 7-voxel rows, each pair isolated by background, go through
+    vrg_label_components itself; labels and sizes must equal the flood-fill oracle's, numbering included."""
+    import itertools
+    from oracle import mask_oracle as mo
+    W = 7
+    rows = np.array(list(itertools.product([0, 1], repeat=W)), dtype=bool)  # 128 rows
+    per_plane = 64
+    n_pairs = len(rows) ** 2
+    planes = n_pairs // per_plane
+    m = np.zeros((2 * planes, 3 * per_plane, W + 2), dtype=bool)  # every second plane and every third row stay empty
+    a_idx, b_idx = np.divmod(np.arange(n_pairs), len(rows))
+    z = 2 * (np.arange(n_pairs) // per_plane)
+    y = 3 * (np.arange(n_pairs) % per_plane)
+    m[z, y, 1:W + 1] = rows[a_idx]
+    m[z, y + 1, 1:W + 1] = rows[b_idx]
+    labeled, result = gvv().labelVolume(m)
+    olab, ores = mo.label_oracle(m)
+    assert np.array_equal(labeled, olab)
+    assert [tuple(map(int, r)) for r in result] == [tuple(map(int, r)) for r in ores]
+
+
+def test_edt_lines_fuzz_against_the_oracle():
+    """The kernel-side twin of tests/test_mask_host.py::test_edt_line_pass_transcription_equals_brute_force: the same four
+    kinds of adversarial lines (sparse zeros, lines without any zero, ramps, dense zeros) as thin volumes along each axis, so
+    that k_edt_rows and both k_edt_lines passes each see them, against the min-plus oracle."""
+    from oracle import mask_oracle as mo
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n = int(rng.integers(1, 70))
+        kind = trial % 4
+        if kind == 0:
+            line = rng.random(n) < 0.85
+        elif kind == 1:
+            line = np.ones(n, dtype=bool)  # no zero on the line: the distance comes from the other axes (or is "infinite")
+        elif kind == 2:
+            line = np.ones(n, dtype=bool); line[[0, -1]] = False
+        else:
+            line = rng.random(n) < 0.5
+        for axis in range(3):
+            shape = [int(rng.integers(1, 4)), int(rng.integers(1, 4)), int(rng.integers(1, 4))]
+            shape[axis] = n
+            m = np.ones(shape, dtype=bool)
+            idx = [slice(None)] * 3
+            for j in range(int(np.prod(shape)) // n):  # every line of the volume along `axis` gets a variant of the pattern
+                pos = list(np.unravel_index(j, [s for i, s in enumerate(shape) if i != axis]))
+                pos.insert(axis, slice(None))
+                v = np.roll(line, j)
+                if kind == 1 and j == 0:
+                    v = v.copy(); v[n // 2] = False  # one zero in the whole volume: every other line is "infinite" until it sees it
+                m[tuple(pos)] = v
+            got = gvv().distance_transform_edt(m)
+            want = mo.edt_oracle(m)
+            if not m.all():  # SciPy's (and the oracle's) result for a mask without any zero is not a distance; skipped
+                assert np.array_equal(got, want), (trial, axis, shape)

@@ -36,7 +36,9 @@ def test_argument_errors_raise_before_any_gpu_call():
 
 
 def test_run_pair_pruning_rule_of_the_component_merge():
-    """The rule k_cc_merge (csrc/vrg_mask.cu) uses to link a voxel to the previous row -- straight across only if the voxel
+    """DESIGN CHECK of the idea, not of the shipped kernel (its kernel-side twin, same inputs through vrg_label_components, is
+    tests/test_gpu_mask.py::test_component_merge_on_every_pair_of_seven_voxel_rows).
+    The rule k_cc_merge (csrc/vrg_mask.cu) uses to link a voxel to the previous row -- straight across only if the voxel
     or its neighbour starts an x-run, the left diagonal only across a background voxel and under the same condition, the
     right diagonal across a background voxel always -- transcribed to Python and checked exhaustively on all pairs of rows
     of 7 voxels: it links exactly the pairs of runs that touch (26-connectivity within two rows), each at least once."""
@@ -79,7 +81,9 @@ def test_run_pair_pruning_rule_of_the_component_merge():
 
 
 def test_edt_line_pass_transcription_equals_brute_force():
-    """The line pass of the distance transform (k_edt_lines, csrc/vrg_edt.cu) -- lower envelope of parabolas in which the
+    """DESIGN CHECK of the idea, not of the shipped kernel (kernel-side twin: tests/test_gpu_mask.py::
+    test_edt_lines_fuzz_against_the_oracle).
+    The line pass of the distance transform (k_edt_lines, csrc/vrg_edt.cu) -- lower envelope of parabolas in which the
     zeros inside a stretch of background are neither pushed nor popped -- transcribed to Python and fuzzed against the plain
     double loop, infinite inputs (rows without a zero voxel) included."""
     INF = 1 << 30
@@ -133,3 +137,11 @@ def test_edt_line_pass_transcription_equals_brute_force():
             f = np.where(rng.random(n) < 0.5, 0, rng.integers(1, 400, n))
         f = [int(v) for v in f]
         assert line_pass(f) == brute(f), f
+
+
+def test_label_volume_refuses_multi_valued_input_before_any_gpu_call():
+    """skimage.measure.label connects equal values only; the drop-in labels the non-zero mask: exact for binary volumes, and it
+    says so instead of returning different labels for a label map."""
+    v = np.zeros((3, 4, 5)); v[0, 0, 0] = 1; v[0, 0, 1] = 2
+    with pytest.raises(ValueError):
+        gvv.labelVolume(v)
