@@ -277,39 +277,36 @@ __global__ void __launch_bounds__(TABLE_BLOCK) k_table(Params p, int final) {
 //   dil26(~S in volume) = x-dilate(~(a[y-1] & a[y] & a[y+1]) & valid)
 // Rows are loaded two ahead of their use, so the L2 latency of the three 128-byte loads per row is hidden.
 struct Strip {
-    const uint32_t *z0, *z1, *z2;  // column pointers of planes zl-1, zl, zl+1 (nullptr = outside the volume)
-    int Y, WP;
+    long long base;  // word index of this lane's column in plane zl, row 0
     uint32_t vm;
+    int flags;       // bit 0: column inside the row, bit 1: plane zl-1 exists, bit 2: plane zl+1 exists, bit 3: active lane
     bool active;
     uint32_t op, ap, oc, ac, sc, on, an, sn, o2, a2, s2;  // rows y-1, y, y+1, y+2
 
-    __device__ __forceinline__ void row(int yy, uint32_t &o, uint32_t &a, uint32_t &s) const {
+    __device__ __forceinline__ void row(const Params &p, int yy, uint32_t &o, uint32_t &a, uint32_t &s) const {
         o = 0u; a = 0xFFFFFFFFu; s = 0u;
-        if (z1 != nullptr && yy >= 0 && yy < Y) {
-            const long long off = (long long)yy * WP;
-            s = z1[off];
-            const uint32_t w0 = z0 ? z0[off] : 0u, w2 = z2 ? z2[off] : 0u;
+        if ((flags & 1) && yy >= 0 && yy < p.Y) {
+            const uint32_t *q = p.S + base + (long long)yy * p.WP;
+            s = q[0];
+            const uint32_t w0 = (flags & 2) ? q[-p.plane_words] : 0u, w2 = (flags & 4) ? q[p.plane_words] : 0u;
             o = w0 | s | w2;
-            a = (z0 ? w0 : 0xFFFFFFFFu) & s & (z2 ? w2 : 0xFFFFFFFFu);
+            a = ((flags & 2) ? w0 : 0xFFFFFFFFu) & s & ((flags & 4) ? w2 : 0xFFFFFFFFu);
         }
     }
     __device__ __forceinline__ void begin(const Params &p, int zl, int y0, int c, int lane) {
         const bool inr = c >= 0 && c < p.XW;
         active = inr && lane >= 1 && lane <= p.segw;
         vm = inr ? valid_mask(p, c) : 0u;
-        Y = p.Y; WP = p.WP;
-        const uint32_t *col = p.S + (long long)zl * p.plane_words + c;
-        z1 = inr ? col : nullptr;
-        z0 = (inr && zl - 1 >= p.valid_lo) ? col - p.plane_words : nullptr;
-        z2 = (inr && zl + 1 < p.valid_hi) ? col + p.plane_words : nullptr;
+        base = (long long)zl * p.plane_words + c;
+        flags = (inr ? 1 : 0) | ((inr && zl - 1 >= p.valid_lo) ? 2 : 0) | ((inr && zl + 1 < p.valid_hi) ? 4 : 0);
         uint32_t sp;
-        row(y0 - 1, op, ap, sp);
-        row(y0, oc, ac, sc);
-        row(y0 + 1, on, an, sn);
+        row(p, y0 - 1, op, ap, sp);
+        row(p, y0, oc, ac, sc);
+        row(p, y0 + 1, on, an, sn);
     }
     // bands of row y (s = segmented word, returns inner | outer-without-E); then slides one row down
-    __device__ __forceinline__ void step(int y, uint32_t &s, uint32_t &inner, uint32_t &outer) {
-        row(y + 2, o2, a2, s2);
+    __device__ __forceinline__ void step(const Params &p, int y, uint32_t &s, uint32_t &inner, uint32_t &outer) {
+        row(p, y + 2, o2, a2, s2);
         const uint32_t dil_s = dilate_x1(op | oc | on);
         const uint32_t dil_n = dilate_x1(~(ap & ac & an) & vm);
         s = sc;
@@ -425,7 +422,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
             const int sg = r % p.nseg, t = r / p.nseg, y = t % p.Y, zl = t / p.Y;
             st.begin(p, zl, y, sg * p.segw - 1 + lane, lane);
             uint32_t s, inner, outer;
-            st.step(y, s, inner, outer);
+            st.step(p, y, s, inner, outer);
             flips += band_row<MODE, LATTICE>(p, s_dbits, zl, y, sg, s, inner, outer, st.active, true, lane);
         }
     } else {
@@ -437,7 +434,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_band(Params p) {
             st.begin(p, un.zl, un.y0, un.sg * p.segw - 1 + lane, lane);
             for (int y = un.y0; y < un.y1; ++y) {
                 uint32_t s, inner, outer;
-                st.step(y, s, inner, outer);
+                st.step(p, y, s, inner, outer);
                 flips += band_row<MODE, LATTICE>(p, s_dbits, un.zl, y, un.sg, s, inner, outer, st.active, own, lane);
             }
         }
@@ -558,19 +555,27 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     int stage = 0;
     uint32_t parity = 0;
     long long flips = 0;
-    Strip st;
-    int c0 = 0;
+    Strip st, nx;  // nx: the window of this warp's NEXT unit, requested while the last row of the current one is evaluated (a
+                   // window restart is nine loads, one L2 round trip; behind a unit of 4 rows that was 5 % of a thin slab's sweep)
+    int c0 = 0, nu = nunits, nzl = 0, nsg = 0, ny = 0, ny1 = 0;
     bool own = false;
     while (cu < nunits) {
         const int y = cy;
-        if (fresh) {  // new unit: (re)start the window
+        if (fresh) {  // first unit: start the window
             c0 = csg * p.segw - 1;
             own = czl >= p.own_lo && czl < p.own_hi;
             st.begin(p, czl, y, c0 + lane, lane);
             fresh = false;
         }
+        if (y + 1 >= cy1) {  // last row of the unit: lane 0 announced the next one when it issued this row
+            nu = myring[ctail & (UNIT_RING - 1)];
+            if (nu < nunits) {
+                decode(nu, nzl, nsg, ny, ny1);
+                nx.begin(p, nzl, ny, nsg * p.segw - 1 + lane, lane);
+            }
+        }
         uint32_t s, inner, outer;
-        st.step(y, s, inner, outer);
+        st.step(p, y, s, inner, outer);
         const long long widx = (long long)czl * p.plane_words + (long long)y * p.WP + c0 + lane;
         const long long ridx = ((long long)czl * p.Y + y) * p.nseg + csg;
         const uint8_t was = p.rowflag[ridx];
@@ -611,11 +616,12 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         const uint32_t f = band & (D ^ s);
         store_flips(p, widx, ridx, was, f, st.active, own, lane);
         if (own) flips += __popc(f);
-        if (++cy >= cy1) {  // next unit of this warp's sequence (lane 0 wrote it at least a row ago)
-            __syncwarp();
-            cu = myring[ctail++ & (UNIT_RING - 1)];
-            if (cu < nunits) decode(cu, czl, csg, cy, cy1);
-            fresh = true;
+        if (++cy >= cy1) {  // on to the next unit of this warp's sequence: its window is under way
+            ++ctail;
+            cu = nu; czl = nzl; csg = nsg; cy = ny; cy1 = ny1;
+            st = nx;
+            c0 = csg * p.segw - 1;
+            own = czl >= p.own_lo && czl < p.own_hi;
         }
     }
     flips = warp_sum(flips);
@@ -643,7 +649,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep_dense_ldg(Params p) {
         st.begin(p, un.zl, un.y0, c, lane);
         for (int y = un.y0; y < un.y1; ++y) {
             uint32_t s, inner, outer;
-            st.step(y, s, inner, outer);
+            st.step(p, y, s, inner, outer);
             const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
             const long long ridx = ((long long)un.zl * p.Y + y) * p.nseg + un.sg;
             const uint8_t was = p.rowflag[ridx];
@@ -1087,7 +1093,7 @@ __global__ void __launch_bounds__(BLOCK) k_init_bands(Params p) {
         st.begin(p, un.zl, un.y0, c, lane);
         for (int y = un.y0; y < un.y1; ++y) {
             uint32_t s, inner, outer;
-            st.step(y, s, inner, outer);
+            st.step(p, y, s, inner, outer);
             if (!st.active) continue;
             const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
             if (p.E) {
@@ -1414,7 +1420,7 @@ __global__ void __launch_bounds__(BLOCK) k_labels(Params p, uint8_t *__restrict_
         st.begin(p, un.zl, un.y0, c, lane);
         for (int y = un.y0; y < un.y1; ++y) {
             uint32_t s, inner, outer;
-            st.step(y, s, inner, outer);
+            st.step(p, y, s, inner, outer);
             const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
             const uint32_t e = (p.E && st.active) ? p.E[widx] : 0u;
             outer &= ~e;
@@ -1488,7 +1494,7 @@ __global__ void __launch_bounds__(BLOCK) k_mask_flips(Params p) {
         st.begin(p, un.zl, un.y0, c, lane);
         for (int y = un.y0; y < un.y1; ++y) {
             uint32_t s, inner, outer;
-            st.step(y, s, inner, outer);
+            st.step(p, y, s, inner, outer);
             const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
             const long long ridx = ((long long)un.zl * p.Y + y) * p.nseg + un.sg;
             if (p.E != nullptr && outer) outer &= ~p.E[widx];

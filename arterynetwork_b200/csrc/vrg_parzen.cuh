@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(BLOCK) k_cont_band(Params p, Cont q) {
         st.begin(p, un.zl, un.y0, c, lane);
         for (int y = un.y0; y < un.y1; ++y) {
             uint32_t s, inner, outer;
-            st.step(y, s, inner, outer);
+            st.step(p, y, s, inner, outer);
             const long long widx = (long long)un.zl * p.plane_words + (long long)y * p.WP + c;
             if (p.E != nullptr && outer) outer &= ~p.E[widx];  // outer is non-zero on active lanes only
             const uint32_t band = inner | outer;

@@ -416,7 +416,6 @@ __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail_pipe(Params p, P2P q, un
         return;
     }
     const bool go = s_ctl[1] != 0;  // the cap of VRG:101 is tested before the flips are applied
-    const unsigned long long seq = ((unsigned long long)s_ctl[3] << 32) | (unsigned long long)(sweep + 1);
     const int gw = blockIdx.x * TAIL_WARPS + warp, nw = G * TAIL_WARPS;
     const int *fl = front_list(p, sweep & 1);
     const int nfront = go ? fl[0] : 0;
@@ -548,7 +547,7 @@ __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail_pipe(Params p, P2P q, un
 
 // k_async_stats (second stream, one small block beside the running sweep): the statistics all-reduce of the update the tail
 // kernel just applied (slabs), then the exit tests of VRG:91-104,118 and the loop bookkeeping of VRG:113-117.
-constexpr int ASYNC_BLOCK = 256;
+constexpr int ASYNC_BLOCK = 128;  // small: these blocks have to find room on SMs the sweep's blocks occupy (registers!)
 __global__ void __launch_bounds__(ASYNC_BLOCK) k_async_stats(Params p, P2P q, long long *gstats, int p2p) {
     __shared__ int s_ok;
     if (p.ctrl[C_STATUS] != RUNNING || !p.ctrl[C_TAIL_APPLIED]) return;
