@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libvrg_b200.so")
-SOURCES = ["vrg_b200.cu", "vrg_phantom.cu", "vrg_edt.cu", "vrg_mask.cu"]
-DEPS = SOURCES + ["vrg_kernels.cuh", "vrg_p2p.cuh", "vrg_parzen.cuh", "vrg_scratch.cuh", os.path.join("..", "..", "include", "vrg_b200.h")]
+SOURCES = ["vrg_b200.cu", "vrg_phantom.cu", "vrg_edt.cu", "vrg_mask.cu", "vrg_strict.cu"]
+DEPS = SOURCES + ["vrg_kernels.cuh", "vrg_tail.cuh", "vrg_p2p.cuh", "vrg_parzen.cuh", "vrg_scratch.cuh", os.path.join("..", "..", "include", "vrg_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -37,7 +37,21 @@ class Result(ctypes.Structure):
                 ("q_add_to_inside", i64), ("q_remove_to_outside", i64), ("q_cancel_repromoted", i64), ("redone_sweeps", i64)]
 
 
+class StrictResult(ctypes.Structure):
+    _fields_ = [("iterations", i64), ("exit_reason", i64), ("n_in", i64), ("n_out", i64), ("n_excluded", i64),
+                ("n_levels", i64), ("kernel_launches", i64), ("skipped", i64), ("dropped", i64), ("rounds", i64)]
+
+
 _SIGS = {
+    "vrg_strict_create": [ctypes.c_int, vp, ctypes.c_double, i64, i64, ctypes.c_double, ctypes.POINTER(vp)],
+    "vrg_strict_destroy": [vp],
+    "vrg_strict_init": [vp, vp, vp],
+    "vrg_strict_step": [vp, ctypes.POINTER(StrictResult)],
+    "vrg_strict_run": [vp, ctypes.POINTER(StrictResult)],
+    "vrg_strict_download": [vp, vp, vp],
+    "vrg_strict_list": [vp, ctypes.c_int, vp, vp, vp, i64, ctypes.POINTER(i64)],
+    "vrg_strict_get_trace": [vp, vp, i64, ctypes.POINTER(i64)],
+    "vrg_strict_get_sums": [vp, vp, vp],
     "vrg_create": [ctypes.POINTER(Config), ctypes.POINTER(vp)],
     "vrg_destroy": [vp],
     "vrg_set_stream": [vp, vp],

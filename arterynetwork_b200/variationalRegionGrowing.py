@@ -15,6 +15,10 @@ Module switches (the reference has none; defaults reproduce it):
               move over NVLink peer memory) -- the call itself does not change.
 ``INTENSITY`` how the sweep reads intensities (``index`` | ``f64_band`` | ``f64_dense``).
 ``MAX_SECONDS`` the reference's 120 s wall-clock exit (VRG:97); ``None`` disables it.
+``LIST_ORDER`` ``False`` = the order-free result (below); ``True`` = the strict engine (``csrc/vrg_strict.cu``): the
+              reference WITH the effects of its list processing order -- flipped points walked in ``allBnd`` order,
+              stale band labels kept in ``valueMap``, drifting running Parzen sums, ``segmented`` rows in the
+              reference's own order (VRG:156-259).  One GPU, level-table data, fresh maps (labels 0 / 3 / 4).
 
 Differences from the reference, all deliberate (DESIGN.md "Boundary"):
 
@@ -57,6 +61,7 @@ DEVICES = None  # None: DEVICE only; "all" or a list of CUDA ordinals: z-slabs o
 INTENSITY = "index"  # how the sweep reads intensities: f64_dense | f64_band | index | continuous
 CONTINUOUS_MAX_VOXELS = 1 << 24  # fall back to the brute-force Parzen mode (continuous data) up to this volume size
 HOST_THREADS = 8  # host-side conversions (label dtype, int64 segmentedMap) run in z-chunks on this many threads
+LIST_ORDER = False  # True: bug-compatible list-order semantics, see the module docstring
 LAST_RUN = {}  # result of the most recent call: iterations, exit_reason, n_in, ..., q_* order-dependence counters
 
 _EXIT_SUFFIX = {nat.EXIT_CONVERGED: "", nat.EXIT_MAX_TIME: " (Max time reached)",
@@ -193,6 +198,41 @@ def _warn_order_dependence(res):
                       VRGOrderDependenceWarning, stacklevel=3)
 
 
+def _finish_lines(res, segmented, data3):
+    nz = sum(_pool_map(lambda zz: int(np.count_nonzero(data3[zz[0]:zz[1]])), _chunks(data3.shape[0], HOST_THREADS)))
+    if res["exit_reason"] == nat.EXIT_MAX_ITER:  # VRG:118-120
+        print('Segmented points are: \n', segmented)
+        print('Max iteration reached! Finished at iteration {}'.format(res["iterations"]))
+    else:  # VRG:94-104
+        print('Finished at iteration {}{}'.format(res["iterations"], _EXIT_SUFFIX[res["exit_reason"]]))
+    print('Total segmented voxels: ' + '{}/{}'.format(segmented.shape[0], nz))
+
+
+def _list_order_run(dataArray, valueMap, H, maxSegmentSize):
+    """``LIST_ORDER = True``: the strict engine.  The list order is the raster order of the USER's axes, so an F-ordered
+    volume is copied to C order instead of being transposed."""
+    global LAST_RUN
+    from .strict import StrictEngine
+    if dataArray.ndim > 3 or dataArray.ndim == 0:
+        raise NotImplementedError("variationalRegionGrowing: 1-D to 3-D volumes only, got ndim=%d" % dataArray.ndim)
+    shape3 = (1,) * (3 - dataArray.ndim) + dataArray.shape
+    data3 = np.ascontiguousarray(dataArray, dtype=np.float64).reshape(shape3)
+    vm8 = _labels_u8(np.ascontiguousarray(valueMap).reshape(shape3))
+    if not np.isin(vm8, (0, 3, 4)).all():
+        raise ValueError("variationalRegionGrowing (LIST_ORDER): the initial valueMap may only hold the labels 0, 3 and 4")
+    with StrictEngine(shape3, H=H, max_segment_size=maxSegmentSize, iter_max=ITER_MAX, device=DEVICE,
+                      max_seconds=MAX_SECONDS or 0.0) as eng:
+        eng.init(data3, vm8)
+        res = eng.run()
+        labels = eng.value_map()
+        segmented = eng.segmented()[:, 3 - dataArray.ndim:]
+    LAST_RUN = dict(res)
+    valueMap[...] = labels.reshape(dataArray.shape)
+    segmentedMap = (labels <= 1).astype(np.int64).reshape(dataArray.shape)
+    _finish_lines(res, segmented, data3)
+    return segmented, segmentedMap, valueMap
+
+
 def variationalRegionGrowing(dataArray, valueMap, H=2.25, maxSegmentSize=5000):
     """B200 implementation of VRG:10-121.  See the module docstring for the contract."""
     global LAST_RUN
@@ -201,6 +241,8 @@ def variationalRegionGrowing(dataArray, valueMap, H=2.25, maxSegmentSize=5000):
         raise TypeError("valueMap must be an ndarray (it is updated in place, as in the reference)")
     if dataArray.shape != valueMap.shape:
         raise ValueError("dataArray and valueMap must have the same shape")
+    if LIST_ORDER:
+        return _list_order_run(dataArray, valueMap, H, maxSegmentSize)
     data3, transposed = _as_zyx(dataArray)
     vm_view = valueMap.T if transposed else valueMap
     vm3 = vm_view.reshape(data3.shape)
@@ -240,14 +282,7 @@ def variationalRegionGrowing(dataArray, valueMap, H=2.25, maxSegmentSize=5000):
     else:
         segmentedMap[...] = seg3.reshape(vm_view.shape).T
         segmented = np.argwhere(segmentedMap == 1)  # C order of the user's axes
-    nz = sum(_pool_map(lambda zz: int(np.count_nonzero(data3[zz[0]:zz[1]])), _chunks(data3.shape[0], HOST_THREADS)))
-    total = '{}/{}'.format(segmented.shape[0], nz)
-    if res["exit_reason"] == nat.EXIT_MAX_ITER:  # VRG:118-120
-        print('Segmented points are: \n', segmented)
-        print('Max iteration reached! Finished at iteration {}'.format(res["iterations"]))
-    else:  # VRG:94-104
-        print('Finished at iteration {}{}'.format(res["iterations"], _EXIT_SUFFIX[res["exit_reason"]]))
-    print('Total segmented voxels: ' + total)
+    _finish_lines(res, segmented, data3)
     _warn_order_dependence(res)
     return segmented, segmentedMap, valueMap
 

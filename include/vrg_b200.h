@@ -206,6 +206,41 @@ int vrg_get_table_levels(vrg_handle *h, double *levels_out, int64_t cap); /* the
 /* continuous mode: flat voxel index (own planes) and the normalised sums of the last decision at every band voxel */
 int vrg_get_band_sums(vrg_handle *h, int64_t *vox_out, double *pin_out, double *pout_out, int64_t cap, int64_t *n);
 
+/* ---- strict (list-order) mode, SURVEY.md section 8(f) N4 -------------------------------------------------------
+ * The entry points above return the ORDER-FREE result: identical to the reference wherever the reference's own result
+ * does not depend on the order of its band lists (vrg_result.q_* say when a run left that domain).  This second engine
+ * reproduces the reference WITH its list order (Code/variationalRegionGrowing.py:156-259): flipped points processed in
+ * allBnd order against the labels at their turn (VRG:163,169,198), band labels set without a look at the neighbours
+ * (VRG:174,202), Parzen corrections selected by the labels after the call (VRG:232-233) and the drifting running sums
+ * innerProb / outerProb that follow (VRG:236-247).  Outputs are the reference's: the valueMap with its stale band labels
+ * and `segmented` in the reference's row order.  Single GPU, whole volume (< 2^31 voxels), <= VRG_MAX_LEVELS distinct
+ * intensities, initial labels 0 / 3 / 4.  See arterynetwork_b200/csrc/vrg_strict.cu for how the list walk is parallel. */
+typedef struct vrg_strict vrg_strict;
+typedef struct {
+    int64_t iterations;  /* the number the reference prints, VRG:94 */
+    int64_t exit_reason; /* vrg_exit */
+    int64_t n_in, n_out, n_excluded, n_levels;
+    int64_t kernel_launches;
+    int64_t skipped;     /* listed flips that were in neither band any more at their turn (VRG:169,198 both false) */
+    int64_t dropped;     /* flipped voxels whose label after the call was not 1 or 2: left out of the corrections (Q3) */
+    int64_t rounds;      /* wavefront rounds so far (the longest chains of order dependences, summed over iterations) */
+} vrg_strict_result;
+int vrg_strict_create(int device, const int64_t *shape /* Z, Y, X */, double H, int64_t iter_max, int64_t max_segment_size,
+                      double max_seconds, vrg_strict **out);
+int vrg_strict_destroy(vrg_strict *h);
+/* dataArray + valueMap (host, whole volume) and the init branch of update(), VRG:40-50,129-155 */
+int vrg_strict_init(vrg_strict *h, const double *data_host, const uint8_t *value_map_host);
+int vrg_strict_step(vrg_strict *h, vrg_strict_result *res); /* one pass of the while loop, VRG:58-117 */
+int vrg_strict_run(vrg_strict *h, vrg_strict_result *res);  /* to one of the exits */
+/* the reference's valueMap as it stands (stale band labels included) and segmentedMap (0/1); either may be NULL */
+int vrg_strict_download(vrg_strict *h, uint8_t *value_map_out, uint8_t *seg_map_out);
+/* which = 0: the band in allBnd order (VRG:48,111) with innerProb/innerSize, outerProb/outerSize of every band voxel
+ * (VRG:79-82; sums may be NULL); which = 1: the segmented voxels in the reference's row order (VRG:126,172,200).
+ * vox_out: flat C-order voxel indices; cap in entries; *n = how many there are (VRG_ERR_ARG when cap is too small). */
+int vrg_strict_list(vrg_strict *h, int which, int64_t *vox_out, double *pin_out, double *pout_out, int64_t cap, int64_t *n);
+int vrg_strict_get_trace(vrg_strict *h, int64_t *rows_out, int64_t cap_rows, int64_t *n_rows); /* (n_flips,n_in,n_out) */
+int vrg_strict_get_sums(vrg_strict *h, double *pin_out, double *pout_out); /* innerProb, outerProb, whole volume, unnormalised */
+
 /* synthetic phantom generated on the device (bench configs that exceed host RAM) */
 int vrg_phantom_device(int device, const int64_t *shape, int64_t z0, int64_t nz, const int64_t *segments,
                        int64_t n_segments, const int64_t *roots, int64_t n_roots, int64_t seed, int64_t quantum,
