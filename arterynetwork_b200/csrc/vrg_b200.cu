@@ -64,6 +64,7 @@ struct vrg_handle {
     bool have_data = false, have_levels = false, inited = false, separate_gstats = false;
     int64_t launches = 0;
     int grid = 148 * 8;
+    bool no_wide = false;  // A/B switch VRG_NO_WIDE: rows of 31 / 32 words stay two 16-word segments in the dense sweep
     bool dense_attr_set = false, force_ldg = false, hist_attr_set = false, attached = false;
     const uint8_t *vm_base = nullptr;  // valueMap as indexed by local plane (own buffer or attached)
     // optional per-kernel timing (CUDA events on the launch stream), see vrg_profile
@@ -115,9 +116,14 @@ static const int HASH_CAP = 1 << 18;
         else KERNEL<MODE_F64_BAND, false><<<GRID, BLK, SMEM, h->stream>>>(__VA_ARGS__);                   \
     } while (0)
 
-static size_t dense_smem_bytes(const Params &p) {
+static size_t dense_smem_bytes(const Params &p, bool wide = false) {
     return (size_t)((p.LW * 4 + 127) & ~127) + ((DENSE_WARPS * (DENSE_STAGES * 8 + UNIT_RING * 4) + 127) & ~127) +
-           (size_t)DENSE_WARPS * DENSE_STAGES * STAGE_BYTES;
+           (size_t)DENSE_WARPS * DENSE_STAGES * (wide ? WIDE_STAGE_BYTES : STAGE_BYTES);
+}
+// rows of 31 / 32 words (two 16-word segments): one warp per whole row in the dense sweep, if its 8 KB stages fit
+static bool dense_wide(const vrg_handle *h) {
+    const Params &p = h->p;
+    return p.nseg == 2 && p.segw == 16 && dense_smem_bytes(p, true) <= 227 * 1024 && !h->no_wide;
 }
 
 static cudaEvent_t prof_event(vrg_handle *h) {
@@ -173,6 +179,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     h->sms = prop.multiProcessorCount;
     h->grid = h->sms * 8;
     h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;  // A/B switch: plain loads instead of the TMA rings (sweep, init histogram)
+    h->no_wide = getenv("VRG_NO_WIDE") != nullptr;
     h->graph_ok = getenv("VRG_NO_GRAPH") == nullptr;    // A/B switch: vrg_run stays on plain stream launches
     h->tail_ok = getenv("VRG_NO_FUSED_TAIL") == nullptr;  // A/B switch: the separate kernels behind the sweep
     if (const char *e = getenv("VRG_PIPELINE")) h->pipe_mode = atoi(e) != 0;  // A/B switch (default: pipelined on slabs only)
@@ -198,7 +205,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     p.mhH = -0.5 * cfg->H;
     p.dirty_lists = cfg->intensity_mode == VRG_INTENSITY_F64_BAND || cfg->intensity_mode == VRG_INTENSITY_INDEX;
     {   // rows per work unit of the dense sweep: long units on large volumes (fewer window restarts), short ones on thin slabs
-        const long long rows_per_warp = (long long)(h->nz_own + 2) * Y * p.nseg / ((long long)h->sms * DENSE_WARPS);
+        const long long rows_per_warp = (long long)(h->nz_own + 2) * Y * (p.nseg == 2 && p.segw == 16 ? 1 : p.nseg) / ((long long)h->sms * DENSE_WARPS);
         p.dense_rows = rows_per_warp >= 96 ? 8 : 4;  // measured: profiles/README.md (r2b, r2c)
         if (const char *e = getenv("VRG_DENSE_ROWS")) p.dense_rows = std::max(1, atoi(e));  // A/B switch
     }
@@ -707,14 +714,19 @@ static int enqueue_sweep(vrg_handle *h) {
     const size_t smem = (size_t)p.LW * sizeof(uint32_t);
     if (h->prof) cudaEventRecord(prof_event(h), h->stream);
     if (h->cfg.intensity_mode == VRG_INTENSITY_F64_DENSE) {
-        const size_t dsm = dense_smem_bytes(p);
+        const bool wide = dense_wide(h);
+        const size_t dsm = dense_smem_bytes(p, wide);
         if ((p.X & 1) == 0 && (((uintptr_t)p.data) & 15) == 0 && dsm <= 227 * 1024 && !h->force_ldg) {  // TMA ring: 16-byte aligned row segments
             if (!h->dense_attr_set) {
                 CK(cudaFuncSetAttribute(k_sweep_dense<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 CK(cudaFuncSetAttribute(k_sweep_dense<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                CK(cudaFuncSetAttribute(k_sweep_dense<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                CK(cudaFuncSetAttribute(k_sweep_dense<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 h->dense_attr_set = true;
             }
-            if (p.lattice) k_sweep_dense<true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+            if (wide && p.lattice) k_sweep_dense<true, true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+            else if (wide) k_sweep_dense<false, true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+            else if (p.lattice) k_sweep_dense<true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
             else k_sweep_dense<false><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
         } else if (p.lattice) k_sweep_dense_ldg<true><<<h->grid, BLOCK, smem, h->stream>>>(p);
         else k_sweep_dense_ldg<false><<<h->grid, BLOCK, smem, h->stream>>>(p);

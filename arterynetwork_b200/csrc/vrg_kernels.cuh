@@ -108,6 +108,13 @@ __device__ __forceinline__ uint32_t dilate_x1(uint32_t v) {
     const uint32_t l = __shfl_up_sync(FULL, v, 1), r = __shfl_down_sync(FULL, v, 1);
     return v | __funnelshift_l(l, v, 1) | __funnelshift_r(v, r, 1);
 }
+// same for a warp whose 32 lanes ARE the row (no halo lanes): nothing lies beyond lane 0 and lane 31
+__device__ __forceinline__ uint32_t dilate_x1_row(uint32_t v, int lane) {
+    uint32_t l = __shfl_up_sync(FULL, v, 1), r = __shfl_down_sync(FULL, v, 1);
+    if (lane == 0) l = 0u;
+    if (lane == 31) r = 0u;
+    return v | __funnelshift_l(l, v, 1) | __funnelshift_r(v, r, 1);
+}
 __device__ __forceinline__ uint32_t dilate_x2(uint32_t v) {
     const uint32_t l = __shfl_up_sync(FULL, v, 1), r = __shfl_down_sync(FULL, v, 1);
     return v | __funnelshift_l(l, v, 1) | __funnelshift_r(v, r, 1) | __funnelshift_l(l, v, 2) | __funnelshift_r(v, r, 2);
@@ -293,9 +300,11 @@ struct Strip {
             a = ((flags & 2) ? w0 : 0xFFFFFFFFu) & s & ((flags & 4) ? w2 : 0xFFFFFFFFu);
         }
     }
+    // WIDE: the warp's 32 lanes are the whole row (lane = word column, no halo lanes); dense sweep on rows of 31 / 32 words
+    template <bool WIDE = false>
     __device__ __forceinline__ void begin(const Params &p, int zl, int y0, int c, int lane) {
         const bool inr = c >= 0 && c < p.XW;
-        active = inr && lane >= 1 && lane <= p.segw;
+        active = WIDE ? inr : (inr && lane >= 1 && lane <= p.segw);
         vm = inr ? valid_mask(p, c) : 0u;
         base = (long long)zl * p.plane_words + c;
         flags = (inr ? 1 : 0) | ((inr && zl - 1 >= p.valid_lo) ? 2 : 0) | ((inr && zl + 1 < p.valid_hi) ? 4 : 0);
@@ -305,10 +314,11 @@ struct Strip {
         row(p, y0 + 1, on, an, sn);
     }
     // bands of row y (s = segmented word, returns inner | outer-without-E); then slides one row down
-    __device__ __forceinline__ void step(const Params &p, int y, uint32_t &s, uint32_t &inner, uint32_t &outer) {
+    template <bool WIDE = false>
+    __device__ __forceinline__ void step(const Params &p, int y, uint32_t &s, uint32_t &inner, uint32_t &outer, int lane = 0) {
         row(p, y + 2, o2, a2, s2);
-        const uint32_t dil_s = dilate_x1(op | oc | on);
-        const uint32_t dil_n = dilate_x1(~(ap & ac & an) & vm);
+        const uint32_t dil_s = WIDE ? dilate_x1_row(op | oc | on, lane) : dilate_x1(op | oc | on);
+        const uint32_t dil_n = WIDE ? dilate_x1_row(~(ap & ac & an) & vm, lane) : dilate_x1(~(ap & ac & an) & vm);
         s = sc;
         inner = active ? (s & dil_n) : 0u;
         outer = active ? (~s & vm & dil_s) : 0u;
@@ -342,6 +352,27 @@ __device__ __forceinline__ void store_flips(const Params &p, long long widx, lon
             if (p.C != nullptr) p.C[widx] = 0u;  // k_cancel refills it for rows that still flip
         }
         if (lane == 0) {
+            if (any != (was != 0)) p.rowflag[ridx] = any ? 1 : 0;
+            if (any && own) {
+                int *fl = front_list(p, (int)(p.ctrl[C_SWEEPS] & 1));
+                fl[1 + atomicAdd(&fl[0], 1)] = (int)ridx;
+            }
+        }
+    }
+}
+
+// the same for a warp that holds a whole row of two 16-word segments (lanes 0..15 and 16..31): flags, stores and front rows
+// stay per segment, as every other kernel expects them; `was` = the flag of the lane's own segment
+__device__ __forceinline__ void store_flips_wide(const Params &p, long long widx, long long ridx, uint8_t was, uint32_t f, bool active,
+                                                 bool own, int lane) {
+    const unsigned hit = __ballot_sync(FULL, f != 0u);
+    const bool any = ((lane < 16 ? hit : hit >> 16) & 0xFFFFu) != 0u;
+    if (any || was) {
+        if (active) {
+            p.F[widx] = f;
+            if (p.C != nullptr) p.C[widx] = 0u;
+        }
+        if ((lane & 15) == 0) {
             if (any != (was != 0)) p.rowflag[ridx] = any ? 1 : 0;
             if (any && own) {
                 int *fl = front_list(p, (int)(p.ctrl[C_SWEEPS] & 1));
@@ -480,8 +511,13 @@ constexpr int UNIT_RING = 8;  // the prefetcher is at most DENSE_STAGES + 1 rows
 // every iteration: the volume is streamed at 8 B/voxel by 1-D TMA bulk copies, one row segment (<= 7680 B) per stage,
 // into a per-warp ring in shared memory; the warp that consumed a stage re-arms it, so no cross-warp sync exists.
 // Needs X even (16-byte alignment of every row segment); otherwise the host launches k_sweep_dense_ldg.
-template <bool LATTICE>
+// WIDE (rows of 31 or 32 words, e.g. X = 1024): such a row is two 16-word segments for every other kernel, which left half
+// of this kernel's lanes idle; here one warp takes the whole row -- lane = word column, no halo lanes (nothing lies beyond
+// the row ends), one 8 KB stage per row, flags and front rows still per segment.
+constexpr int WIDE_STAGE_BYTES = 32 * 32 * 8;
+template <bool LATTICE, bool WIDE = false>
 __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
+    constexpr int SB = WIDE ? WIDE_STAGE_BYTES : STAGE_BYTES;
     if (p.ctrl[C_STATUS] != RUNNING) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *s_dbits = (uint32_t *)smem_raw;
@@ -493,14 +529,14 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     for (int i = threadIdx.x; i < p.LW; i += DENSE_WARPS * 32) s_dbits[i] = table_bits(p)[i];
     uint64_t *mybar = bars + warp * DENSE_STAGES;
     int *myring = rings + warp * UNIT_RING;
-    double *mystage = stages + (size_t)warp * DENSE_STAGES * (STAGE_BYTES / 8);
+    double *mystage = stages + (size_t)warp * DENSE_STAGES * (SB / 8);
     // the part of a stage that no row segment ever overwrites (beyond the shortest segment: the row's tail, and the
     // words up to the batch width) must hold a valid intensity, since the evaluation below is branch-free
     {
-        const int shortest = min(p.segw * 32, p.X - (p.nseg - 1) * p.segw * 32);
+        const int shortest = WIDE ? p.X : min(p.segw * 32, p.X - (p.nseg - 1) * p.segw * 32);
 #pragma unroll
         for (int s = 0; s < DENSE_STAGES; ++s)
-            for (int i = shortest + lane; i < STAGE_BYTES / 8; i += 32) mystage[s * (STAGE_BYTES / 8) + i] = p.lev0;
+            for (int i = shortest + lane; i < SB / 8; i += 32) mystage[s * (SB / 8) + i] = p.lev0;
     }
     if (lane == 0) {
 #pragma unroll
@@ -514,11 +550,11 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     const int nyb = (p.Y + R - 1) / R;
     const int nwarps = gridDim.x * DENSE_WARPS;
     const int w = blockIdx.x * DENSE_WARPS + warp;
-    const int nunits = (zhi - zlo) * nyb * p.nseg;
+    const int nunits = (zhi - zlo) * nyb * (WIDE ? 1 : p.nseg);
     unsigned long long *next_unit = (unsigned long long *)&p.ctrl[C_NEXT_UNIT];
     auto decode = [&](int u, int &zl, int &sg, int &y, int &y1) {
-        sg = u % p.nseg;
-        const int t = u / p.nseg;
+        sg = WIDE ? 0 : u % p.nseg;
+        const int t = WIDE ? u : u / p.nseg;
         y = (t % nyb) * R;
         zl = zlo + t / nyb;
         y1 = min(p.Y, y + R);
@@ -530,11 +566,11 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         if (pu < nunits) decode(pu, pzl, psg, py, py1);
     };
     auto pre_issue = [&](int s) {  // one row segment into stage s, then step to the next row
-        const int x0 = psg * p.segw * 32;
-        const uint32_t bytes = (uint32_t)min(p.segw * 32, p.X - x0) * 8u;
+        const int x0 = WIDE ? 0 : psg * p.segw * 32;
+        const uint32_t bytes = (uint32_t)(WIDE ? p.X : min(p.segw * 32, p.X - x0)) * 8u;
         const double *src = p.data + (long long)pzl * p.plane_vox + (long long)py * p.X + x0;
         mbar_expect_tx(mybar + s, bytes);
-        tma_bulk_load(mystage + (size_t)s * (STAGE_BYTES / 8), src, bytes, mybar + s);
+        tma_bulk_load(mystage + (size_t)s * (SB / 8), src, bytes, mybar + s);
         if (++py >= py1) {
             pu = pu_next;
             pu_next = pu_next < nunits ? 2 * nwarps + (int)atomicAdd(next_unit, 1ull) : pu_next;  // used a whole unit later
@@ -562,29 +598,29 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
     while (cu < nunits) {
         const int y = cy;
         if (fresh) {  // first unit: start the window
-            c0 = csg * p.segw - 1;
+            c0 = WIDE ? 0 : csg * p.segw - 1;
             own = czl >= p.own_lo && czl < p.own_hi;
-            st.begin(p, czl, y, c0 + lane, lane);
+            st.template begin<WIDE>(p, czl, y, c0 + lane, lane);
             fresh = false;
         }
         if (y + 1 >= cy1) {  // last row of the unit: lane 0 announced the next one when it issued this row
             nu = myring[ctail & (UNIT_RING - 1)];
             if (nu < nunits) {
                 decode(nu, nzl, nsg, ny, ny1);
-                nx.begin(p, nzl, ny, nsg * p.segw - 1 + lane, lane);
+                nx.template begin<WIDE>(p, nzl, ny, (WIDE ? 0 : nsg * p.segw - 1) + lane, lane);
             }
         }
         uint32_t s, inner, outer;
-        st.step(p, y, s, inner, outer);
+        st.template step<WIDE>(p, y, s, inner, outer, lane);
         const long long widx = (long long)czl * p.plane_words + (long long)y * p.WP + c0 + lane;
-        const long long ridx = ((long long)czl * p.Y + y) * p.nseg + csg;
+        const long long ridx = ((long long)czl * p.Y + y) * p.nseg + (WIDE ? (lane >> 4) : csg);
         const uint8_t was = p.rowflag[ridx];
         if (p.E != nullptr && outer) outer &= ~p.E[widx];
         const uint32_t band = inner | outer;
         // decision bit of every voxel of the row segment: word j of the segment ends up in lane j + 1.
         // Branch-free over all 30 words (the stage beyond the row end holds valid intensities, see the fill above;
         // their bits are masked by the band), so the compiler interleaves the words' dependency chains.
-        const double *sv = mystage + (size_t)stage * (STAGE_BYTES / 8) + lane;
+        const double *sv = mystage + (size_t)stage * (SB / 8) + lane;
         mbar_wait(mybar + stage, parity);
         // phase 1 (no convergence points, so the 30 dependency chains overlap): bit j+1 of `mine` = decision of this
         // lane's voxel in word j;  phase 2: 32x32 bit transpose across the warp, lane j+1 ends up with word j.
@@ -592,10 +628,10 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         // batches of 10 words: loads first, then the level arithmetic, then the table look-ups, so that ten
         // dependency chains are in flight at once whatever the register allocator would prefer.  (Narrower batches
         // that overshoot segw less -- 4 x 7 for 28 words, 3 x 8 for 22 -- measured the same or slower: profiles/README.md.)
-        constexpr int BW = 10;
-        const int nbatch = (p.segw + BW - 1) / BW;
+        constexpr int BW = WIDE ? 8 : 10;
+        const int nbatch = ((WIDE ? p.XW : p.segw) + BW - 1) / BW;
 #pragma unroll
-        for (int jb = 0; jb < WORDS_PER_WARP; jb += BW) {
+        for (int jb = 0; jb < (WIDE ? 32 : WORDS_PER_WARP); jb += BW) {
             if (jb / BW >= nbatch) break;  // warp-uniform (words past segw hold valid stale data, masked by the band)
             double v[BW];
             int l[BW];
@@ -607,20 +643,21 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
 #pragma unroll
             for (int k = 0; k < BW; ++k) wd[k] = s_dbits[l[k] >> 5];
 #pragma unroll
-            for (int k = 0; k < BW; ++k) mine |= ((wd[k] >> (l[k] & 31)) & 1u) << (jb + k + 1);
+            for (int k = 0; k < BW; ++k) mine |= ((wd[k] >> (l[k] & 31)) & 1u) << (jb + k + (WIDE ? 0 : 1));
         }
         const uint32_t D = transpose32(mine, lane);
         __syncwarp();
         if (lane == 0 && pu < nunits) pre_issue(stage);  // the stage is drained (values are in registers): re-arm it for a later row
         if (++stage == DENSE_STAGES) { stage = 0; parity ^= 1u; }
         const uint32_t f = band & (D ^ s);
-        store_flips(p, widx, ridx, was, f, st.active, own, lane);
+        if (WIDE) store_flips_wide(p, widx, ridx, was, f, st.active, own, lane);
+        else store_flips(p, widx, ridx, was, f, st.active, own, lane);
         if (own) flips += __popc(f);
         if (++cy >= cy1) {  // on to the next unit of this warp's sequence: its window is under way
             ++ctail;
             cu = nu; czl = nzl; csg = nsg; cy = ny; cy1 = ny1;
             st = nx;
-            c0 = csg * p.segw - 1;
+            c0 = WIDE ? 0 : csg * p.segw - 1;
             own = czl >= p.own_lo && czl < p.own_hi;
         }
     }

@@ -191,9 +191,12 @@ def test_dropin_falls_back_to_continuous_mode():
     ((70, 83, 131), dict(cell=(70, 83, 131), margin=5, depth=4, root_r2=9, min_len=10, max_len=24)),
     ((33, 40, 1000), dict(cell=(33, 40, 250), margin=4, depth=3, root_r2=9, min_len=10, max_len=30)),
     ((24, 24, 32), dict(cell=(24, 24, 32), margin=3, depth=2, root_r2=4, min_len=5, max_len=9)),
+    ((20, 24, 1024), dict(cell=(20, 24, 128), margin=3, depth=2, root_r2=4, min_len=8, max_len=40)),
+    ((18, 22, 990), dict(cell=(18, 22, 110), margin=3, depth=2, root_r2=4, min_len=8, max_len=36)),
 ])
 def test_ragged_shapes_match_c_oracle(shape, kw, mode):
-    """X not a multiple of 32, rows longer than one warp segment (XW > 30), several trees."""
+    """X not a multiple of 32, rows longer than one warp segment (XW > 30), several trees; rows of exactly 31 / 32 words (the
+    dense sweep then takes a whole row per warp, without halo lanes)."""
     from arterynetwork_b200.phantom import make_phantom
     from oracle.c_oracle import vrg_oracle_c
     data, vm, _ = make_phantom(shape, seed=5, **kw)
