@@ -28,105 +28,187 @@ using vrg_scratch::Buf;
 constexpr int EDT_INF = 1 << 30;  // "no zero voxel seen yet"; sums with k^2 are formed in 64 bits
 constexpr unsigned FULLMASK = 0xFFFFFFFFu;
 
-// pass x: one warp per row, 32 voxels per step; the nearest zero to the left is a running maximum of positions,
-// the nearest to the right a running minimum, each a 5-step warp scan plus a carry
-__global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ mask, int *__restrict__ out, long long nrows, int X) {
-    const int lane = threadIdx.x & 31;
+// pass x: one warp per row.  The row's foreground bits go to shared memory (and to the packed bit volume the other passes
+// read); the nearest zero to the left / right of a voxel is then bit arithmetic inside its own 32-voxel word, or the running
+// "last zero seen" of the words before it / the per-word "next zero" table of the words behind it.  Only FOREGROUND voxels
+// get their x-distance stored (uint16; 0xFFFF = no zero in this row): the background's distance is 0 and is implied by its
+// bit, so a thin mask costs the pass one byte read per voxel and next to nothing else.
+__global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ mask, uint16_t *__restrict__ d1, uint32_t *__restrict__ bits,
+                                                  long long nrows, int X, int XW) {
+    extern __shared__ uint32_t sm_rows[];  // per warp: XW words of bits, XW ints "nearest zero in a later word"
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *rb = sm_rows + (size_t)warp * 2 * XW;
+    int *rf = (int *)(rb + XW);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const int NONE_L = -(1 << 20), NONE_R = 1 << 20;  // farther than any axis: the squared distance saturates to EDT_INF
-    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+    const int NONE_L = -(1 << 20), NONE_R = 1 << 20;
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp; r < nrows; r += nwarps) {
         const uint8_t *row = mask + r * X;
-        int *orow = out + r * X;
-        int carry = NONE_L;
-        for (int x0 = 0; x0 < X; x0 += 32) {  // left to right: store the distance to the left zero
-            const int x = x0 + lane;
-            int v = (x < X && row[x] == 0) ? x : NONE_L;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULLMASK, v, o);
-                if (lane >= o) v = max(v, t);
+        if ((X & 3) == 0 && (((uintptr_t)row) & 3) == 0) {
+            // 128 voxels per step: a 4-byte load per lane, its four "non-zero" bits, then the eight lanes of each 32-voxel word
+            // OR their nibbles together (three shuffles)
+            for (int w0 = 0; w0 < XW; w0 += 4) {
+                const int x = 32 * w0 + 4 * lane;
+                uint32_t nib = 0xFu;  // beyond the row end there is no voxel, hence no zero
+                if (x < X) {
+                    const uint32_t v = *(const uint32_t *)(row + x);
+                    const uint32_t nz = (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+                    nib = ((nz >> 7) & 1u) | ((nz >> 14) & 2u) | ((nz >> 21) & 4u) | ((nz >> 28) & 8u);
+                }
+                uint32_t word = nib << (4 * (lane & 7));
+                word |= __shfl_xor_sync(FULLMASK, word, 1);
+                word |= __shfl_xor_sync(FULLMASK, word, 2);
+                word |= __shfl_xor_sync(FULLMASK, word, 4);
+                const int w = w0 + (lane >> 3);
+                if ((lane & 7) == 0 && w < XW) {
+                    rb[w] = word;
+                    bits[r * XW + w] = (w == XW - 1 && (X & 31)) ? (word & ((1u << (X & 31)) - 1u)) : word;
+                }
             }
-            v = max(v, carry);
-            carry = __shfl_sync(FULLMASK, v, 31);
-            if (x < X) orow[x] = x - v;  // >= 2^20 - X when there is no zero to the left
+        } else {
+            for (int w = 0; w < XW; ++w) {
+                const int x = 32 * w + lane;
+                const bool fg = x < X ? row[x] != 0 : true;
+                const uint32_t word = __ballot_sync(FULLMASK, fg);
+                if (lane == 0) {
+                    rb[w] = word;
+                    bits[r * XW + w] = (w == XW - 1 && (X & 31)) ? (word & ((1u << (X & 31)) - 1u)) : word;
+                }
+            }
         }
-        carry = NONE_R;
-        for (int x0 = ((X - 1) / 32) * 32; x0 >= 0; x0 -= 32) {  // right to left
-            const int x = x0 + lane;
-            int v = (x < X && row[x] == 0) ? x : NONE_R;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_down_sync(FULLMASK, v, o);
-                if (lane + o < 32) v = min(v, t);
-            }
-            v = min(v, carry);
-            carry = __shfl_sync(FULLMASK, v, 0);
-            if (x < X) {
-                const int d = min(orow[x], v - x);
-                orow[x] = d >= 32768 ? EDT_INF : d * d;
+        __syncwarp();
+        if (lane == 0) {  // next zero behind every word (a few hundred trivial steps per row)
+            int nz = NONE_R;
+            for (int w = XW - 1; w >= 0; --w) {
+                rf[w] = nz;
+                const uint32_t zw = ~rb[w];
+                if (zw) nz = 32 * w + __ffs(zw) - 1;
             }
         }
+        __syncwarp();
+        int left = NONE_L;  // last zero in the words before this one
+        for (int w = 0; w < XW; ++w) {
+            const uint32_t word = rb[w], zw = ~word;
+            if (word == 0u) { left = 32 * w + 31; continue; }  // a word of background: nothing to store (warp-uniform)
+            const int x = 32 * w + lane;
+            if (x < X && ((word >> lane) & 1u)) {
+                const uint32_t below = zw & ((2u << lane) - 1u), above = zw & ~((1u << lane) - 1u);
+                const int xl = below ? 32 * w + 31 - __clz(below) : left;
+                const int xr = above ? 32 * w + __ffs(above) - 1 : rf[w];
+                const int d = min(x - xl, xr - x);
+                d1[r * X + x] = d >= 32768 ? (uint16_t)0xFFFF : (uint16_t)d;
+            }
+            if (zw) left = 32 * w + 31 - __clz(zw);
+        }
+        __syncwarp();
     }
 }
 
-// pass y / z: out(u) = min_i (u - i)^2 + f(i) along one axis: lower envelope of parabolas (Meijster).  Thread = one
-// line; `line` enumerates (outer, x) so that threads of a warp sit on neighbouring x, walk u in lockstep, and every
-// access is a coalesced row of the volume.
-// Where f(u) = 0 the answer is 0, and a zero shields everything behind it ((u - i)^2 + f(i) > (u - z)^2 for i beyond a
-// zero at z): only the zeros next to a positive voxel can matter to the envelope, so the zeros inside a stretch of
-// background are neither pushed nor popped.  For a vessel mask almost every voxel is background: the pass is two reads
-// and one write per voxel, and the envelope stack (s / t / g: parabola apex, start of its reign, height) holds a few
-// entries per vessel crossing, at the front of the line's slots, which stay in cache.  For a solid mask (the brain) the
-// runs are long and the scan is still O(n) per line whatever the distances.  A line is one dependent chain: inputs are
-// fetched eight steps ahead in both directions, and the pops of the backward scan (entries below the top no longer
-// change) fetch four stack entries at once.
-__global__ void __launch_bounds__(128) k_edt_lines(const int *__restrict__ in, int *__restrict__ out, short *__restrict__ s,
-                                                   int *__restrict__ t, int *__restrict__ g, long long nlines, int len,
-                                                   long long stride, int X, long long outer_stride) {
+// pass y / z: out(u) = min_i (u - i)^2 + f(i) along one axis: lower envelope of parabolas (Meijster).  Thread = one line;
+// the 32 lanes of a warp sit on 32 neighbouring x of one row (lines are enumerated over rows padded to whole words), walk
+// u in lockstep, and every access is a coalesced row segment of the volume.
+// Where f(u) = 0 the answer is 0, and a zero shields everything behind it ((u - i)^2 + f(i) > (u - z)^2 for i beyond a zero
+// at z): only the zeros next to a positive voxel can matter to the envelope.  f(u) = 0 exactly at the background voxels, in
+// every pass, so WHICH voxels are zero comes from the packed foreground bits (one 4-byte word per warp and step) and the
+// input volume is read at foreground voxels only; the y pass also writes foreground voxels only (nobody reads the rest).
+// For a vessel mask almost every voxel is background: the two line passes together read the bit volume four times and a few
+// per cent of the distance volumes, and write the result once.  For a solid mask (the brain) the scan is O(n) per line
+// whatever the distances; its envelope stack lives in global memory, one packed 8-byte entry (apex | start of its reign |
+// height) per push.  A line is one dependent chain: inputs are fetched eight steps ahead in both directions, and the pops
+// of the backward scan (entries below the top no longer change) fetch four stack entries at once.
+// OUT: 0 = squared distance, int32, foreground voxels only (y pass); 1 = distance, float64, every voxel, raises *flag where
+// no zero voxel exists (z pass of the public EDT); 2 = squared distance, int32, every voxel (z pass for the vessel-mask rule).
+template <typename TIn> __device__ __forceinline__ long long edt_in(TIn v);
+template <> __device__ __forceinline__ long long edt_in<uint16_t>(uint16_t v) { return v == 0xFFFF ? (long long)EDT_INF : (long long)v * v; }
+template <> __device__ __forceinline__ long long edt_in<int>(int v) { return v; }
+__device__ __forceinline__ unsigned long long edt_pack(int s, int t, int g) {
+    return ((unsigned long long)(uint32_t)g << 32) | ((unsigned long long)(uint32_t)t << 16) | (unsigned long long)(uint32_t)s;
+}
+
+template <typename TIn, int OUT>
+__global__ void __launch_bounds__(128) k_edt_lines(const TIn *__restrict__ in, void *__restrict__ outv, const uint32_t *__restrict__ bits,
+                                                   unsigned long long *__restrict__ stack, long long nouter, int len, long long stride,
+                                                   int X, int XW, long long outer_stride, long long bit_outer_stride,
+                                                   long long bit_stride, int *flag) {
+    const int lane = threadIdx.x & 31;
+    const long long padded = (long long)XW * 32, nlines = nouter * padded;
+    bool inf = false;
     for (long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x; line < nlines; line += (long long)gridDim.x * blockDim.x) {
-        const long long base = (line / X) * outer_stride + (line % X);
-        const int *f = in + base;
-        short *ss = s + base;
-        int *tt = t + base, *gg = g + base;
-        int *o = out + base;
+        const long long outer = line / padded;
+        const int x = (int)(line % padded);
+        const bool active = x < X;
+        const long long base = outer * outer_stride + (active ? x : 0);
+        const uint32_t *bw = bits + outer * bit_outer_stride + (x >> 5);  // warp-uniform
+        const TIn *f = in + base;
+        unsigned long long *st = stack + base;
         // forward scan.  Registers hold the top of the stack (sq, tq, fq = f(sq)); q = depth - 1, -1 = empty.
-        int q = -1, sq = 0, tq = 0, prev = 0;
+        int q = -1, sq = 0, tq = 0;
+        bool prev = false;
+        uint32_t pw = 0u;  // the warp's bit word of the row before the current batch
         long long fq = 0;
         constexpr int PF = 8;
         for (int u0 = 0; u0 < len; u0 += PF) {
-            int fpre[PF + 1];
+            uint32_t wd[PF + 1], any = 0u;
 #pragma unroll
-            for (int k = 0; k <= PF; ++k) fpre[k] = f[(long long)min(u0 + k, len - 1) * stride];
+            for (int k = 0; k <= PF; ++k) { wd[k] = u0 + k < len ? bw[(long long)(u0 + k) * bit_stride] : 0u; any |= wd[k]; }
+            const uint32_t before = pw;
+            pw = wd[PF - 1];
+            // eight rows of background under the whole warp, behind a row of background and before one (warp-uniform): no voxel
+            // of them can matter to anybody's envelope
+            if ((any | before) == 0u) { prev = false; continue; }
+            bool bit[PF + 1];
+            TIn fpre[PF];
+#pragma unroll
+            for (int k = 0; k <= PF; ++k) bit[k] = active && ((wd[k] >> lane) & 1u);
+#pragma unroll
+            for (int k = 0; k < PF; ++k) fpre[k] = bit[k] ? f[(long long)(u0 + k) * stride] : (TIn)0;
 #pragma unroll
             for (int k = 0; k < PF; ++k) {
                 const int u = u0 + k;
                 if (u >= len) break;
-                const long long fu = fpre[k];
-                const bool wanted = fu == 0 ? (prev > 0 || (u + 1 < len && fpre[k + 1] > 0)) : fu < EDT_INF;
-                prev = (int)fu;
+                const long long fu = bit[k] ? edt_in<TIn>(fpre[k]) : 0;
+                const bool wanted = bit[k] ? fu < EDT_INF : (active && (prev || bit[k + 1]));
+                prev = bit[k];
                 if (!wanted) continue;  // background away from any foreground, or an infinite parabola
                 while (q >= 0) {
                     // F(tq, sq) > F(tq, u): the new parabola is already lower where the top one starts to reign: pop
                     const long long a = (long long)(tq - sq) * (tq - sq) + fq, b = (long long)(tq - u) * (tq - u) + fu;
                     if (a <= b) break;
                     --q;
-                    if (q >= 0) { sq = ss[(long long)q * stride]; tq = tt[(long long)q * stride]; fq = gg[(long long)q * stride]; }
+                    if (q >= 0) {
+                        const unsigned long long e = st[(long long)q * stride];
+                        sq = (int)(e & 0xFFFFu); tq = (int)((e >> 16) & 0xFFFFu); fq = (long long)(e >> 32);
+                    }
                 }
                 long long w = 0;  // first position where parabola u is the lowest
                 if (q >= 0) w = 1 + ((long long)u * u - (long long)sq * sq + fu - fq) / (2LL * (u - sq));
                 if (w < len) {
                     ++q; sq = u; tq = (int)w; fq = fu;
-                    ss[(long long)q * stride] = (short)u; tt[(long long)q * stride] = (int)w; gg[(long long)q * stride] = (int)fu;
+                    st[(long long)q * stride] = edt_pack(u, (int)w, (int)fu);
                 }
             }
         }
         // backward scan
         constexpr int PB = 4;
-        int ps[PB], pt[PB], pg[PB], have = 0;  // entries q-1 .. q-have, fetched ahead (ps[0] is the next one to pop)
+        unsigned long long pe[PB];
+        int have = 0;  // entries q-1 .. q-have, fetched ahead (pe[0] is the next one to pop)
         for (int u0 = len - 1; u0 >= 0; u0 -= PF) {
-            int fpre[PF];
+            uint32_t wd[PF], any = 0u;
 #pragma unroll
-            for (int k = 0; k < PF; ++k) fpre[k] = f[(long long)max(u0 - k, 0) * stride];
+            for (int k = 0; k < PF; ++k) { wd[k] = u0 - k >= 0 ? bw[(long long)(u0 - k) * bit_stride] : 0u; any |= wd[k]; }
+            if (any == 0u) {  // background under the whole warp: zeros, and the envelope is popped when a foreground voxel needs it
+                if (OUT != 0 && active) {
+#pragma unroll
+                    for (int k = 0; k < PF; ++k) {
+                        if (u0 - k < 0) break;
+                        if (OUT == 1) ((double *)outv)[base + (long long)(u0 - k) * stride] = 0.0;
+                        else ((int *)outv)[base + (long long)(u0 - k) * stride] = 0;
+                    }
+                }
+                continue;
+            }
+            bool bit[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) bit[k] = active && ((wd[k] >> lane) & 1u);
 #pragma unroll
             for (int k = 0; k < PF; ++k) {
                 const int u = u0 - k;
@@ -134,34 +216,26 @@ __global__ void __launch_bounds__(128) k_edt_lines(const int *__restrict__ in, i
                 while (q > 0 && u < tq) {  // the top parabola reigns from tq on: below it the previous one does
                     if (have == 0) {
 #pragma unroll
-                        for (int j = 0; j < PB; ++j) {
-                            const long long e = (long long)max(q - 1 - j, 0) * stride;
-                            ps[j] = ss[e]; pt[j] = tt[e]; pg[j] = gg[e];
-                        }
+                        for (int j = 0; j < PB; ++j) pe[j] = st[(long long)max(q - 1 - j, 0) * stride];
                         have = min(PB, q);
                     }
                     --q; --have;
-                    sq = ps[0]; tq = pt[0]; fq = pg[0];
+                    sq = (int)(pe[0] & 0xFFFFu); tq = (int)((pe[0] >> 16) & 0xFFFFu); fq = (long long)(pe[0] >> 32);
 #pragma unroll
-                    for (int j = 0; j + 1 < PB; ++j) { ps[j] = ps[j + 1]; pt[j] = pt[j + 1]; pg[j] = pg[j + 1]; }
+                    for (int j = 0; j + 1 < PB; ++j) pe[j] = pe[j + 1];
                 }
-                long long d = EDT_INF;
-                if (fpre[k] == 0) d = 0;
-                else if (q >= 0) d = (long long)(u - sq) * (u - sq) + fq;
-                o[(long long)u * stride] = d >= EDT_INF ? EDT_INF : (int)d;
+                long long d = 0;
+                if (bit[k]) {
+                    d = q >= 0 ? (long long)(u - sq) * (u - sq) + fq : (long long)EDT_INF;
+                    if (d >= EDT_INF) { d = EDT_INF; inf = true; }
+                }
+                if (OUT == 0) { if (bit[k]) ((int *)outv)[base + (long long)u * stride] = (int)d; }
+                else if (OUT == 1) { if (active) ((double *)outv)[base + (long long)u * stride] = sqrt((double)d); }
+                else { if (active) ((int *)outv)[base + (long long)u * stride] = (int)d; }
             }
         }
     }
-}
-
-__global__ void __launch_bounds__(256) k_edt_sqrt(const int *__restrict__ sq, double *__restrict__ out, long long n, int *no_background) {
-    bool inf = false;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
-        const int v = sq[p];
-        inf |= v >= EDT_INF;
-        out[p] = sqrt((double)v);
-    }
-    if (inf) *no_background = 1;
+    if (OUT == 1 && inf) *flag = 1;
 }
 
 int edt_check(const int64_t *shape) {
@@ -170,38 +244,49 @@ int edt_check(const int64_t *shape) {
     return VRG_OK;
 }
 
-// squared distances (int32) of a device mask; scratch = 3 int32 + 1 int16 volume.  sq_out must hold n ints.
-// Asynchronous on `stream`.
-int edt_squared_device(const uint8_t *d_mask, const int64_t *shape, int *sq_out, cudaStream_t stream) {
+// The three passes.  out_mode 1: Euclidean distance, float64, into `out` (*flag raised when the mask has no zero voxel);
+// out_mode 2: squared distance, int32.  Scratch: uint16 x-distances, int32 y-pass result, the packed bit volume and the
+// 8-byte envelope stack slots (14.1 bytes per voxel).  Asynchronous on `stream`.
+int edt_passes(const uint8_t *d_mask, const int64_t *shape, void *out, int out_mode, int *flag, cudaStream_t stream) {
     const long long Z = shape[0], Y = shape[1], X = shape[2], n = Z * Y * X;
-    Buf a, t, s, g;
-    cudaError_t e = a.alloc(n * sizeof(int), stream);
-    if (e == cudaSuccess) e = t.alloc(n * sizeof(int), stream);
-    if (e == cudaSuccess) e = g.alloc(n * sizeof(int), stream);
-    if (e == cudaSuccess) e = s.alloc(n * sizeof(short), stream);
+    const int XW = (int)((X + 31) / 32);
+    Buf d1, a, st, bits;
+    cudaError_t e = d1.alloc(n * sizeof(uint16_t), stream);
+    if (e == cudaSuccess) e = a.alloc(n * sizeof(int), stream);
+    if (e == cudaSuccess) e = st.alloc(n * sizeof(unsigned long long), stream);
+    if (e == cudaSuccess) e = bits.alloc((size_t)Z * Y * XW * sizeof(uint32_t), stream);
     if (e == cudaSuccess) {
         const int grid = 148 * 8;
-        const int gy = (int)std::min<long long>((Z * X + 127) / 128, 148 * 16), gz = (int)std::min<long long>((Y * X + 127) / 128, 148 * 16);
-        k_edt_rows<<<grid, 256, 0, stream>>>(d_mask, sq_out, Z * Y, (int)X);                                             // mask -> sq_out
-        k_edt_lines<<<gy, 128, 0, stream>>>(sq_out, a.as<int>(), s.as<short>(), t.as<int>(), g.as<int>(), Z * X, (int)Y, X, (int)X, X * Y);   // y: sq_out -> a
-        k_edt_lines<<<gz, 128, 0, stream>>>(a.as<int>(), sq_out, s.as<short>(), t.as<int>(), g.as<int>(), Y * X, (int)Z, X * Y, (int)(X * Y), 0);  // z: a -> sq_out
+        const long long per_block = 128;
+        const int gy = (int)std::min<long long>((Z * XW * 32 + per_block - 1) / per_block, 148 * 16);
+        const int gz = (int)std::min<long long>((Y * XW * 32 + per_block - 1) / per_block, 148 * 16);
+        k_edt_rows<<<grid, 256, (size_t)8 * 2 * XW * sizeof(uint32_t), stream>>>(d_mask, d1.as<uint16_t>(), bits.as<uint32_t>(), Z * Y, (int)X, XW);
+        k_edt_lines<uint16_t, 0><<<gy, 128, 0, stream>>>(d1.as<uint16_t>(), a.p, bits.as<uint32_t>(), st.as<unsigned long long>(), Z, (int)Y, X,
+                                                          (int)X, XW, X * Y, Y * XW, XW, nullptr);
+        if (out_mode == 1)
+            k_edt_lines<int, 1><<<gz, 128, 0, stream>>>(a.as<int>(), out, bits.as<uint32_t>(), st.as<unsigned long long>(), Y, (int)Z, X * Y,
+                                                         (int)X, XW, X, XW, (long long)Y * XW, flag);
+        else
+            k_edt_lines<int, 2><<<gz, 128, 0, stream>>>(a.as<int>(), out, bits.as<uint32_t>(), st.as<unsigned long long>(), Y, (int)Z, X * Y,
+                                                         (int)X, XW, X, XW, (long long)Y * XW, flag);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA;
     return VRG_OK;
 }
 
+int edt_squared_device(const uint8_t *d_mask, const int64_t *shape, int *sq_out, cudaStream_t stream) {
+    return edt_passes(d_mask, shape, sq_out, 2, nullptr, stream);
+}
+
 int edt_device(const uint8_t *d_mask, const int64_t *shape, double *d_out, cudaStream_t stream) {
-    const long long n = (long long)shape[0] * shape[1] * shape[2];
-    Buf sq, flag;
-    cudaError_t e = sq.alloc(n * sizeof(int), stream);
-    if (e == cudaSuccess) e = flag.alloc(sizeof(int), stream);
+    Buf flag;
+    cudaError_t e = flag.alloc(sizeof(int), stream);
     int rc = VRG_OK;
     if (e == cudaSuccess) {
-        rc = edt_squared_device(d_mask, shape, sq.as<int>(), stream);
+        cudaMemsetAsync(flag.p, 0, sizeof(int), stream);
+        rc = edt_passes(d_mask, shape, d_out, 1, flag.as<int>(), stream);
         if (rc == VRG_OK) {
-            cudaMemsetAsync(flag.p, 0, sizeof(int), stream);
-            k_edt_sqrt<<<148 * 8, 256, 0, stream>>>(sq.as<int>(), d_out, n, flag.as<int>());
             int h_flag = 0;
             e = cudaMemcpyAsync(&h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
