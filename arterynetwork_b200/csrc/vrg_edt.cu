@@ -35,14 +35,16 @@ constexpr unsigned FULLMASK = 0xFFFFFFFFu;
 // bit, so a thin mask costs the pass one byte read per voxel and next to nothing else.
 __global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ mask, uint16_t *__restrict__ d1, uint32_t *__restrict__ bits,
                                                   long long nrows, int X, int XW) {
-    extern __shared__ uint32_t sm_rows[];  // per warp: XW words of bits, XW ints "nearest zero in a later word"
+    extern __shared__ uint32_t sm_rows[];  // per warp: XW words of bits, XW ints "last zero before the word", XW "next zero behind it"
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *rb = sm_rows + (size_t)warp * 2 * XW;
-    int *rf = (int *)(rb + XW);
+    uint32_t *rb = sm_rows + (size_t)warp * 3 * XW;
+    int *lf = (int *)(rb + XW), *rf = lf + XW;
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const int NONE_L = -(1 << 20), NONE_R = 1 << 20;
+    const uint32_t tail = (X & 31) ? ((1u << (X & 31)) - 1u) : 0xFFFFFFFFu;
     for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp; r < nrows; r += nwarps) {
         const uint8_t *row = mask + r * X;
+        uint32_t seen = 0u;  // OR of the foreground words this lane stored
         if ((X & 3) == 0 && (((uintptr_t)row) & 3) == 0) {
             // 128 voxels per step: a 4-byte load per lane, its four "non-zero" bits, then the eight lanes of each 32-voxel word
             // OR their nibbles together (three shuffles)
@@ -60,8 +62,10 @@ __global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ ma
                 word |= __shfl_xor_sync(FULLMASK, word, 4);
                 const int w = w0 + (lane >> 3);
                 if ((lane & 7) == 0 && w < XW) {
+                    const uint32_t real = w == XW - 1 ? (word & tail) : word;
                     rb[w] = word;
-                    bits[r * XW + w] = (w == XW - 1 && (X & 31)) ? (word & ((1u << (X & 31)) - 1u)) : word;
+                    bits[r * XW + w] = real;
+                    seen |= real;
                 }
             }
         } else {
@@ -70,36 +74,89 @@ __global__ void __launch_bounds__(256) k_edt_rows(const uint8_t *__restrict__ ma
                 const bool fg = x < X ? row[x] != 0 : true;
                 const uint32_t word = __ballot_sync(FULLMASK, fg);
                 if (lane == 0) {
+                    const uint32_t real = w == XW - 1 ? (word & tail) : word;
                     rb[w] = word;
-                    bits[r * XW + w] = (w == XW - 1 && (X & 31)) ? (word & ((1u << (X & 31)) - 1u)) : word;
+                    bits[r * XW + w] = real;
+                    seen |= real;
+                }
+            }
+        }
+        if (!__any_sync(FULLMASK, seen != 0u)) continue;  // a row of background: nothing to store
+        __syncwarp();
+        // per word: the last zero in the words before it, the next zero in the words behind it (warp scans, 32 words per step)
+        int carry = NONE_L;
+        for (int c = 0; c < XW; c += 32) {
+            const int w = c + lane;
+            const uint32_t zw = w < XW ? ~rb[w] : 0u;
+            int v = zw ? 32 * w + 31 - __clz(zw) : NONE_L;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULLMASK, v, o);
+                if (lane >= o) v = max(v, t);
+            }
+            int ex = __shfl_up_sync(FULLMASK, v, 1);
+            if (lane == 0) ex = NONE_L;
+            if (w < XW) lf[w] = max(ex, carry);
+            carry = max(carry, __shfl_sync(FULLMASK, v, 31));
+        }
+        carry = NONE_R;
+        for (int c = ((XW - 1) / 32) * 32; c >= 0; c -= 32) {
+            const int w = c + lane;
+            const uint32_t zw = w < XW ? ~rb[w] : 0u;
+            int v = zw ? 32 * w + __ffs(zw) - 1 : NONE_R;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_down_sync(FULLMASK, v, o);
+                if (lane + o < 32) v = min(v, t);
+            }
+            int ex = __shfl_down_sync(FULLMASK, v, 1);
+            if (lane == 31) ex = NONE_R;
+            if (w < XW) rf[w] = min(ex, carry);
+            carry = min(carry, __shfl_sync(FULLMASK, v, 0));
+        }
+        __syncwarp();
+        // the words that hold foreground, one after the other (lane = voxel of the word)
+        for (int c = 0; c < XW; c += 32) {
+            const int wl = c + lane;
+            unsigned todo = __ballot_sync(FULLMASK, wl < XW && (wl == XW - 1 ? (rb[wl] & tail) : rb[wl]) != 0u);
+            while (todo) {
+                const int w = c + __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t word = rb[w], zw = ~word;
+                const int x = 32 * w + lane;
+                if (x < X && ((word >> lane) & 1u)) {
+                    const uint32_t below = zw & ((2u << lane) - 1u), above = zw & ~((1u << lane) - 1u);
+                    const int xl = below ? 32 * w + 31 - __clz(below) : lf[w];
+                    const int xr = above ? 32 * w + __ffs(above) - 1 : rf[w];
+                    const int d = min(x - xl, xr - x);
+                    d1[r * X + x] = d >= 32768 ? (uint16_t)0xFFFF : (uint16_t)d;
                 }
             }
         }
         __syncwarp();
-        if (lane == 0) {  // next zero behind every word (a few hundred trivial steps per row)
-            int nz = NONE_R;
-            for (int w = XW - 1; w >= 0; --w) {
-                rf[w] = nz;
-                const uint32_t zw = ~rb[w];
-                if (zw) nz = 32 * w + __ffs(zw) - 1;
-            }
+    }
+}
+
+// Summary of the bit volume for the line passes: one word per (line-warp, batch of 8 steps) = OR of the warp's bit words of
+// the batch's rows and of the row before and the row behind it.  Zero = the batch is background and no voxel of it can
+// matter to anybody's envelope: the line passes skip it after one load.
+__global__ void __launch_bounds__(256) k_edt_summary(const uint32_t *__restrict__ bits, uint32_t *__restrict__ sum, long long nouter, int len,
+                                                     int XW, long long bit_outer_stride, long long bit_stride) {
+    const int nb = (len + 7) / 8;
+    const long long total = nouter * nb * XW;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int xw = (int)(i % XW);
+        const long long t = i / XW;
+        const int ub = (int)(t % nb);
+        const long long outer = t / nb;
+        const uint32_t *bw = bits + outer * bit_outer_stride + xw;
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int k = -1; k <= 8; ++k) {
+            const int u = 8 * ub + k;
+            if (u >= 0 && u < len) acc |= bw[(long long)u * bit_stride];
         }
-        __syncwarp();
-        int left = NONE_L;  // last zero in the words before this one
-        for (int w = 0; w < XW; ++w) {
-            const uint32_t word = rb[w], zw = ~word;
-            if (word == 0u) { left = 32 * w + 31; continue; }  // a word of background: nothing to store (warp-uniform)
-            const int x = 32 * w + lane;
-            if (x < X && ((word >> lane) & 1u)) {
-                const uint32_t below = zw & ((2u << lane) - 1u), above = zw & ~((1u << lane) - 1u);
-                const int xl = below ? 32 * w + 31 - __clz(below) : left;
-                const int xr = above ? 32 * w + __ffs(above) - 1 : rf[w];
-                const int d = min(x - xl, xr - x);
-                d1[r * X + x] = d >= 32768 ? (uint16_t)0xFFFF : (uint16_t)d;
-            }
-            if (zw) left = 32 * w + 31 - __clz(zw);
-        }
-        __syncwarp();
+        sum[i] = acc;  // layout [outer][batch][xw]
     }
 }
 
@@ -128,7 +185,7 @@ template <typename TIn, int OUT>
 __global__ void __launch_bounds__(128) k_edt_lines(const TIn *__restrict__ in, void *__restrict__ outv, const uint32_t *__restrict__ bits,
                                                    unsigned long long *__restrict__ stack, long long nouter, int len, long long stride,
                                                    int X, int XW, long long outer_stride, long long bit_outer_stride,
-                                                   long long bit_stride, int *flag) {
+                                                   long long bit_stride, const uint32_t *__restrict__ sum, int *flag) {
     const int lane = threadIdx.x & 31;
     const long long padded = (long long)XW * 32, nlines = nouter * padded;
     bool inf = false;
@@ -138,23 +195,23 @@ __global__ void __launch_bounds__(128) k_edt_lines(const TIn *__restrict__ in, v
         const bool active = x < X;
         const long long base = outer * outer_stride + (active ? x : 0);
         const uint32_t *bw = bits + outer * bit_outer_stride + (x >> 5);  // warp-uniform
+        const int nb = (len + 7) / 8;
+        const uint32_t *sw = sum + (outer * nb) * XW + (x >> 5);        // warp-uniform; batch b at sw[b * XW]
         const TIn *f = in + base;
         unsigned long long *st = stack + base;
         // forward scan.  Registers hold the top of the stack (sq, tq, fq = f(sq)); q = depth - 1, -1 = empty.
         int q = -1, sq = 0, tq = 0;
         bool prev = false;
-        uint32_t pw = 0u;  // the warp's bit word of the row before the current batch
         long long fq = 0;
         constexpr int PF = 8;
+        static_assert(PF == 8, "the summary words describe batches of 8 steps");
         for (int u0 = 0; u0 < len; u0 += PF) {
-            uint32_t wd[PF + 1], any = 0u;
+            // eight rows of background under the whole warp, behind a row of background and before one (warp-uniform): no
+            // voxel of them can matter to anybody's envelope
+            if (sw[(long long)(u0 >> 3) * XW] == 0u) { prev = false; continue; }
+            uint32_t wd[PF + 1];
 #pragma unroll
-            for (int k = 0; k <= PF; ++k) { wd[k] = u0 + k < len ? bw[(long long)(u0 + k) * bit_stride] : 0u; any |= wd[k]; }
-            const uint32_t before = pw;
-            pw = wd[PF - 1];
-            // eight rows of background under the whole warp, behind a row of background and before one (warp-uniform): no voxel
-            // of them can matter to anybody's envelope
-            if ((any | before) == 0u) { prev = false; continue; }
+            for (int k = 0; k <= PF; ++k) wd[k] = u0 + k < len ? bw[(long long)(u0 + k) * bit_stride] : 0u;
             bool bit[PF + 1];
             TIn fpre[PF];
 #pragma unroll
@@ -191,28 +248,29 @@ __global__ void __launch_bounds__(128) k_edt_lines(const TIn *__restrict__ in, v
         constexpr int PB = 4;
         unsigned long long pe[PB];
         int have = 0;  // entries q-1 .. q-have, fetched ahead (pe[0] is the next one to pop)
-        for (int u0 = len - 1; u0 >= 0; u0 -= PF) {
-            uint32_t wd[PF], any = 0u;
-#pragma unroll
-            for (int k = 0; k < PF; ++k) { wd[k] = u0 - k >= 0 ? bw[(long long)(u0 - k) * bit_stride] : 0u; any |= wd[k]; }
-            if (any == 0u) {  // background under the whole warp: zeros, and the envelope is popped when a foreground voxel needs it
+        for (int ub = nb - 1; ub >= 0; --ub) {  // the same batches, last row first
+            const int u0 = min(len - 1, 8 * ub + 7), ulo = 8 * ub;
+            if (sw[(long long)ub * XW] == 0u) {  // background under the whole warp: zeros; the envelope is popped when a foreground voxel needs it
                 if (OUT != 0 && active) {
 #pragma unroll
                     for (int k = 0; k < PF; ++k) {
-                        if (u0 - k < 0) break;
+                        if (u0 - k < ulo) break;
                         if (OUT == 1) ((double *)outv)[base + (long long)(u0 - k) * stride] = 0.0;
                         else ((int *)outv)[base + (long long)(u0 - k) * stride] = 0;
                     }
                 }
                 continue;
             }
+            uint32_t wd[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) wd[k] = u0 - k >= ulo ? bw[(long long)(u0 - k) * bit_stride] : 0u;
             bool bit[PF];
 #pragma unroll
             for (int k = 0; k < PF; ++k) bit[k] = active && ((wd[k] >> lane) & 1u);
 #pragma unroll
             for (int k = 0; k < PF; ++k) {
                 const int u = u0 - k;
-                if (u < 0) break;
+                if (u < ulo) break;
                 while (q > 0 && u < tq) {  // the top parabola reigns from tq on: below it the previous one does
                     if (have == 0) {
 #pragma unroll
@@ -250,25 +308,29 @@ int edt_check(const int64_t *shape) {
 int edt_passes(const uint8_t *d_mask, const int64_t *shape, void *out, int out_mode, int *flag, cudaStream_t stream) {
     const long long Z = shape[0], Y = shape[1], X = shape[2], n = Z * Y * X;
     const int XW = (int)((X + 31) / 32);
-    Buf d1, a, st, bits;
+    Buf d1, a, st, bits, sum;
+    const long long nby = (Y + 7) / 8, nbz = (Z + 7) / 8;
     cudaError_t e = d1.alloc(n * sizeof(uint16_t), stream);
     if (e == cudaSuccess) e = a.alloc(n * sizeof(int), stream);
     if (e == cudaSuccess) e = st.alloc(n * sizeof(unsigned long long), stream);
     if (e == cudaSuccess) e = bits.alloc((size_t)Z * Y * XW * sizeof(uint32_t), stream);
+    if (e == cudaSuccess) e = sum.alloc((size_t)std::max(Z * nby, nbz * Y) * XW * sizeof(uint32_t), stream);
     if (e == cudaSuccess) {
         const int grid = 148 * 8;
         const long long per_block = 128;
         const int gy = (int)std::min<long long>((Z * XW * 32 + per_block - 1) / per_block, 148 * 16);
         const int gz = (int)std::min<long long>((Y * XW * 32 + per_block - 1) / per_block, 148 * 16);
-        k_edt_rows<<<grid, 256, (size_t)8 * 2 * XW * sizeof(uint32_t), stream>>>(d_mask, d1.as<uint16_t>(), bits.as<uint32_t>(), Z * Y, (int)X, XW);
+        k_edt_rows<<<grid, 256, (size_t)8 * 3 * XW * sizeof(uint32_t), stream>>>(d_mask, d1.as<uint16_t>(), bits.as<uint32_t>(), Z * Y, (int)X, XW);
+        k_edt_summary<<<grid, 256, 0, stream>>>(bits.as<uint32_t>(), sum.as<uint32_t>(), Z, (int)Y, XW, Y * XW, XW);
         k_edt_lines<uint16_t, 0><<<gy, 128, 0, stream>>>(d1.as<uint16_t>(), a.p, bits.as<uint32_t>(), st.as<unsigned long long>(), Z, (int)Y, X,
-                                                          (int)X, XW, X * Y, Y * XW, XW, nullptr);
+                                                          (int)X, XW, X * Y, Y * XW, XW, sum.as<uint32_t>(), nullptr);
+        k_edt_summary<<<grid, 256, 0, stream>>>(bits.as<uint32_t>(), sum.as<uint32_t>(), Y, (int)Z, XW, XW, (long long)Y * XW);
         if (out_mode == 1)
             k_edt_lines<int, 1><<<gz, 128, 0, stream>>>(a.as<int>(), out, bits.as<uint32_t>(), st.as<unsigned long long>(), Y, (int)Z, X * Y,
-                                                         (int)X, XW, X, XW, (long long)Y * XW, flag);
+                                                         (int)X, XW, X, XW, (long long)Y * XW, sum.as<uint32_t>(), flag);
         else
             k_edt_lines<int, 2><<<gz, 128, 0, stream>>>(a.as<int>(), out, bits.as<uint32_t>(), st.as<unsigned long long>(), Y, (int)Z, X * Y,
-                                                         (int)X, XW, X, XW, (long long)Y * XW, flag);
+                                                         (int)X, XW, X, XW, (long long)Y * XW, sum.as<uint32_t>(), flag);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? VRG_ERR_NOMEM : VRG_ERR_CUDA;

@@ -7,9 +7,11 @@
 //   GVV:216      the result is saved as a uint8 mask
 // and labelVolume (GVV:108-136): labelled volume + (label, size) list, components numbered in raster order.
 //
-// Connected components: lock-free union-find over voxel indices (roots = smallest index of the component, so the
-// raster-order numbering of skimage / SciPy falls out of a prefix sum over the roots).  Voxels of one x-run start out
-// pointing at the run's first voxel (a warp scan per row), so only links between rows and planes need unions.
+// Connected components: lock-free union-find over voxel indices with randomised linking (the root with the smaller hashed
+// index wins: expected logarithmic depth whatever the order of the concurrent unions); the smallest voxel index of every
+// component is recorded beside its size, and the raster-order numbering of skimage / SciPy is a prefix sum over those first
+// voxels.  Voxels of one x-run start out pointing at the run's first voxel (a warp scan per row), so only links between
+// rows and planes need unions.
 #include "../../include/vrg_b200.h"
 
 #include "vrg_scratch.cuh"
@@ -62,9 +64,14 @@ __global__ void __launch_bounds__(256) k_rule(const double *__restrict__ v, cons
 }
 
 // ---- connected components ------------------------------------------------------------------------------------------------
-// parent[p] = first voxel of p's x-run (foreground) or -1 (background): one warp per row, running maximum of the
-// positions of background voxels
-__global__ void __launch_bounds__(256) k_cc_init(const uint8_t *__restrict__ fg, int *__restrict__ parent, long long nrows, int X) {
+// parent[p] = first voxel of p's x-run, foreground voxels only (nobody reads the parent of a background voxel: every consumer
+// looks at the one-byte mask first, so a thin mask costs each pass 1 byte per voxel instead of 4): one warp per row, running
+// maximum of the positions of background voxels
+// The foreground voxels are also appended to `list` (any order): the union, flatten and count steps then run one thread per
+// FOREGROUND voxel with full warps, instead of one thread per voxel with a lane or two of a warp at work.
+__global__ void __launch_bounds__(256) k_cc_init(const uint8_t *__restrict__ fg, int *__restrict__ parent, int *__restrict__ size,
+                                                 int *__restrict__ first, int *__restrict__ list, unsigned int *__restrict__ list_n,
+                                                 long long nrows, int X) {
     const int lane = threadIdx.x & 31;
     const long long nwarps = (long long)gridDim.x * 8;
     for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < nrows; r += nwarps) {
@@ -73,6 +80,12 @@ __global__ void __launch_bounds__(256) k_cc_init(const uint8_t *__restrict__ fg,
         for (int x0 = 0; x0 < X; x0 += 32) {
             const int x = x0 + lane;
             const bool f = x < X && row[x] != 0;
+            const unsigned fmask = __ballot_sync(FULLMASK, f);
+            if (fmask == 0u) { carry = min(x0 + 31, X - 1); continue; }  // 32 voxels of background: the last one is the nearest so far
+            unsigned int slot = 0;
+            if (lane == 0) slot = atomicAdd(list_n, (unsigned int)__popc(fmask));
+            slot = __shfl_sync(FULLMASK, slot, 0);
+            if (f) list[slot + __popc(fmask & ((1u << lane) - 1u))] = (int)(r * X + x);
             int v = (x < X && !f) ? x : -1;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -81,7 +94,11 @@ __global__ void __launch_bounds__(256) k_cc_init(const uint8_t *__restrict__ fg,
             }
             v = max(v, carry);
             carry = __shfl_sync(FULLMASK, v, 31);
-            if (x < X) parent[r * X + x] = f ? (int)(r * X + v + 1) : -1;
+            if (f) {  // size / first are read at roots only, and roots are foreground voxels
+                parent[r * X + x] = (int)(r * X + v + 1);
+                size[r * X + x] = 0;
+                if (first != nullptr) first[r * X + x] = 0x7FFFFFFF;
+            }
         }
     }
 }
@@ -95,14 +112,25 @@ __device__ __forceinline__ int cc_find(int *parent, int a) {
         a = ga;
     }
 }
+// Which of two roots wins a union is decided by a hash of their indices, not by the indices: all links of a thin structure
+// are made at the same time between singletons, and "the smaller index wins" then builds one path as long as the vessel
+// (every later find walked it: 11 GB of pointer chasing at C3), while random priorities cut it into pieces of expected
+// length two or three and keep the forest logarithmically shallow.  Links go from a root to a node of strictly smaller
+// (priority, index), so there are no cycles; a root is hooked by compare-and-swap, so a node is hooked once.
+__device__ __forceinline__ uint32_t cc_prio(int a) {
+    uint32_t x = (uint32_t)a * 0x9E3779B1u;
+    x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
+    return x;
+}
 __device__ __forceinline__ void cc_union(int *parent, int a, int b) {
     while (true) {
         a = cc_find(parent, a); b = cc_find(parent, b);
         if (a == b) return;
-        if (a < b) { const int t = a; a = b; b = t; }  // the larger root is hung under the smaller one
-        const int old = atomicMin(&parent[a], b);
+        const uint32_t pa = cc_prio(a), pb = cc_prio(b);
+        if (pa < pb || (pa == pb && a < b)) { const int t = a; a = b; b = t; }  // a loses: it is hung under b
+        const int old = atomicCAS(&parent[a], a, b);
         if (old == a) return;
-        a = old;
+        a = old;  // somebody hooked a first: go on from its new parent
     }
 }
 
@@ -113,69 +141,116 @@ __device__ __forceinline__ void cc_union(int *parent, int a, int b) {
 // Four voxels per thread and load: background words (almost all of a vessel mask) cost one 32-bit load.
 __device__ __forceinline__ void cc_merge_voxel(const uint8_t *__restrict__ fg, int *parent, long long p, int Y, int X) {
     const int x = (int)(p % X), y = (int)((p / X) % Y), z = (int)(p / ((long long)X * Y));
-    const bool pstart = x == 0 || !fg[p - 1];
+    // the 17 mask bytes the rule below can look at are requested together (one round trip instead of a chain of them)
+    const bool pl = x > 0 && fg[p - 1];
+    bool ok[4], c0[4], cm1[4], cm2[4], cp1[4];
+    long long qs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int dz = k == 0 ? 0 : -1, dy = k == 0 ? -1 : k - 2;
         const int zz = z + dz, yy = y + dy;
-        if (zz < 0 || yy < 0 || yy >= Y) continue;
-        const long long q = ((long long)zz * Y + yy) * X + x;
-        const bool ql = x > 0 && fg[q - 1];
-        if (fg[q]) {
-            if (pstart || !ql) cc_union(parent, (int)p, (int)q);
+        ok[k] = zz >= 0 && yy >= 0 && yy < Y;
+        const long long q = ok[k] ? ((long long)zz * Y + yy) * X + x : p;
+        qs[k] = q;
+        c0[k] = ok[k] && fg[q];
+        cm1[k] = ok[k] && x > 0 && fg[q - 1];
+        cm2[k] = ok[k] && x > 1 && fg[q - 2];
+        cp1[k] = ok[k] && x + 1 < X && fg[q + 1];
+    }
+    const bool pstart = !pl;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+        const long long q = qs[k];
+        if (c0[k]) {
+            if (pstart || !cm1[k]) cc_union(parent, (int)p, (int)q);
         } else {
-            if (ql && (pstart || x < 2 || !fg[q - 2])) cc_union(parent, (int)p, (int)(q - 1));
-            if (x + 1 < X && fg[q + 1]) cc_union(parent, (int)p, (int)(q + 1));  // q + 1 starts its run (q is background)
+            if (cm1[k] && (pstart || x < 2 || !cm2[k])) cc_union(parent, (int)p, (int)(q - 1));
+            if (cp1[k]) cc_union(parent, (int)p, (int)(q + 1));  // q + 1 starts its run (q is background)
         }
     }
 }
-__global__ void __launch_bounds__(256) k_cc_merge(const uint8_t *__restrict__ fg, int *parent, int Z, int Y, int X) {
-    const long long n = (long long)Z * Y * X, ngroups = (n + 3) / 4;
-    const bool aligned = (((uintptr_t)fg) & 3) == 0;
-    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (long long)gridDim.x * 256) {
-        const long long p0 = g * 4;
-        uint32_t w;
-        if (aligned && p0 + 3 < n) w = *(const uint32_t *)(fg + p0);
-        else {
-            w = 0;
-            for (int b = 0; b < 4; ++b)
-                if (p0 + b < n) w |= (uint32_t)fg[p0 + b] << (8 * b);
-        }
-        if (w == 0u) continue;
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if ((w >> (8 * b)) & 0xFFu) cc_merge_voxel(fg, parent, p0 + b, Y, X);
+__global__ void __launch_bounds__(256) k_cc_merge(const uint8_t *__restrict__ fg, int *parent, const int *__restrict__ list,
+                                                  const unsigned int *__restrict__ list_n, int Y, int X) {
+    // Every lane of a warp makes the same number of trips and the warp is brought back together at the end of each one: the
+    // unions are compare-and-swap loops, and without the barrier the compiler lets the lanes of a warp drift apart for the rest
+    // of the kernel (seen with ncu on the first version: one active thread per instruction, 20 x the instructions).
+    const long long m = *list_n, nround = (m + 31) / 32 * 32;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nround; i += (long long)gridDim.x * 256) {
+        if (i < m) cc_merge_voxel(fg, parent, list[i], Y, X);
+        __syncwarp();
     }
 }
 
 // parent[p] = root; component sizes at the roots (one atomic per group of equal roots in a warp).
 // The walk to the root is read-only here: with path halving, another thread's late write of a stale grandparent
 // could land on parent[p] after p's own thread stored the root, and the consumers below index by parent[p].
-__global__ void __launch_bounds__(256) k_cc_flatten_count(int *parent, int *__restrict__ size, long long n) {
+// `first` (optional): first[root] = smallest voxel index of the component (the numbering is in raster order of those).
+__device__ __forceinline__ uint32_t cc_load4(const uint8_t *__restrict__ fg, long long p0, long long n, bool aligned) {
+    if (aligned && p0 + 3 < n) return *(const uint32_t *)(fg + p0);
+    uint32_t w = 0u;
+    for (int b = 0; b < 4; ++b)
+        if (p0 + b < n) w |= (uint32_t)(fg[p0 + b] != 0) << (8 * b);
+    return w;
+}
+__global__ void __launch_bounds__(256) k_cc_flatten_count(int *parent, int *__restrict__ size, int *__restrict__ first,
+                                                          const int *__restrict__ list, const unsigned int *__restrict__ list_n) {
     const int lane = threadIdx.x & 31;
-    const long long nround = (n + 255) / 256 * 256;
-    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < nround; p += (long long)gridDim.x * 256) {
-        int root = -1;
-        if (p < n && parent[p] >= 0) {
-            root = (int)p;
+    const long long m = *list_n, nround = (m + 31) / 32 * 32;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nround; i += (long long)gridDim.x * 256) {
+        int root = -1, p = 0x7FFFFFFF;
+        if (i < m) {
+            p = list[i];
+            root = p;
             for (int up = parent[root]; up != root; up = parent[root]) root = up;
             parent[p] = root;
         }
         const unsigned peers = __match_any_sync(FULLMASK, root);
-        if (root >= 0 && lane == __ffs(peers) - 1) atomicAdd(&size[root], __popc(peers));
+        const int pmin = __reduce_min_sync(peers, p);  // smallest voxel index among the lanes of the same root (the list has no order)
+        if (root >= 0 && lane == __ffs(peers) - 1) {
+            atomicAdd(&size[root], __popc(peers));
+            if (first != nullptr) atomicMin(&first[root], pmin);
+        }
+    }
+}
+// chunk_count[c] = first voxels of components in chunk c of the volume (chunk_count zeroed by the caller)
+__global__ void __launch_bounds__(256) k_cc_chunk_roots(const int *__restrict__ parent, const int *__restrict__ first,
+                                                        const int *__restrict__ list, const unsigned int *__restrict__ list_n,
+                                                        int *__restrict__ chunk_count, int chunk) {
+    const long long m = *list_n;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < m; i += (long long)gridDim.x * 256) {
+        const int p = list[i];
+        if (first[parent[p]] == p) atomicAdd(&chunk_count[p / chunk], 1);
     }
 }
 
 // keep[p] = foreground and component size > min_size (GVV:198-200); counts the kept voxels and components
-__global__ void __launch_bounds__(256) k_cc_filter(const int *__restrict__ parent, const int *__restrict__ size, long long n,
-                                                   long long min_size, uint8_t *__restrict__ out, unsigned long long *counts) {
+__global__ void __launch_bounds__(256) k_cc_filter(const uint8_t *__restrict__ fg, const int *__restrict__ parent,
+                                                   const int *__restrict__ size, long long n, long long min_size,
+                                                   uint8_t *__restrict__ out, unsigned long long *counts) {
     unsigned long long kept = 0, comps = 0;
-    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n; p += (long long)gridDim.x * 256) {
-        const int root = parent[p];
-        const bool keep = root >= 0 && size[root] > min_size;
-        out[p] = keep ? 1 : 0;
-        kept += keep;
-        comps += keep && root == p;
+    const bool aligned = (((uintptr_t)fg) & 3) == 0 && (((uintptr_t)out) & 3) == 0;
+    const long long ngroups = (n + 3) / 4;
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (long long)gridDim.x * 256) {
+        const long long p0 = g * 4;
+        const uint32_t w = cc_load4(fg, p0, n, aligned);
+        uint32_t o = 0u;
+        if (w != 0u) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (!((w >> (8 * b)) & 0xFFu)) continue;
+                const long long p = p0 + b;
+                const int root = parent[p];
+                const bool keep = size[root] > min_size;
+                o |= (uint32_t)keep << (8 * b);
+                kept += keep;
+                comps += keep && root == p;
+            }
+        }
+        if (aligned && p0 + 3 < n) *(uint32_t *)(out + p0) = o;
+        else
+            for (int b = 0; b < 4; ++b)
+                if (p0 + b < n) out[p0 + b] = (uint8_t)((o >> (8 * b)) & 1u);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -189,23 +264,10 @@ __global__ void __launch_bounds__(256) k_cc_filter(const int *__restrict__ paren
 }
 
 // raster-order numbering: roots per chunk of 1024 voxels -> exclusive scan over chunks -> labels
-constexpr int CHUNK = 1024;
-__global__ void __launch_bounds__(256) k_cc_chunk_roots(const int *__restrict__ parent, long long n, int *__restrict__ chunk_count) {
-    const long long c0 = (long long)blockIdx.x;
-    for (long long c = c0; c * CHUNK < n; c += gridDim.x) {
-        int cnt = 0;
-        for (int i = threadIdx.x; i < CHUNK; i += 256) {
-            const long long p = c * CHUNK + i;
-            cnt += p < n && parent[p] == p;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, o);
-        __shared__ int s[8];
-        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
-        __syncthreads();
-        if (threadIdx.x == 0) chunk_count[c] = s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7];
-        __syncthreads();
-    }
+constexpr int CHUNK = 4096;
+__device__ __forceinline__ bool cc_is_first(const uint8_t *__restrict__ fg, const int *__restrict__ parent, const int *__restrict__ first,
+                                            long long p) {
+    return fg[p] && first[parent[p]] == (int)p;
 }
 // one block: chunk_count -> exclusive prefix sums in place; total -> *total
 __global__ void __launch_bounds__(1024) k_cc_scan_chunks(int *chunk_count, long long nchunks, int *total) {
@@ -245,16 +307,19 @@ __global__ void __launch_bounds__(1024) k_cc_scan_chunks(int *chunk_count, long 
 }
 // number[root] = 1 + rank of the root in raster order (written into `size`, which is no longer needed at the roots'
 // slots once `sizes_by_label` has been filled), then labels[p] = number[root(p)]
-__global__ void __launch_bounds__(256) k_cc_number_roots(const int *__restrict__ parent, long long n, const int *__restrict__ chunk_base,
-                                                         int *__restrict__ size, int *__restrict__ sizes_by_label) {
+__global__ void __launch_bounds__(256) k_cc_number_roots(const uint8_t *__restrict__ fg, const int *__restrict__ parent,
+                                                         const int *__restrict__ first, long long n, const int *__restrict__ chunk_base,
+                                                         const int *__restrict__ total, int *__restrict__ size,
+                                                         int *__restrict__ sizes_by_label) {
     const long long c0 = (long long)blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int s_w[8];
     for (long long c = c0; c * CHUNK < n; c += gridDim.x) {
         int running = chunk_base[c];
+        if (((c + 1) * CHUNK < n ? chunk_base[c + 1] : *total) == running) continue;  // no first voxel in this chunk (block-uniform)
         for (int i0 = 0; i0 < CHUNK; i0 += 256) {  // 256 voxels at a time, in order
             const long long p = c * CHUNK + i0 + threadIdx.x;
-            const bool is_root = p < n && parent[p] == p;
+            const bool is_root = p < n && cc_is_first(fg, parent, first, p);  // the component's first voxel stands for its root
             const unsigned b = __ballot_sync(FULLMASK, is_root);
             if (lane == 0) s_w[warp] = __popc(b);
             __syncthreads();
@@ -264,19 +329,35 @@ __global__ void __launch_bounds__(256) k_cc_number_roots(const int *__restrict__
             for (int w = 0; w < 8; ++w) tot += s_w[w];
             if (is_root) {
                 const int number = before + __popc(b & ((1u << lane) - 1u)) + 1;
-                sizes_by_label[number - 1] = size[p];
-                size[p] = number;
+                const int root = parent[p];
+                sizes_by_label[number - 1] = size[root];
+                size[root] = number;
             }
             running += tot;
             __syncthreads();
         }
     }
 }
-__global__ void __launch_bounds__(256) k_cc_labels(const int *__restrict__ parent, const int *__restrict__ number, long long n,
-                                                   int *__restrict__ labels) {
-    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n; p += (long long)gridDim.x * 256) {
-        const int root = parent[p];
-        labels[p] = root >= 0 ? number[root] : 0;
+__global__ void __launch_bounds__(256) k_cc_labels(const uint8_t *__restrict__ fg, const int *__restrict__ parent,
+                                                   const int *__restrict__ number, long long n, int *__restrict__ labels) {
+    const bool aligned = (((uintptr_t)fg) & 3) == 0 && (((uintptr_t)labels) & 15) == 0;
+    const long long ngroups = (n + 3) / 4;
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < ngroups; g += (long long)gridDim.x * 256) {
+        const long long p0 = g * 4;
+        const uint32_t w = cc_load4(fg, p0, n, aligned);
+        int4 o = make_int4(0, 0, 0, 0);
+        if (w != 0u) {
+            if (w & 0xFFu) o.x = number[parent[p0]];
+            if (w & 0xFF00u) o.y = number[parent[p0 + 1]];
+            if (w & 0xFF0000u) o.z = number[parent[p0 + 2]];
+            if (w & 0xFF000000u) o.w = number[parent[p0 + 3]];
+        }
+        if (aligned && p0 + 3 < n) *(int4 *)(labels + p0) = o;
+        else {
+            const int v[4] = {o.x, o.y, o.z, o.w};
+            for (int b = 0; b < 4; ++b)
+                if (p0 + b < n) labels[p0 + b] = v[b];
+        }
     }
 }
 
@@ -300,12 +381,14 @@ bool shape_ok(const int64_t *shape) {
 }
 
 // parent / size of the 26-connected components of a device uint8 volume (non-zero = foreground)
-int components_device(const uint8_t *d_fg, const int64_t *shape, int *d_parent, int *d_size, cudaStream_t st) {
-    const long long Z = shape[0], Y = shape[1], X = shape[2], n = Z * Y * X;
-    cudaMemsetAsync(d_size, 0, n * sizeof(int), st);
-    k_cc_init<<<GRID, 256, 0, st>>>(d_fg, d_parent, Z * Y, (int)X);
-    k_cc_merge<<<GRID, 256, 0, st>>>(d_fg, d_parent, (int)Z, (int)Y, (int)X);
-    k_cc_flatten_count<<<GRID, 256, 0, st>>>(d_parent, d_size, n);
+// d_list: n ints; d_list_n: one counter (the number of foreground voxels ends up there)
+int components_device(const uint8_t *d_fg, const int64_t *shape, int *d_parent, int *d_size, int *d_first, int *d_list,
+                      unsigned int *d_list_n, cudaStream_t st) {
+    const long long Z = shape[0], Y = shape[1], X = shape[2];
+    cudaMemsetAsync(d_list_n, 0, sizeof(unsigned int), st);
+    k_cc_init<<<GRID, 256, 0, st>>>(d_fg, d_parent, d_size, d_first, d_list, d_list_n, Z * Y, (int)X);
+    k_cc_merge<<<GRID, 256, 0, st>>>(d_fg, d_parent, d_list, d_list_n, (int)Y, (int)X);
+    k_cc_flatten_count<<<GRID, 256, 0, st>>>(d_parent, d_size, d_first, d_list, d_list_n);
     return status_of(cudaGetLastError());
 }
 
@@ -320,23 +403,28 @@ extern "C" int vrg_label_components_device(int device, const uint8_t *binary_dev
     vrg_scratch::pool_setup(device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const long long n = (long long)shape[0] * shape[1] * shape[2], nchunks = (n + CHUNK - 1) / CHUNK;
-    DevBuf parent, size, chunks, total, bylabel;
+    DevBuf parent, size, first, list, list_n, chunks, total, bylabel;
     cudaError_t e = parent.alloc(n * sizeof(int), st);
     if (e == cudaSuccess) e = size.alloc(n * sizeof(int), st);
+    if (e == cudaSuccess) e = first.alloc(n * sizeof(int), st);
+    if (e == cudaSuccess) e = list.alloc(n * sizeof(int), st);
+    if (e == cudaSuccess) e = list_n.alloc(sizeof(unsigned int), st);
     if (e == cudaSuccess) e = chunks.alloc(nchunks * sizeof(int), st);
     if (e == cudaSuccess) e = total.alloc(sizeof(int), st);
     if (e != cudaSuccess) return status_of(e);
-    int rc = components_device(binary_dev, shape, parent.as<int>(), size.as<int>(), st);
+    int rc = components_device(binary_dev, shape, parent.as<int>(), size.as<int>(), first.as<int>(), list.as<int>(), list_n.as<unsigned int>(), st);
     if (rc != VRG_OK) return rc;
-    k_cc_chunk_roots<<<GRID, 256, 0, st>>>(parent.as<int>(), n, chunks.as<int>());
+    cudaMemsetAsync(chunks.p, 0, nchunks * sizeof(int), st);
+    k_cc_chunk_roots<<<GRID, 256, 0, st>>>(parent.as<int>(), first.as<int>(), list.as<int>(), list_n.as<unsigned int>(), chunks.as<int>(), CHUNK);
     k_cc_scan_chunks<<<1, 1024, 0, st>>>(chunks.as<int>(), nchunks, total.as<int>());
     int K = 0;
     e = cudaMemcpyAsync(&K, total.p, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = bylabel.alloc((size_t)K * sizeof(int), st);
     if (e != cudaSuccess) return status_of(e);
-    k_cc_number_roots<<<GRID, 256, 0, st>>>(parent.as<int>(), n, chunks.as<int>(), size.as<int>(), bylabel.as<int>());
-    k_cc_labels<<<GRID, 256, 0, st>>>(parent.as<int>(), size.as<int>(), n, labels_dev);
+    k_cc_number_roots<<<GRID, 256, 0, st>>>(binary_dev, parent.as<int>(), first.as<int>(), n, chunks.as<int>(), total.as<int>(), size.as<int>(),
+                                            bylabel.as<int>());
+    k_cc_labels<<<GRID, 256, 0, st>>>(binary_dev, parent.as<int>(), size.as<int>(), n, labels_dev);
     e = cudaGetLastError();
     if (e == cudaSuccess && sizes_out && sizes_cap > 0 && K > 0) {
         std::vector<int> tmp((size_t)std::min<int64_t>(K, sizes_cap));
@@ -375,7 +463,7 @@ extern "C" int vrg_vessel_mask_device(int device, const double *vesselness_dev, 
     vrg_scratch::pool_setup(device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const long long n = (long long)shape[0] * shape[1] * shape[2];
-    DevBuf sq, partial, parent, size, counts, binary;
+    DevBuf sq, partial, parent, size, counts, binary, list, list_n;
     cudaError_t e = sq.alloc(n * sizeof(int), st);
     if (e == cudaSuccess) e = partial.alloc(2 * GRID * sizeof(double), st);
     if (e == cudaSuccess) e = counts.alloc(2 * sizeof(unsigned long long), st);
@@ -399,11 +487,14 @@ extern "C" int vrg_vessel_mask_device(int device, const double *vesselness_dev, 
     sq.release();  // stream-ordered: the block is reusable once k_rule has run
     e = parent.alloc(n * sizeof(int), st);
     if (e == cudaSuccess) e = size.alloc(n * sizeof(int), st);
+    if (e == cudaSuccess) e = list.alloc(n * sizeof(int), st);
+    if (e == cudaSuccess) e = list_n.alloc(sizeof(unsigned int), st);
     if (e != cudaSuccess) return status_of(e);
-    rc = components_device(binary.as<uint8_t>(), shape, parent.as<int>(), size.as<int>(), st);
+    rc = components_device(binary.as<uint8_t>(), shape, parent.as<int>(), size.as<int>(), nullptr, list.as<int>(), list_n.as<unsigned int>(), st);
     if (rc != VRG_OK) return rc;
     cudaMemsetAsync(counts.p, 0, 2 * sizeof(unsigned long long), st);
-    k_cc_filter<<<GRID, 256, 0, st>>>(parent.as<int>(), size.as<int>(), n, min_size, mask_out_dev, counts.as<unsigned long long>());
+    k_cc_filter<<<GRID, 256, 0, st>>>(binary.as<uint8_t>(), parent.as<int>(), size.as<int>(), n, min_size, mask_out_dev,
+                                      counts.as<unsigned long long>());
     unsigned long long hc[2] = {0, 0};
     e = cudaMemcpyAsync(hc, counts.p, sizeof hc, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
