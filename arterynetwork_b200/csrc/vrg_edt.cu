@@ -372,6 +372,15 @@ int bad_args(const char *what) {
 
 }  // namespace
 
+// shared with vrg_mask.cu: the x pass alone -- uint16 distance to the nearest zero voxel of the same row at every FOREGROUND
+// voxel (0xFFFF: none in this row) and the packed foreground bits, [Z*Y][ceil(X/32)] words
+int vrg_edt_rows_device_internal(const uint8_t *d_mask, const int64_t *shape, uint16_t *d1, uint32_t *bits, cudaStream_t stream) {
+    const long long Z = shape[0], Y = shape[1], X = shape[2];
+    const int XW = (int)((X + 31) / 32);
+    k_edt_rows<<<148 * 8, 256, (size_t)8 * 3 * XW * sizeof(uint32_t), stream>>>(d_mask, d1, bits, Z * Y, (int)X, XW);
+    return cudaGetLastError() == cudaSuccess ? VRG_OK : VRG_ERR_CUDA;
+}
+
 // shared with vrg_mask.cu: squared EDT of a device mask into a device int32 volume
 int vrg_edt_squared_device_internal(const uint8_t *d_mask, const int64_t *shape, int *sq_out, cudaStream_t stream) {
     return edt_squared_device(d_mask, shape, sq_out, stream);

@@ -23,6 +23,7 @@
 #include <vector>
 
 int vrg_edt_squared_device_internal(const uint8_t *d_mask, const int64_t *shape, int *sq_out, cudaStream_t stream);
+int vrg_edt_rows_device_internal(const uint8_t *d_mask, const int64_t *shape, uint16_t *d1, uint32_t *bits, cudaStream_t stream);
 void vrg_set_error_internal(const char *msg);  // vrg_b200.cu: text behind vrg_last_error()
 
 namespace {
@@ -60,6 +61,170 @@ __global__ void __launch_bounds__(256) k_rule(const double *__restrict__ v, cons
         const bool near_edge = sqrt((double)edt_sq[p]) <= edge_distance;
         const bool zeroed = (near_edge && x <= t_edge) || x <= t_all;
         out[p] = (!zeroed && x != 0.0) ? 1 : 0;
+    }
+}
+
+// The same rule without a distance transform of the whole brain.  The distance to the brain boundary enters the rule only at
+// voxels whose vesselness lies in (t_all, t_edge] (below, the voxel is zeroed anyway; above, it is kept anyway): bright vessel
+// voxels, a fraction of a per cent of the volume.  k_rule_classify settles every other voxel and lists those; k_rule_near
+// answers "is a non-brain voxel within edge_distance?" for each listed voxel exactly, one warp per voxel, from the packed
+// bits of the brain mask: min over the rows (dz, dy) within reach of dz^2 + dy^2 + (distance to the nearest zero of that row
+// within reach)^2 -- the separable transform restricted to the window that can matter.
+__global__ void __launch_bounds__(256) k_rule_classify(const double *__restrict__ v, long long n, double t_edge, double t_all,
+                                                       uint8_t *__restrict__ out, int *__restrict__ cand, unsigned int *__restrict__ cand_n) {
+    const int lane = threadIdx.x & 31;
+    const long long ngroups = (n + 3) / 4, nround = (ngroups + 31) / 32 * 32;
+    const bool aligned = (((uintptr_t)v) & 15) == 0 && (((uintptr_t)out) & 3) == 0;
+    for (long long g = (long long)blockIdx.x * 256 + threadIdx.x; g < nround; g += (long long)gridDim.x * 256) {
+        const long long p0 = g * 4;
+        double x[4] = {0.0, 0.0, 0.0, 0.0};
+        if (g < ngroups) {
+            if (aligned && p0 + 3 < n) {
+                const double2 a = *(const double2 *)(v + p0), b = *(const double2 *)(v + p0 + 2);
+                x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+            } else {
+                for (int k = 0; k < 4; ++k)
+                    if (p0 + k < n) x[k] = v[p0 + k];
+            }
+        }
+        uint32_t o = 0u;
+        unsigned c = 0u;  // bit k: voxel p0 + k is a candidate
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool settled = x[k] <= t_all || x[k] > t_edge || x[k] == 0.0;  // padding (0.0) is settled
+            o |= (uint32_t)(x[k] > t_edge && x[k] != 0.0) << (8 * k);            // candidates start at 0
+            c |= (unsigned)(!settled) << k;
+        }
+        if (g < ngroups) {
+            if (aligned && p0 + 3 < n) *(uint32_t *)(out + p0) = o;
+            else
+                for (int k = 0; k < 4; ++k)
+                    if (p0 + k < n) out[p0 + k] = (uint8_t)((o >> (8 * k)) & 1u);
+        }
+        if (__any_sync(FULLMASK, c != 0u)) {  // rare: append the candidates of this warp
+            const int mine = __popc(c);
+            int incl = mine;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int t = __shfl_up_sync(FULLMASK, incl, s);
+                if (lane >= s) incl += t;
+            }
+            unsigned int slot = 0;
+            if (lane == 31) slot = atomicAdd(cand_n, (unsigned int)incl);
+            slot = __shfl_sync(FULLMASK, slot, 31) + (unsigned int)(incl - mine);
+            for (int k = 0; k < 4; ++k)
+                if (c & (1u << k)) cand[slot++] = (int)(p0 + k);
+        }
+    }
+}
+// packed foreground bits of a uint8 volume, [rows][XW] words (bits beyond the row end are 0)
+__global__ void __launch_bounds__(256) k_pack_bits(const uint8_t *__restrict__ mask, uint32_t *__restrict__ bits, long long nrows, int X, int XW) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * 8;
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+        const uint8_t *row = mask + r * X;
+        if ((X & 3) == 0 && (((uintptr_t)row) & 3) == 0) {  // 128 voxels per step: four bytes per lane, eight lanes per word
+            for (int w0 = 0; w0 < XW; w0 += 4) {
+                const int x = 32 * w0 + 4 * lane;
+                uint32_t nib = 0u;
+                if (x < X) {
+                    const uint32_t v = *(const uint32_t *)(row + x);
+                    const uint32_t nz = (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+                    nib = ((nz >> 7) & 1u) | ((nz >> 14) & 2u) | ((nz >> 21) & 4u) | ((nz >> 28) & 8u);
+                }
+                uint32_t word = nib << (4 * (lane & 7));
+                word |= __shfl_xor_sync(FULLMASK, word, 1);
+                word |= __shfl_xor_sync(FULLMASK, word, 2);
+                word |= __shfl_xor_sync(FULLMASK, word, 4);
+                const int w = w0 + (lane >> 3);
+                if ((lane & 7) == 0 && w < XW) bits[r * XW + w] = word;
+            }
+        } else {
+            for (int w = 0; w < XW; ++w) {
+                const int x = 32 * w + lane;
+                const uint32_t word = __ballot_sync(FULLMASK, x < X && row[x] != 0);
+                if (lane == 0) bits[r * XW + w] = word;
+            }
+        }
+    }
+}
+// "a non-brain voxel lies in this block" for blocks of 8 planes x 8 rows x 32 voxels, one bit per x: a listed voxel whose
+// surrounding blocks hold none is settled after one word per lane (the summary of a whole volume is a megabyte, L2-resident)
+__global__ void __launch_bounds__(256) k_zero_summary(const uint32_t *__restrict__ bits, uint32_t *__restrict__ sum, int Z, int Y, int X, int XW) {
+    const int nyb = (Y + 7) / 8, nzb = (Z + 7) / 8;
+    const long long total = (long long)nzb * nyb * XW;
+    const uint32_t tail = (X & 31) ? ((1u << (X & 31)) - 1u) : 0xFFFFFFFFu;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int w = (int)(i % XW), yb = (int)((i / XW) % nyb), zb = (int)(i / ((long long)XW * nyb));
+        uint32_t acc = 0u;
+        for (int z = 8 * zb; z < min(Z, 8 * zb + 8); ++z)
+            for (int y = 8 * yb; y < min(Y, 8 * yb + 8); ++y) acc |= ~bits[((long long)z * Y + y) * XW + w];
+        sum[i] = w == XW - 1 ? acc & tail : acc;
+    }
+}
+// one warp per listed voxel, one lane per row (dz, dy) of the (2W+1)^2 rows within reach: the nearest non-brain voxel of the row
+// inside [x - W, x + W] comes from one to three words of packed bits
+__global__ void __launch_bounds__(256) k_rule_near(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ sum,
+                                                   const int *__restrict__ cand, const unsigned int *__restrict__ cand_n, int Z, int Y, int X,
+                                                   int XW, double edge_distance, int W, uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long m = *cand_n, nwarps = (long long)gridDim.x * 8;
+    const int side = 2 * W + 1, nrows = side * side;
+    for (long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); i < m; i += nwarps) {
+        const int p = cand[i];
+        const int x = p % X, y = (p / X) % Y, z = p / (X * Y);
+        const int xlo = max(0, x - W), xhi = min(X - 1, x + W);
+        {   // coarse: any non-brain voxel in the blocks that cover the box?  (deep inside the brain: none, and that is the answer)
+            const int nyb = (Y + 7) / 8;
+            const int zb0 = max(0, z - W) >> 3, zb1 = min(Z - 1, z + W) >> 3, yb0 = max(0, y - W) >> 3, yb1 = min(Y - 1, y + W) >> 3;
+            const int w0 = xlo >> 5, nw = (xhi >> 5) - w0 + 1, ny = yb1 - yb0 + 1, combos = (zb1 - zb0 + 1) * ny * nw;
+            bool some = false;
+            for (int c0 = 0; c0 < combos && !some; c0 += 32) {
+                const int c = c0 + lane;
+                bool hit = false;
+                if (c < combos) {
+                    const int w = w0 + c % nw, yb = yb0 + (c / nw) % ny, zb = zb0 + c / (nw * ny);
+                    const int b0 = max(xlo - 32 * w, 0), b1 = min(xhi - 32 * w, 31);
+                    const uint32_t win = (b1 == 31 ? 0xFFFFFFFFu : ((2u << b1) - 1u)) & ~((1u << b0) - 1u);
+                    hit = (sum[((long long)zb * nyb + yb) * XW + w] & win) != 0u;
+                }
+                some = __any_sync(FULLMASK, hit);
+            }
+            if (!some) {
+                if (lane == 0) out[p] = 1;
+                continue;
+            }
+        }
+        bool near = false;
+        for (int r0 = 0; r0 < nrows && !near; r0 += 32) {
+            const int r = r0 + lane;
+            bool hit = false;
+            if (r < nrows) {
+                const int dz = r / side - W, dy = r % side - W;
+                const int zz = z + dz, yy = y + dy;
+                if (zz >= 0 && zz < Z && yy >= 0 && yy < Y) {
+                    const uint32_t *rw = bits + ((long long)zz * Y + yy) * XW;
+                    int best = 1 << 20;  // |dx| to the nearest zero voxel of this row within the window
+                    for (int w = xlo >> 5; w <= (xhi >> 5); ++w) {
+                        const int b0 = max(xlo - 32 * w, 0), b1 = min(xhi - 32 * w, 31);  // window bits of this word
+                        const uint32_t win = (b1 == 31 ? 0xFFFFFFFFu : ((2u << b1) - 1u)) & ~((1u << b0) - 1u);
+                        const uint32_t zw = ~rw[w] & win;
+                        if (!zw) continue;
+                        const int xb = x - 32 * w;  // position of x relative to this word (may lie outside 0..31)
+                        const uint32_t below = xb >= 31 ? zw : (xb < 0 ? 0u : zw & ((2u << xb) - 1u));
+                        const uint32_t above = xb <= 0 ? zw : (xb > 31 ? 0u : zw & ~((1u << xb) - 1u));
+                        if (below) best = min(best, xb - (31 - __clz(below)));
+                        if (above) best = min(best, (__ffs(above) - 1) - xb);
+                    }
+                    if (best < (1 << 20)) {
+                        const long long d2 = (long long)dz * dz + (long long)dy * dy + (long long)best * best;
+                        hit = sqrt((double)d2) <= edge_distance;  // the reference compares the float64 distance
+                    }
+                }
+            }
+            near = __any_sync(FULLMASK, hit);
+        }
+        if (lane == 0 && !near) out[p] = 1;
     }
 }
 
@@ -464,8 +629,7 @@ extern "C" int vrg_vessel_mask_device(int device, const double *vesselness_dev, 
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const long long n = (long long)shape[0] * shape[1] * shape[2];
     DevBuf sq, partial, parent, size, counts, binary, list, list_n;
-    cudaError_t e = sq.alloc(n * sizeof(int), st);
-    if (e == cudaSuccess) e = partial.alloc(2 * GRID * sizeof(double), st);
+    cudaError_t e = partial.alloc(2 * GRID * sizeof(double), st);
     if (e == cudaSuccess) e = counts.alloc(2 * sizeof(unsigned long long), st);
     if (e == cudaSuccess) e = binary.alloc(n, st);
     if (e != cudaSuccess) return status_of(e);
@@ -480,11 +644,32 @@ extern "C" int vrg_vessel_mask_device(int device, const double *vesselness_dev, 
     if (!std::isfinite(lo) || !std::isfinite(hi)) { vrg_set_error_internal("vesselness volume holds NaN or Inf"); return VRG_ERR_NONFINITE; }
     const double t_edge = lo + edge_fraction * (hi - lo), t_all = lo + fraction * (hi - lo);  // GVV:189,191, same expression
     if (thresholds_out) { thresholds_out[0] = t_edge; thresholds_out[1] = t_all; }
-    // distance to the brain-mask boundary, GVV:183 (squared, exact)
-    int rc = vrg_edt_squared_device_internal(brain_mask_dev, shape, sq.as<int>(), st);
-    if (rc != VRG_OK) return rc;
-    k_rule<<<GRID, 256, 0, st>>>(vesselness_dev, sq.as<int>(), n, edge_distance, t_edge, t_all, binary.as<uint8_t>());
-    sq.release();  // stream-ordered: the block is reusable once k_rule has run
+    int rc = VRG_OK;
+    if (edge_distance >= 0.0 && edge_distance <= 40.0) {
+        // the distance to the brain-mask boundary (GVV:183) only where the rule can depend on it: see k_rule_near
+        const long long Z = shape[0], Y = shape[1], X = shape[2];
+        const int XW = (int)((X + 31) / 32);
+        DevBuf bits, zsum, cand, cand_n;
+        e = bits.alloc((size_t)Z * Y * XW * sizeof(uint32_t), st);
+        if (e == cudaSuccess) e = zsum.alloc((size_t)((Z + 7) / 8) * ((Y + 7) / 8) * XW * sizeof(uint32_t), st);
+        if (e == cudaSuccess) e = cand.alloc(n * sizeof(int), st);
+        if (e == cudaSuccess) e = cand_n.alloc(sizeof(unsigned int), st);
+        if (e != cudaSuccess) return status_of(e);
+        k_pack_bits<<<GRID, 256, 0, st>>>(brain_mask_dev, bits.as<uint32_t>(), Z * Y, (int)X, XW);
+        k_zero_summary<<<GRID, 256, 0, st>>>(bits.as<uint32_t>(), zsum.as<uint32_t>(), (int)Z, (int)Y, (int)X, XW);
+        cudaMemsetAsync(cand_n.p, 0, sizeof(unsigned int), st);
+        k_rule_classify<<<GRID, 256, 0, st>>>(vesselness_dev, n, t_edge, t_all, binary.as<uint8_t>(), cand.as<int>(), cand_n.as<unsigned int>());
+        k_rule_near<<<GRID, 256, 0, st>>>(bits.as<uint32_t>(), zsum.as<uint32_t>(), cand.as<int>(), cand_n.as<unsigned int>(), (int)Z, (int)Y, (int)X, XW,
+                                          edge_distance, (int)edge_distance, binary.as<uint8_t>());
+    } else {
+        // distance to the brain-mask boundary, GVV:183 (squared, exact), over the whole volume
+        e = sq.alloc(n * sizeof(int), st);
+        if (e != cudaSuccess) return status_of(e);
+        rc = vrg_edt_squared_device_internal(brain_mask_dev, shape, sq.as<int>(), st);
+        if (rc != VRG_OK) return rc;
+        k_rule<<<GRID, 256, 0, st>>>(vesselness_dev, sq.as<int>(), n, edge_distance, t_edge, t_all, binary.as<uint8_t>());
+        sq.release();  // stream-ordered: the block is reusable once k_rule has run
+    }
     e = parent.alloc(n * sizeof(int), st);
     if (e == cudaSuccess) e = size.alloc(n * sizeof(int), st);
     if (e == cudaSuccess) e = list.alloc(n * sizeof(int), st);
