@@ -497,6 +497,10 @@ static int launch_init_hist(vrg_handle *h) {
         CK(cudaFuncSetAttribute(k_init_hist_tma<MODE_INDEX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CK(cudaFuncSetAttribute(k_init_hist_tma<MODE_F64_BAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CK(cudaFuncSetAttribute(k_init_hist_tma<MODE_F64_BAND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_shared<MODE_INDEX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_shared<MODE_INDEX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_shared<MODE_F64_BAND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(k_init_hist_shared<MODE_F64_BAND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         h->hist_attr_set = true;
     }
     // TMA-staged variant: the level source streams through a per-warp ring (16-byte aligned row segments only)
@@ -504,6 +508,19 @@ static int launch_init_hist(vrg_handle *h) {
     const uintptr_t src_base = h->cfg.intensity_mode == VRG_INTENSITY_INDEX ? (uintptr_t)p.index : (uintptr_t)p.data;
     if (((size_t)p.X * elem) % 16 == 0 && (src_base & 15) == 0 && !h->force_ldg) {
         const size_t stage_bytes = ((size_t)p.segw * 32 * elem + 127) & ~(size_t)127;
+        {   // one shared-memory histogram per warp (atomics): many warps per SM
+            const size_t per_w = (size_t)((p.L + 1) & ~1) * sizeof(unsigned int);
+            const size_t per = per_w + HIST_STAGES * stage_bytes + HIST_STAGES * 8;
+            // the kernel evaluates whole batches of 10 words: on a short row the last batch reads (and ignores) up to 2560 bytes
+            // behind its stage, which must still be shared memory of this block
+            const size_t slack = 10 * 32 * sizeof(double);
+            const int hw = (int)std::min<size_t>(16, (227 * 1024 - 256 - slack) / per);
+            if (hw >= 8 && getenv("VRG_HIST_PRIVATE") == nullptr) {
+                const size_t smem = (((size_t)hw * HIST_STAGES * 8 + 127) & ~(size_t)127) + (size_t)hw * HIST_STAGES * stage_bytes + hw * per_w + slack;
+                LAUNCH_ML(k_init_hist_shared, h->sms, hw * 32, smem, p, hw, (int)stage_bytes);
+                return VRG_OK;
+            }
+        }
         const size_t per = per_warp + HIST_STAGES * stage_bytes + HIST_STAGES * 8;
         const int hw = (int)std::min<size_t>(16, (227 * 1024 - 256) / per);
         if (hw >= 3) {

@@ -296,21 +296,46 @@ __device__ __forceinline__ void absorb(const SP &p, long long v) {
     }
 }
 
-// one flipped point, one warp: VRG:163-228
-__device__ void process_flip(const SP &p, long long idx, int lane) {
+// one flipped point, one warp: VRG:163-228.  The 5x5x5 labels around the point are fetched once into shared memory (`lab`, 128
+// bytes per warp; 0xFF = outside the volume): nothing else writes them while this point is processed (points processed side by
+// side are further than 3 apart), so the 26 neighbours are walked on the cached copy -- their order matters (a neighbour
+// promoted at its step is seen by the tests of the later ones) -- and each lane then writes its own neighbour's new state back.
+__device__ void process_flip(const SP &p, long long idx, int lane, uint8_t *lab) {
     const long long vox = p.fvox[idx];
     const Pos c = pos_of(p, vox);
-    const bool nlane = lane < 27 && lane != 13;
-    absorb(p, nlane ? nbr(p, c, lane) : -1);  // VRG:165-168
+    long long g[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int i = lane + 32 * t;
+        g[t] = -1;
+        if (i < 125) {
+            const int z = c.z + i / 25 - 2, y = c.y + (i / 5) % 5 - 2, x = c.x + i % 5 - 2;
+            if (z >= 0 && z < p.Z && y >= 0 && y < p.Y && x >= 0 && x < p.X) g[t] = ((long long)z * p.Y + y) * p.X + x;
+            lab[i] = g[t] >= 0 ? ld8(p.vm + g[t]) : (uint8_t)0xFF;
+        }
+    }
     __syncwarp();
-    const uint8_t lab = ld8(p.vm + vox);
-    if (lab != 1 && lab != 2) {  // in no band any more at its turn
+    const uint8_t lab0 = lab[62];
+    const bool exec = lab0 == 1 || lab0 == 2;
+    // 4 -> 3: the 3x3x3 of every listed point (VRG:165-168), the 5x5x5 of a processed one (VRG:177-179,205-208: the 3x3x3 of
+    // each of its in-bounds neighbours).  No label test below tells 3 from 4, so all of it can come first.
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int i = lane + 32 * t;
+        if (i < 125 && g[t] >= 0 && lab[i] == 4) {
+            const bool inner = abs(i / 25 - 2) <= 1 && abs((i / 5) % 5 - 2) <= 1 && abs(i % 5 - 2) <= 1;
+            if (exec || inner) { absorb(p, g[t]); lab[i] = 3; }
+        }
+    }
+    __syncwarp();
+    if (!exec) {  // in no band any more at its turn
         if (lane == 0) { atomicAdd((u64 *)&p.cnt[C_SKIPPED], 1ull); p.rank[vox] = 0u; }
         return;
     }
-    const bool removal = lab == 1;
+    const bool removal = lab0 == 1;
     if (lane == 0) {
         const int b = p.lev[vox];
+        lab[62] = removal ? 2 : 1;
         p.vm[vox] = removal ? 2 : 1;  // VRG:174,202: no look at the neighbours
         p.key[vox] = order_key(p.iter, idx, 0);
         if (removal) {
@@ -326,23 +351,32 @@ __device__ void process_flip(const SP &p, long long idx, int lane) {
     // the labels a neighbour can move between: removal: 2 -> 3 unless a 1 is near, 0 -> 1;  addition: 1 -> 0 unless a 2 is near, 3 -> 2
     const uint8_t settle_from = removal ? 2 : 1, needs = removal ? 1 : 2, settle_to = removal ? 3 : 0;
     const uint8_t promote_from = removal ? 0 : 3, promote_to = removal ? 1 : 2;
+    const bool nlane = lane < 27 && lane != 13;
+    const int myoff = (lane / 9 - 1) * 25 + ((lane / 3) % 3 - 1) * 5 + (lane % 3 - 1);  // neighbour `lane` in the 5^3 cache
+    int action = 0;  // what happened to neighbour `lane`: 1 settled, 2 promoted
     for (int o = 0; o < 27; ++o) {
         if (o == 13) continue;
-        const long long q = nbr(p, c, o);
-        if (q < 0) continue;  // uniform across the warp
-        const Pos cq = pos_of(p, q);
-        const long long q2 = nlane ? nbr(p, cq, lane) : -1;
-        absorb(p, q2);  // VRG:177-179,205-208
-        const uint8_t lq = ld8(p.vm + q);
+        const int qi = 62 + (o / 9 - 1) * 25 + ((o / 3) % 3 - 1) * 5 + (o % 3 - 1);
+        const uint8_t lq = lab[qi];
         if (lq == settle_from) {  // VRG:183-190,218-227
-            const unsigned near = __ballot_sync(0xFFFFFFFFu, q2 >= 0 && ld8(p.vm + q2) == needs);
-            if (!near && lane == 0) { p.vm[q] = settle_to; p.pin[q] = 0.0; p.pout[q] = 0.0; }
+            const unsigned near = __ballot_sync(0xFFFFFFFFu, nlane && lab[qi + myoff] == needs);
+            if (!near) {
+                if (lane == o) action = 1;
+                if (lane == 0) lab[qi] = settle_to;
+            }
         } else if (lq == promote_from) {  // VRG:193-196,209-212
-            if (lane == 0) { p.vm[q] = promote_to; p.newf[q] = 1; p.key[q] = order_key(p.iter, idx, o + 1); }
+            if (lane == o) action = 2;
+            if (lane == 0) lab[qi] = promote_to;
         }
         __syncwarp();
     }
+    if (action) {
+        const long long q = nbr(p, c, lane);
+        if (action == 1) { p.vm[q] = settle_to; p.pin[q] = 0.0; p.pout[q] = 0.0; }
+        else { p.vm[q] = promote_to; p.newf[q] = 1; p.key[q] = order_key(p.iter, idx, lane + 1); }
+    }
     if (lane == 0) p.rank[vox] = 0u;
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(BLK) k_wave(SP p, long long nf) {
@@ -351,6 +385,7 @@ __global__ void __launch_bounds__(BLK) k_wave(SP p, long long nf) {
     const int lane = threadIdx.x & 31;
     const long long gwarp = gtid >> 5, nwarps = gsize >> 5;
     volatile long long *cnt = p.cnt;
+    __shared__ uint8_t s_lab[BLK / 32][128];
     long long n_act = nf;
     int round = 0;
     while (n_act > 0) {
@@ -390,7 +425,7 @@ __global__ void __launch_bounds__(BLK) k_wave(SP p, long long nf) {
         grid.sync();
         const long long n_ready = cnt[C_READY0 + cur], n_next = cnt[C_ACT0 + (cur ^ 1)];
         // phase B: they are pairwise further than 3 apart: process them side by side, one warp each
-        for (long long j = gwarp; j < n_ready; j += nwarps) process_flip(p, __ldcg(p.ready + j), lane);
+        for (long long j = gwarp; j < n_ready; j += nwarps) process_flip(p, __ldcg(p.ready + j), lane, s_lab[threadIdx.x >> 5]);
         if (gtid == 0) { cnt[C_READY0 + (cur ^ 1)] = 0; cnt[C_ACT0 + cur] = 0; cnt[C_ROUNDS] += 1; }
         grid.sync();
         n_act = n_next;
