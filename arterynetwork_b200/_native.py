@@ -74,6 +74,7 @@ _SIGS = {
     "vrg_enqueue_table": [vp],
     "vrg_p2p_connect_local": [ctypes.POINTER(vp), ctypes.c_int],
     "vrg_labels_hash": [vp, ctypes.POINTER(ctypes.c_uint64)],
+    "vrg_count_nonzero": [vp, ctypes.POINTER(i64)],
     "vrg_download_segmented_map_i64": [vp, vp],
     "vrg_profile": [vp, ctypes.c_int],
     "vrg_get_profile": [vp, vp, vp],

@@ -1618,6 +1618,15 @@ __global__ void __launch_bounds__(BLOCK) k_hash_labels(const uint8_t *__restrict
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// np.count_nonzero(dataArray) of the own planes (the second printed line, VRG:95): -0.0 counts as zero, NaN as non-zero
+__global__ void __launch_bounds__(BLOCK) k_count_nonzero(const double *__restrict__ data, long long n, unsigned long long *out) {
+    unsigned long long acc = 0;
+    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) acc += data[i] != 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 __global__ void __launch_bounds__(BLOCK) k_expand_i64(const uint8_t *__restrict__ src, long long *__restrict__ dst, long long n) {
     for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (long long)gridDim.x * BLOCK) dst[i] = src[i];
 }

@@ -211,6 +211,12 @@ class VRGEngine:
         nat.check(self.lib.vrg_download_segmented_map_i64(self._h, out.ctypes.data))
         return out
 
+    def count_nonzero(self) -> int:
+        """np.count_nonzero of the own planes of the intensity volume, counted on the device (VRG:95)."""
+        n = nat.i64(0)
+        nat.check(self.lib.vrg_count_nonzero(self._h, ctypes.byref(n)))
+        return int(n.value)
+
     def labels_hash(self) -> int:
         """Position-sensitive 64-bit hash of the own planes' labels; slab hashes add up (mod 2^64) to the whole volume's."""
         v = ctypes.c_uint64(0)
@@ -220,13 +226,19 @@ class VRGEngine:
     def labels_device(self, dev_ptr: int):
         nat.check(self.lib.vrg_labels_device(self._h, nat.vp(dev_ptr)))
 
-    def segmented(self) -> np.ndarray:
+    def segmented(self, at_most=None) -> np.ndarray:
+        """Rows (z, y, x) of the segmented voxels of the own planes, C order.  ``at_most``: an upper bound of their number
+        (e.g. the run's ``n_in``) saves the counting pass over the bit-plane."""
         n = nat.i64(0)
-        nat.check(self.lib.vrg_download_segmented(self._h, None, 0, ctypes.byref(n)))
-        out = np.empty((n.value, 3), dtype=np.int64)
-        if n.value:
-            nat.check(self.lib.vrg_download_segmented(self._h, out.ctypes.data, n.value, ctypes.byref(n)))
-        return out
+        if at_most is None:
+            nat.check(self.lib.vrg_download_segmented(self._h, None, 0, ctypes.byref(n)))
+            at_most = n.value
+        out = np.empty((int(at_most), 3), dtype=np.int64)
+        if at_most:
+            nat.check(self.lib.vrg_download_segmented(self._h, out.ctypes.data, int(at_most), ctypes.byref(n)))
+            if n.value > at_most:  # the bound was wrong: once more with the count
+                return self.segmented()
+        return out[: n.value]
 
     def trace(self) -> np.ndarray:
         cap = int(self.cfg.iter_max) + 2

@@ -45,6 +45,7 @@ Differences from the reference, all deliberate (DESIGN.md "Boundary"):
 from __future__ import annotations
 
 import itertools
+import time
 import warnings
 from concurrent.futures import ThreadPoolExecutor
 
@@ -60,7 +61,7 @@ DEVICE = 0
 DEVICES = None  # None: DEVICE only; "all" or a list of CUDA ordinals: z-slabs over those GPUs, in this process
 INTENSITY = "index"  # how the sweep reads intensities: f64_dense | f64_band | index | continuous
 CONTINUOUS_MAX_VOXELS = 1 << 24  # fall back to the brute-force Parzen mode (continuous data) up to this volume size
-HOST_THREADS = 8  # host-side conversions (label dtype, int64 segmentedMap) run in z-chunks on this many threads
+HOST_THREADS = max(1, min(16, (__import__("os").cpu_count() or 8)))  # host-side conversions (label dtype, int64 segmentedMap) run in z-chunks on this many threads
 LIST_ORDER = False  # True: bug-compatible list-order semantics, see the module docstring
 LAST_RUN = {}  # result of the most recent call: iterations, exit_reason, n_in, ..., q_* order-dependence counters
 
@@ -184,8 +185,11 @@ class _Run:
     def segmented_map_i64_into(self, out3):
         self._each(lambda e: e.segmented_map_i64(out3[e.z_begin:e.z_end]))
 
-    def segmented(self):
-        return np.concatenate(self._each(lambda e: e.segmented()))
+    def segmented(self, at_most=None):
+        return np.concatenate(self._each(lambda e: e.segmented(at_most)))
+
+    def count_nonzero(self):
+        return sum(self._each(lambda e: e.count_nonzero()))
 
 
 def _warn_order_dependence(res):
@@ -198,8 +202,9 @@ def _warn_order_dependence(res):
                       VRGOrderDependenceWarning, stacklevel=3)
 
 
-def _finish_lines(res, segmented, data3):
-    nz = sum(_pool_map(lambda zz: int(np.count_nonzero(data3[zz[0]:zz[1]])), _chunks(data3.shape[0], HOST_THREADS)))
+def _finish_lines(res, segmented, data3, nz=None):
+    if nz is None:
+        nz = sum(_pool_map(lambda zz: int(np.count_nonzero(data3[zz[0]:zz[1]])), _chunks(data3.shape[0], HOST_THREADS)))
     if res["exit_reason"] == nat.EXIT_MAX_ITER:  # VRG:118-120
         print('Segmented points are: \n', segmented)
         print('Max iteration reached! Finished at iteration {}'.format(res["iterations"]))
@@ -243,23 +248,41 @@ def variationalRegionGrowing(dataArray, valueMap, H=2.25, maxSegmentSize=5000):
         raise ValueError("dataArray and valueMap must have the same shape")
     if LIST_ORDER:
         return _list_order_run(dataArray, valueMap, H, maxSegmentSize)
+    clock = [time.perf_counter()]
+    host_seconds = {}
+
+    def lap(name):  # where the wall time of a call goes: LAST_RUN["host_seconds"]
+        now = time.perf_counter()
+        host_seconds[name] = host_seconds.get(name, 0.0) + now - clock[0]
+        clock[0] = now
     data3, transposed = _as_zyx(dataArray)
     vm_view = valueMap.T if transposed else valueMap
     vm3 = vm_view.reshape(data3.shape)
     vm8 = _labels_u8(vm3)
+    lap("labels_to_uint8")
     direct = not transposed  # user arrays are C-ordered views of (Z, Y, X): results are written straight into them
     devices = _device_list()
-    segmentedMap = np.empty(dataArray.shape, dtype=np.int64)  # np.full(shape, 0), VRG:45
-    seg3 = segmentedMap.reshape(data3.shape) if direct else np.empty(data3.shape, dtype=np.int64)
-    lab3 = np.empty(data3.shape, dtype=np.uint8)
+    # The labels come back into the uint8 copy of the caller's map (or into the caller's map itself when that is uint8: it is
+    # updated in place anyway, VRG:137-228): pages that are already mapped, not 0.5 GB of fresh ones.
+    lab3 = vm8
+    nonzero = [None]
 
     def run(mode):
+        lap("allocate_outputs")
         with _Run(data3.shape, H, maxSegmentSize, mode, devices) as r:
+            lap("create_handles")
             r.upload(data3, vm8)
+            lap("upload")
             res = r.run()
+            lap("levels_init_iterations")
             r.labels_into(lab3)
-            r.segmented_map_i64_into(seg3)
-            return res, r.segmented()
+            lap("download_labels")
+            seg = r.segmented(res["n_in"])
+            lap("download_segmented_rows")
+            nonzero[0] = r.count_nonzero()  # np.count_nonzero(dataArray) of VRG:95, counted where the volume already is
+            lap("count_nonzero_on_device")
+        lap("destroy_handles")
+        return res, seg
 
     try:
         res, seg_zyx = run(INTENSITY)
@@ -270,19 +293,36 @@ def variationalRegionGrowing(dataArray, valueMap, H=2.25, maxSegmentSize=5000):
             raise
         res, seg_zyx = run("continuous")
     LAST_RUN = dict(res)
+    LAST_RUN["host_seconds"] = host_seconds
     # in place, VRG:137-228 (z-chunks on host threads: a uint8 -> int64 pass over the whole volume otherwise)
-    if direct and valueMap.flags.c_contiguous:
+    if lab3 is vm3:
+        pass  # the caller's own uint8 map was the download target
+    elif direct and valueMap.flags.c_contiguous:
         out3 = valueMap.reshape(data3.shape)
         _pool_map(lambda zz: out3.__setitem__(slice(zz[0], zz[1]), lab3[zz[0]:zz[1]]), _chunks(data3.shape[0], HOST_THREADS))
     else:
         lab_user = lab3.reshape(vm_view.shape)
         valueMap[...] = lab_user.T if transposed else lab_user
-    if direct:
-        segmented = seg_zyx[:, 3 - dataArray.ndim:]
-    else:
-        segmentedMap[...] = seg3.reshape(vm_view.shape).T
-        segmented = np.argwhere(segmentedMap == 1)  # C order of the user's axes
-    _finish_lines(res, segmented, data3)
+    lap("value_map_in_place")
+    segmented = seg_zyx[:, 3 - dataArray.ndim:]
+    if transposed:
+        segmented = segmented[:, ::-1]
+        segmented = np.ascontiguousarray(segmented[np.lexsort(segmented.T[::-1])])  # C order of the user's axes
+    # VRG:45-46 as the reference does it: a zero-filled int64 map with ones at the segmented voxels -- downloading the map as
+    # int64 was 4 GB and a second of single-threaded page faults at C3
+    segmentedMap = np.empty(dataArray.shape, dtype=np.int64)
+    flat_map = segmentedMap.reshape(-1)
+    n_all = flat_map.size  # zero-filled in parallel: first-touch page faults are what a fresh 4 GB array costs
+    _pool_map(lambda ab: flat_map[ab[0]:ab[1]].fill(0), [(n_all * i // HOST_THREADS, n_all * (i + 1) // HOST_THREADS) for i in range(HOST_THREADS)])
+    if len(segmented):
+        flat = segmented[:, 0].copy()
+        for ax in range(1, dataArray.ndim):
+            flat *= dataArray.shape[ax]
+            flat += segmented[:, ax]
+        flat_map[flat] = 1
+    lap("segmented_map_int64")
+    _finish_lines(res, segmented, data3, nonzero[0])
+    lap("print")
     _warn_order_dependence(res)
     return segmented, segmentedMap, valueMap
 

@@ -532,7 +532,8 @@ def dropin_e2e(ctx, shape, seed, devices, ref_labels=None, host=None):
             sweeps = mod.LAST_RUN["sweeps"]
             nvox = data.size
             entry = {"seconds": best, "Gvoxel_updates_per_s": nvox * sweeps / best / 1e9, "sweeps": sweeps,
-                     "stdout": buf.getvalue().strip().splitlines(), "n_gpus": len(devices)}
+                     "stdout": buf.getvalue().strip().splitlines(), "n_gpus": len(devices),
+                     "host_seconds_last_call": {k: round(x, 4) for k, x in mod.LAST_RUN.get("host_seconds", {}).items()}}
             if ref_labels is not None:
                 entry["labels_equal_oracle"] = bool(np.array_equal(v_out, ref_labels))
             out[mode] = entry

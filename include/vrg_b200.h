@@ -195,6 +195,8 @@ int vrg_labels_device(vrg_handle *h, uint8_t *value_map_dev_out); /* same, into 
  * splitmix64_finalizer((global linear voxel index << 3) | label) mod 2^64.  Additive over z-slabs: the per-rank hashes of a
  * multi-GPU run add up to the hash of the whole label volume (oracle/c_oracle.py computes the same number on the CPU). */
 int vrg_labels_hash(vrg_handle *h, uint64_t *hash_out);
+/* np.count_nonzero(dataArray) over the own planes, counted on the device (the reference's second printed line, VRG:95) */
+int vrg_count_nonzero(vrg_handle *h, int64_t *count_out);
 /* segmentedMap as the reference returns it (VRG:45-46: np.full(shape, 0) -> int64 0/1), own planes, straight into host memory */
 int vrg_download_segmented_map_i64(vrg_handle *h, int64_t *seg_out);
 /* segmented voxel coordinates (z,y,x) of own planes in C order; returns count via n (cap in rows) */
