@@ -125,7 +125,7 @@ def load(build_if_missing: bool = True):
     if not os.path.exists(_build.LIB):
         raise RuntimeError("vrg_b200: CUDA library %s is missing and cannot be built here (no nvcc); "
                            "there is no CPU fallback" % _build.LIB)
-    lib = ctypes.CDLL(_build.LIB)
+    lib = ctypes.CDLL(os.environ.get("VRG_B200_LIB") or _build.LIB)  # VRG_B200_LIB: an alternative build for A/B measurements
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args

@@ -68,6 +68,8 @@ struct vrg_handle {
     bool have_data = false, have_levels = false, inited = false, separate_gstats = false;
     int64_t launches = 0;
     int grid = 148 * 8;
+    bool slim_sweep = false;  // set while a pipelined batch is enqueued: the dense sweep runs in its 104-register variant
+    bool no_ahead = false;  // A/B switch VRG_NO_AHEAD: vrg_run looks at a batch's status before it queues the next one
     bool no_wide = false;  // A/B switch VRG_NO_WIDE: rows of 31 / 32 words stay two 16-word segments in the dense sweep
     bool dense_attr_set = false, force_ldg = false, hist_attr_set = false, attached = false;
     const uint8_t *vm_base = nullptr;  // valueMap as indexed by local plane (own buffer or attached)
@@ -192,6 +194,7 @@ int vrg_create(const vrg_config *cfg, vrg_handle **out) {
     h->grid = h->sms * 8;
     h->force_ldg = getenv("VRG_DENSE_LDG") != nullptr;  // A/B switch: plain loads instead of the TMA rings (sweep, init histogram)
     h->no_wide = getenv("VRG_NO_WIDE") != nullptr;
+    h->no_ahead = getenv("VRG_NO_AHEAD") != nullptr;
     h->graph_ok = getenv("VRG_NO_GRAPH") == nullptr;    // A/B switch: vrg_run stays on plain stream launches
     h->tail_ok = getenv("VRG_NO_FUSED_TAIL") == nullptr;  // A/B switch: the separate kernels behind the sweep
     if (const char *e = getenv("VRG_PIPELINE")) h->pipe_mode = atoi(e) != 0;  // A/B switch (default: pipelined on slabs only)
@@ -806,9 +809,18 @@ static int enqueue_sweep(vrg_handle *h) {
                 CK(cudaFuncSetAttribute(k_sweep_dense<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 CK(cudaFuncSetAttribute(k_sweep_dense<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 CK(cudaFuncSetAttribute(k_sweep_dense<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                CK(cudaFuncSetAttribute(k_sweep_dense_slim<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                CK(cudaFuncSetAttribute(k_sweep_dense_slim<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                CK(cudaFuncSetAttribute(k_sweep_dense_slim<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                CK(cudaFuncSetAttribute(k_sweep_dense_slim<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 h->dense_attr_set = true;
             }
-            if (wide && p.lattice) k_sweep_dense<true, true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+            if (h->slim_sweep) {  // pipelined run: leave room for the statistics / table kernels beside the sweep
+                if (wide && p.lattice) k_sweep_dense_slim<true, true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+                else if (wide) k_sweep_dense_slim<false, true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+                else if (p.lattice) k_sweep_dense_slim<true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+                else k_sweep_dense_slim<false><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
+            } else if (wide && p.lattice) k_sweep_dense<true, true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
             else if (wide) k_sweep_dense<false, true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
             else if (p.lattice) k_sweep_dense<true><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
             else k_sweep_dense<false><<<h->sms, DENSE_WARPS * 32, dsm, h->stream>>>(p);
@@ -1176,7 +1188,10 @@ static int enqueue_batch(vrg_handle *h, int n) {
             continue;
         }
         if (piped) {
-            if ((rc = enqueue_pipelined(h)) != VRG_OK) return rc;
+            h->slim_sweep = getenv("VRG_NO_SLIM") == nullptr;
+            rc = enqueue_pipelined(h);
+            h->slim_sweep = false;
+            if (rc != VRG_OK) return rc;
             continue;
         }
         if (fused) {  // the table of this sweep was computed by the previous tail (the first one: vrg_run)
@@ -1287,7 +1302,7 @@ int vrg_run(vrg_handle *h, vrg_result *res) {
         CK(cudaMemcpyAsync(h->h_poll + slot * C_WORDS, h->d_ctrl, C_WORDS * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaEventRecord(h->ev_poll[slot], h->stream));
         ++nbatch;
-        const bool ahead = use_graph && h->gexec != nullptr;
+        const bool ahead = use_graph && h->gexec != nullptr && !h->no_ahead;
         if (ahead && nbatch < 2) continue;  // nothing older to look at yet
         const int look = ahead ? (int)((nbatch - 2) & 1) : slot;
         CK(cudaEventSynchronize(h->ev_poll[look]));

@@ -515,8 +515,8 @@ constexpr int UNIT_RING = 8;  // the prefetcher is at most DENSE_STAGES + 1 rows
 // of this kernel's lanes idle; here one warp takes the whole row -- lane = word column, no halo lanes (nothing lies beyond
 // the row ends), one 8 KB stage per row, flags and front rows still per segment.
 constexpr int WIDE_STAGE_BYTES = 32 * 32 * 8;
-template <bool LATTICE, bool WIDE = false>
-__global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
+template <bool LATTICE, bool WIDE>
+__device__ __forceinline__ void sweep_dense_body(const Params &p) {
     constexpr int SB = WIDE ? WIDE_STAGE_BYTES : STAGE_BYTES;
     if (p.ctrl[C_STATUS] != RUNNING) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -603,6 +603,7 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
             st.template begin<WIDE>(p, czl, y, c0 + lane, lane);
             fresh = false;
         }
+#ifndef VRG_NO_NEXT_WINDOW
         if (y + 1 >= cy1) {  // last row of the unit: lane 0 announced the next one when it issued this row
             nu = myring[ctail & (UNIT_RING - 1)];
             if (nu < nunits) {
@@ -610,6 +611,7 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
                 nx.template begin<WIDE>(p, nzl, ny, (WIDE ? 0 : nsg * p.segw - 1) + lane, lane);
             }
         }
+#endif
         uint32_t s, inner, outer;
         st.template step<WIDE>(p, y, s, inner, outer, lane);
         const long long widx = (long long)czl * p.plane_words + (long long)y * p.WP + c0 + lane;
@@ -654,16 +656,37 @@ __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) {
         else store_flips(p, widx, ridx, was, f, st.active, own, lane);
         if (own) flips += __popc(f);
         if (++cy >= cy1) {  // on to the next unit of this warp's sequence: its window is under way
+#ifndef VRG_NO_NEXT_WINDOW
             ++ctail;
             cu = nu; czl = nzl; csg = nsg; cy = ny; cy1 = ny1;
             st = nx;
             c0 = WIDE ? 0 : csg * p.segw - 1;
             own = czl >= p.own_lo && czl < p.own_hi;
+#else
+            __syncwarp();
+            cu = myring[ctail++ & (UNIT_RING - 1)];
+            if (cu < nunits) {
+                decode(cu, czl, csg, cy, cy1);
+                c0 = WIDE ? 0 : csg * p.segw - 1;
+                own = czl >= p.own_lo && czl < p.own_hi;
+                st.template begin<WIDE>(p, czl, cy, c0 + lane, lane);
+            }
+#endif
         }
     }
     flips = warp_sum(flips);
     if (lane == 0 && flips) atomicAdd((unsigned long long *)&p.lstats[2 * p.L + ST_N_FLIPS], (unsigned long long)flips);
 }
+
+template <bool LATTICE, bool WIDE = false>
+__global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) { sweep_dense_body<LATTICE, WIDE>(p); }
+// The same sweep held to 104 registers per thread, for the pipelined run (vrg_tail.cuh): its statistics and table kernels have
+// to find room on the SMs this kernel's blocks occupy -- 14 warps x 112 registers leave 15360 of the 65536, not enough for a
+// 256-thread block of k_async_table (63 registers), which then ran BEHIND the sweep instead of beside it (8 GPUs, C3: 19.7 ms
+// per run; 17.5 ms with 128-thread blocks, which fit but take twice as long; 15.8 ms with this variant and 256 threads,
+// although the sweep itself is a few per cent slower: profiles/r2ak_*).
+template <bool LATTICE, bool WIDE = false>
+__global__ void __maxnreg__(104) k_sweep_dense_slim(Params p) { sweep_dense_body<LATTICE, WIDE>(p); }
 
 // Fallback of the dense sweep for odd X (row segments not 16-byte aligned): plain coalesced 8-byte loads.
 template <bool LATTICE>
