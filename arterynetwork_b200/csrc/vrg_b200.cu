@@ -56,6 +56,7 @@ struct vrg_handle {
     double *d_levels = nullptr, *d_pin = nullptr, *d_pout = nullptr, *d_kmat = nullptr;
     uint32_t *d_dbits = nullptr;
     long long *d_lstats = nullptr, *d_gstats = nullptr, *d_ctrl = nullptr, *d_trace = nullptr;
+    unsigned long long stage_seq = 0;       // chunks staged so far (buffer = parity)
     char *h_stage[2] = {nullptr, nullptr};  // pinned staging buffers of vrg_upload (pageable sources)
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     long long *h_ctrl = nullptr;  // pinned
@@ -357,10 +358,13 @@ static int staged_h2d(vrg_handle *h, void *dst, const void *src, size_t bytes) {
     }
     const int nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
     size_t off = 0;
-    for (int k = 0; off < bytes; ++k, off += CH) {
-        const int b = k & 1;
+    for (; off < bytes; off += CH) {
+        const int b = (int)(h->stage_seq & 1);
         const size_t len = std::min(CH, bytes - off);
-        if (k >= 2) CK(cudaEventSynchronize(h->ev_stage[b]));  // the copy that last used this buffer is done
+        // the copy that last used this buffer has to be done -- also one of an earlier call (the valueMap follows the intensities
+        // through the same two buffers)
+        if (h->stage_seq >= 2) CK(cudaEventSynchronize(h->ev_stage[b]));
+        ++h->stage_seq;
         const char *s0 = (const char *)src + off;
         char *d0 = (char *)h->h_stage[b];
         std::vector<std::thread> th;

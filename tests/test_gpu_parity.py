@@ -521,3 +521,27 @@ def test_pipelined_run_repeats_a_sweep_when_the_table_changes(mode, monkeypatch)
         assert o["iterations"] == ref["iterations"] and o["sweeps"] == ref["iterations"]
         assert np.array_equal(o["labels"], ref["labels"]) and np.array_equal(o["trace"], ref["trace"])
     assert b["redone_sweeps"] == 0
+
+
+def test_staged_upload_of_a_large_pageable_volume():
+    """vrg_upload stages pageable sources of 64 MB and more through two pinned buffers filled by several host threads; the
+    valueMap follows the intensities through the same buffers.  Zeros must arrive as zeros: the device-side
+    np.count_nonzero (vrg_count_nonzero, the reference's second printed line, VRG:95) sees every corrupted byte."""
+    from arterynetwork_b200.engine import VRGEngine
+    shape = (44, 512, 512)  # 92 MB of float64
+    rng = np.random.default_rng(3)
+    data = np.zeros(shape)
+    idx = rng.integers(0, data.size, 50000)
+    data.reshape(-1)[idx] = rng.integers(1, 200, idx.size) / 256.0
+    data[20:24, 250:262, 100:400] = 1.0
+    vm = np.full(shape, 3, dtype=np.uint8)
+    vm[21:23, 254:258, 200:204] = 0
+    with VRGEngine(shape, max_segment_size=10 ** 12, intensity="f64_band") as eng:
+        for _ in range(2):  # the second upload reuses the staging buffers of the first
+            eng.upload(data, vm)
+            assert eng.count_nonzero() == int(np.count_nonzero(data))
+            assert np.array_equal(eng.scan_levels(), np.unique(data))  # a corrupted intensity would be a level of its own
+        eng.init()
+        res = eng.run()
+        lab = eng.labels()
+        assert (lab <= 1).sum() == res["n_in"] and res["n_in"] >= 4 * 12 * 300
