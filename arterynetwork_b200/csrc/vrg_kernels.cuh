@@ -680,13 +680,15 @@ __device__ __forceinline__ void sweep_dense_body(const Params &p) {
 
 template <bool LATTICE, bool WIDE = false>
 __global__ void __launch_bounds__(DENSE_WARPS * 32) k_sweep_dense(Params p) { sweep_dense_body<LATTICE, WIDE>(p); }
-// The same sweep held to 104 registers per thread, for the pipelined run (vrg_tail.cuh): its statistics and table kernels have
-// to find room on the SMs this kernel's blocks occupy -- 14 warps x 112 registers leave 15360 of the 65536, not enough for a
-// 256-thread block of k_async_table (63 registers), which then ran BEHIND the sweep instead of beside it (8 GPUs, C3: 19.7 ms
-// per run; 17.5 ms with 128-thread blocks, which fit but take twice as long; 15.8 ms with this variant and 256 threads,
-// although the sweep itself is a few per cent slower: profiles/r2ak_*).
+// The same sweep held to 96 registers per thread, for the pipelined run (vrg_tail.cuh): its statistics and table kernels have
+// to find room on the SMs this kernel's blocks occupy.  Registers are handed out 512 per warp, so 100..112 per thread all cost
+// 14 warps x 3584 = 50176 of the 65536 and leave 15360: not enough for a 256-thread block of k_async_table (63 -> 64
+// registers, 16384), which then runs BEHIND the sweep instead of beside it.  8 GPUs, C3, per run: 19.7 ms with 112 registers
+// and 128-thread side kernels (they fit, but take twice as long and the sweep's blocks still crowd them), 17.5 ms with 112 /
+// 256 (a cap of 104 allocates the same 112: 17.6 ms), 15.8 ms with 96 / 256 although the sweep itself is 5 % slower
+// (profiles/r2ak_*, r2z_scale_8.json).
 template <bool LATTICE, bool WIDE = false>
-__global__ void __maxnreg__(104) k_sweep_dense_slim(Params p) { sweep_dense_body<LATTICE, WIDE>(p); }
+__global__ void __maxnreg__(96) k_sweep_dense_slim(Params p) { sweep_dense_body<LATTICE, WIDE>(p); }
 
 // Fallback of the dense sweep for odd X (row segments not 16-byte aligned): plain coalesced 8-byte loads.
 template <bool LATTICE>
