@@ -51,3 +51,19 @@ def test_strict_equals_order_free_on_a_clean_input():
     s = vrg_strict_oracle(g["data"], g["value_map_in"], H=g["H"], max_segment_size=g["max_segment_size"])
     assert s["iterations"] == g["iterations"] and np.array_equal(s["value_map"], g["labels"])
     assert np.array_equal(s["trace"], g["trace"])
+
+
+@pytest.mark.parametrize("name", ["edge", "forest40", "tube_two_seeds", "int_levels", "h1"])
+def test_list_order_and_order_free_agree_where_the_reference_is_order_free(name):
+    """On the clean fixtures (recorded from the unmodified reference, Q2 = 0 and no decision changed by Q3) the two
+    restatements are the same function: labels, trace, iteration count -- the list-order oracle adds only the row order."""
+    from golden_util import load_golden
+    g = load_golden(name)
+    s = vrg_strict_oracle(g["data"], g["value_map_in"], H=g["H"], max_segment_size=g["max_segment_size"])
+    o = vrg_oracle(g["data"], g["value_map_in"], H=g["H"], max_segment_size=g["max_segment_size"])
+    assert s["iterations"] == o["iterations"] == g["iterations"]
+    assert np.array_equal(s["trace"], o["trace"]) and np.array_equal(s["trace"], g["trace"])
+    assert np.array_equal(s["value_map"], o["labels"]) and np.array_equal(s["value_map"], g["labels"])
+    rows = s["segmented"]
+    assert len(rows) == int(o["seg"].sum()) and o["seg"][tuple(rows.T)].all()
+    assert len(np.unique(np.ravel_multi_index(tuple(rows.T), o["seg"].shape))) == len(rows)
